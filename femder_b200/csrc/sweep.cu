@@ -1,0 +1,746 @@
+// K5 fused multi-frequency SpMV, K6 COCG vector kernels, K7 receiver gather, and the sweep driver.
+//
+// Replaces the hot loop of FEM3D.compute() (femder/FEM_3D.py:1304-1319): per frequency
+//     G = H + 1j*w*sum_g mu_g A_g - w^2 Q ;  b = -1j*w*q ;  p = solve(G, b)
+// The reference factorises G from scratch with PARDISO per frequency.  Here a batch of F frequencies is
+// solved together by preconditioned COCG (conjugate orthogonal CG for complex symmetric G); the batch
+// shares one pass over the column indices and the (H, Q) values per SpMV.
+//
+// HBM layout
+//   hq[nnz]        double2 (H, Q) in CSR order, indices[nnz] int32, indptr[N+1] int32
+//   overlay        ov_ptr[N+1], ov_cg[n_ov] (col, group), ov_val[n_ov]  boundary admittance entries
+//   vectors        [N][F] complex128 (double2), frequency fastest: a gather of x[col][0..F) is one
+//                  contiguous 16*F-byte segment (a full 128-byte line at F = 8)
+#include "common.cuh"
+#include "../../include/femder_b200.h"
+
+namespace fdb {
+
+constexpr int kMaxF = 16;
+constexpr int kBlock = 256;
+
+struct __align__(16) Scalars {
+    double2 rho[kMaxF];    // r^T z (unconjugated)
+    double2 pq[kMaxF];     // p^T G p
+    double2 beta[kMaxF];
+    double rr[kMaxF];      // ||r||^2
+    double bb[kMaxF];      // ||b||^2
+    double w2[kMaxF];      // omega^2
+    double2 rhs_scale[kMaxF];  // -1j*omega
+    int active[kMaxF];
+    int iters[kMaxF];
+    double tol2;
+    unsigned int ticket[4];
+};
+
+struct SweepWork {
+    int F = 0;
+    int64_t N = 0;
+    int n_groups = 0;
+    int grid = 0;
+    DevBuf<double2> x, r, p, q, dinv;  // [N][F]
+    DevBuf<double2> coef;              // [n_groups][F]  1j*omega*mu
+    DevBuf<double2> partial;           // [grid][F][2]
+    DevBuf<Scalars> sc;
+    DevBuf<double2> stage;             // [F][N] pN export staging
+    DevBuf<double2> rcv_out;           // [F][n_rcv]
+    cudaGraphExec_t graph = nullptr;
+    int graph_iters = 0;
+    int graph_F = 0;
+    bool graph_overlay = false;
+};
+
+void free_sweep_work(SweepWork* w) {
+    if (!w) return;
+    if (w->graph) cudaGraphExecDestroy(w->graph);
+    delete w;
+}
+
+void invalidate_graph(fdb_system* sys) {
+    SweepWork* w = sys->work;
+    if (w && w->graph) {
+        cudaGraphExecDestroy(w->graph);
+        w->graph = nullptr;
+    }
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
+    const double d = b.x * b.x + b.y * b.y;
+    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+// Sum `v` over the lanes that share lane % F, result valid in lanes 0..F-1.
+template <int F>
+__device__ __forceinline__ double warp_sum_by_f(double v) {
+#pragma unroll
+    for (int o = 16; o >= F; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block partials -> partial[blockIdx.x][f][slot]; the last block to arrive adds the partials of all blocks
+// in a fixed order (deterministic) and calls `fin(f, total_slot0, total_slot1)` from one thread per f.
+template <int F, int NV, typename Fin>
+__device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
+                                                      unsigned int* __restrict__ ticket, Fin fin) {
+    __shared__ double s_red[kBlock / 32][kMaxF][NV];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = warp_sum_by_f<F>(v[i]);
+    if (lane < F) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s_red[warp][lane][i] = w[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < F) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0;
+            for (int k = 0; k < kBlock / 32; ++k) s += s_red[k][threadIdx.x][i];
+            partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // kBlock threads: group g = tid / F ... each f gets kBlock/F threads striding over the blocks
+    constexpr int TPF = kBlock / F;
+    const int f = threadIdx.x % F, j = threadIdx.x / F;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0;
+    for (int b = j; b < (int)gridDim.x; b += TPF) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
+    }
+    __shared__ double s_fin[kBlock][NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_fin[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < F) {
+        double tot[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) tot[i] = 0;
+        for (int k = 0; k < TPF; ++k) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) tot[i] += s_fin[k * F + threadIdx.x][i];
+        }
+        fin(threadIdx.x, tot);
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: y[row][f] = sum_k (H_k - w2_f Q_k) x[col_k][f] + sum_ov (coef[g][f] * A_ov) x[col_ov][f]
+// lanes: (row in warp, f); F lanes share one row's matrix entries (broadcast loads)
+// DOT: also accumulate x[row]^T y[row] (unconjugated) -> sc.pq
+// ------------------------------------------------------------------------------------------------
+template <int F, bool DOT, bool OVERLAY>
+__global__ void __launch_bounds__(kBlock) k_spmv(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                  const double2* __restrict__ hq, const int32_t* __restrict__ ov_ptr,
+                                                  const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
+                                                  const double2* __restrict__ coef, const double2* __restrict__ x,
+                                                  double2* __restrict__ y, int64_t n_rows, Scalars* __restrict__ sc,
+                                                  double* __restrict__ partial) {
+    constexpr int RPB = kBlock / F;  // rows per block pass
+    const int f = threadIdx.x % F;
+    const int rl = threadIdx.x / F;
+    const double w2 = sc->w2[f];
+    double dot[2] = {0.0, 0.0};
+    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < n_rows; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + rl;
+        if (row < n_rows) {
+            double2 acc = make_double2(0.0, 0.0);
+            const int kb = indptr[row], ke = indptr[row + 1];
+            for (int k = kb; k < ke; ++k) {
+                const int c = __ldg(&indices[k]);
+                const double2 m = __ldg(&hq[k]);
+                const double g = m.x - w2 * m.y;
+                const double2 xv = x[(int64_t)c * F + f];
+                acc.x += g * xv.x;
+                acc.y += g * xv.y;
+            }
+            if (OVERLAY) {
+                const int ob = ov_ptr[row], oe = ov_ptr[row + 1];
+                for (int k = ob; k < oe; ++k) {
+                    const int2 cg = ov_cg[k];
+                    const double a = ov_val[k];
+                    const double2 cf = coef[cg.y * F + f];
+                    const double2 xv = x[(int64_t)cg.x * F + f];
+                    const double2 t = cmul(make_double2(cf.x * a, cf.y * a), xv);
+                    acc.x += t.x;
+                    acc.y += t.y;
+                }
+            }
+            y[row * F + f] = acc;
+            if (DOT) {
+                const double2 xv = x[row * F + f];
+                const double2 d = cmul(xv, acc);
+                dot[0] += d.x;
+                dot[1] += d.y;
+            }
+        }
+    }
+    if (DOT) {
+        block_reduce_finalize<F, 2>(dot, partial, &sc->ticket[0], [&](int ff, const double* tot) {
+            sc->pq[ff] = make_double2(tot[0], tot[1]);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
+// finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
+// ------------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, double2* __restrict__ r,
+                                                    const double2* __restrict__ p, const double2* __restrict__ q,
+                                                    const double2* __restrict__ dinv, int64_t n_elems,
+                                                    Scalars* __restrict__ sc, double* __restrict__ partial) {
+    const int f = threadIdx.x % F;
+    const bool act = sc->active[f] != 0;
+    double2 alpha = make_double2(0.0, 0.0);
+    if (act) {
+        const double2 pq = sc->pq[f];
+        if (pq.x != 0.0 || pq.y != 0.0) alpha = cdiv(sc->rho[f], pq);
+    }
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        double2 rv = r[i];
+        if (act) {
+            const double2 pv = p[i], qv = q[i];
+            double2 xv = x[i];
+            const double2 ap = cmul(alpha, pv), aq = cmul(alpha, qv);
+            xv.x += ap.x; xv.y += ap.y;
+            rv.x -= aq.x; rv.y -= aq.y;
+            x[i] = xv;
+            r[i] = rv;
+        }
+        const double2 z = cmul(dinv[i], rv);
+        const double2 rz = cmul(rv, z);
+        v[0] += rz.x;
+        v[1] += rz.y;
+        v[2] += rv.x * rv.x + rv.y * rv.y;
+    }
+    block_reduce_finalize<F, 3>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
+        if (sc->active[ff]) {
+            const double2 rho_old = sc->rho[ff];
+            const double2 rho_new = make_double2(tot[0], tot[1]);
+            double2 beta = make_double2(0.0, 0.0);
+            if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
+            sc->rho[ff] = rho_new;
+            sc->rr[ff] = tot[2];
+            sc->iters[ff] += 1;
+            const bool conv = !(tot[2] > sc->tol2 * sc->bb[ff]);  // also stops on NaN
+            if (conv) { sc->active[ff] = 0; beta = make_double2(0.0, 0.0); }
+            sc->beta[ff] = beta;
+        } else {
+            sc->beta[ff] = make_double2(0.0, 0.0);
+        }
+    });
+}
+
+// K6b: p = dinv*r + beta p
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pupdate(double2* __restrict__ p, const double2* __restrict__ r,
+                                                     const double2* __restrict__ dinv, int64_t n_elems,
+                                                     const Scalars* __restrict__ sc) {
+    const int f = threadIdx.x % F;
+    const double2 beta = sc->beta[f];
+    if (!sc->active[f]) return;  // frozen frequency: p is not used while alpha = 0
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        const double2 z = cmul(dinv[i], r[i]);
+        const double2 bp = cmul(beta, p[i]);
+        p[i] = make_double2(z.x + bp.x, z.y + bp.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// set-up kernels for one batch
+// ------------------------------------------------------------------------------------------------
+// dinv[row][f] = 1 / (H_rr - w2_f Q_rr + sum_ov,col==row coef[g][f] A)
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ diag_hq, const int32_t* __restrict__ ov_ptr,
+                                                    const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
+                                                    const double2* __restrict__ coef, bool overlay, int64_t n_rows,
+                                                    const Scalars* __restrict__ sc, double2* __restrict__ dinv) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t row = i / F;
+    const int f = (int)(i % F);
+    if (row >= n_rows) return;
+    const double2 d = diag_hq[row];
+    double2 g = make_double2(d.x - sc->w2[f] * d.y, 0.0);
+    if (overlay) {
+        for (int k = ov_ptr[row]; k < ov_ptr[row + 1]; ++k) {
+            const int2 cg = ov_cg[k];
+            if (cg.x == row) {
+                const double2 cf = coef[cg.y * F + f];
+                const double a = ov_val[k];
+                g.x += cf.x * a;
+                g.y += cf.y * a;
+            }
+        }
+    }
+    const bool zero = (g.x == 0.0 && g.y == 0.0);
+    dinv[i] = zero ? make_double2(1.0, 0.0) : cdiv(make_double2(1.0, 0.0), g);
+}
+
+// r[node][f] = rhs_scale[f] * q_s   (one thread per (source, f); sources are unique nodes)
+template <int F>
+__global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, int n_src,
+                          const Scalars* __restrict__ sc, double2* __restrict__ r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_src * F) return;
+    const int s = i / F, f = i % F;
+    r[(int64_t)src_nodes[s] * F + f] = cmul(sc->rhs_scale[f], src_q[s]);
+}
+
+// warm start: x[row][f] = x[row][F-1] for every f
+template <int F>
+__global__ void k_broadcast_last(double2* __restrict__ x, int64_t n_rows, int src_slot) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n_rows * F) return;
+    const int64_t row = i / F;
+    const int f = (int)(i % F);
+    const double2 v = x[row * F + src_slot];
+    if (f != src_slot) x[i] = v;
+}
+
+// r = r - q    (r holds b on entry; q = G x0)
+__global__ void k_sub(double2* __restrict__ r, const double2* __restrict__ q, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        double2 a = r[i];
+        const double2 b = q[i];
+        a.x -= b.x; a.y -= b.y;
+        r[i] = a;
+    }
+}
+
+// p = dinv r ; rho = r^T p ; rr = ||r||^2 ; activate every frequency whose residual is above tolerance
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_start(double2* __restrict__ p, const double2* __restrict__ r,
+                                                   const double2* __restrict__ dinv, int64_t n_elems, int n_live,
+                                                   Scalars* __restrict__ sc, double* __restrict__ partial) {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        const double2 rv = r[i];
+        const double2 z = cmul(dinv[i], rv);
+        p[i] = z;
+        const double2 rz = cmul(rv, z);
+        v[0] += rz.x;
+        v[1] += rz.y;
+        v[2] += rv.x * rv.x + rv.y * rv.y;
+    }
+    block_reduce_finalize<F, 3>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
+        sc->rho[ff] = make_double2(tot[0], tot[1]);
+        sc->rr[ff] = tot[2];
+        sc->beta[ff] = make_double2(0.0, 0.0);
+        sc->iters[ff] = 0;
+        sc->active[ff] = (ff < n_live && tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
+    });
+}
+
+// true residual norm: rr = ||b - q||^2 with b = r_buf (rebuilt rhs), q = G x
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_resnorm(const double2* __restrict__ b, const double2* __restrict__ q,
+                                                     int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    double v[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        const double2 bv = b[i], qv = q[i];
+        const double dx = bv.x - qv.x, dy = bv.y - qv.y;
+        v[0] += dx * dx + dy * dy;
+    }
+    block_reduce_finalize<F, 1>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rr[ff] = tot[0]; });
+}
+
+// K7: pR[f][i] = sum_j w[i][j] x[node[i][j]][f]
+template <int F>
+__global__ void k_gather_rcv(const double2* __restrict__ x, const int32_t* __restrict__ nodes, const double* __restrict__ w,
+                             int n_rcv, double2* __restrict__ out /* [F][n_rcv] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rcv * F) return;
+    const int rc = i / F, f = i % F;
+    double2 acc = make_double2(0.0, 0.0);
+    bool first = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double wt = w[rc * 4 + j];
+        if (wt == 0.0) continue;
+        const double2 v = x[(int64_t)nodes[rc * 4 + j] * F + f];
+        if (first && wt == 1.0) { acc = v; first = false; continue; }  // on-node receiver: exact copy
+        acc.x += wt * v.x;
+        acc.y += wt * v.y;
+        first = false;
+    }
+    out[(int64_t)f * n_rcv + rc] = acc;
+}
+
+// pN export: stage[f][row] = x[row][f]
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_export(const double2* __restrict__ x, int64_t n_rows, double2* __restrict__ stage) {
+    __shared__ double2 tile[kBlock];
+    constexpr int RPB = kBlock / F;
+    const int64_t row0 = (int64_t)blockIdx.x * RPB;
+    const int64_t i = row0 * F + threadIdx.x;
+    if (i < n_rows * F) tile[threadIdx.x] = x[i];
+    __syncthreads();
+    const int f = threadIdx.x / RPB, rl = threadIdx.x % RPB;
+    if (row0 + rl < n_rows) stage[(int64_t)f * n_rows + row0 + rl] = tile[rl * F + f];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+template <int F>
+struct Launch {
+    static void spmv(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+        const int64_t N = w->N;
+        const int rpb = kBlock / F;
+        int grid = (int)std::min<int64_t>((N + rpb - 1) / rpb, (int64_t)w->grid);
+        auto args = [&](auto kern) {
+            kern<<<grid, kBlock, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p, sys->ov_ptr.p, sys->ov_cg.p,
+                                                  sys->ov_val.p, w->coef.p, x, y, N, w->sc.p, (double*)w->partial.p);
+        };
+        if (dot) {
+            if (overlay) args(k_spmv<F, true, true>); else args(k_spmv<F, true, false>);
+        } else {
+            if (overlay) args(k_spmv<F, false, true>); else args(k_spmv<F, false, false>);
+        }
+    }
+    static int egrid(SweepWork* w) {
+        return (int)std::min<int64_t>((w->N * F + kBlock - 1) / kBlock, (int64_t)w->grid);
+    }
+    static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
+        const int64_t ne = w->N * F;
+        spmv(sys, w, w->p.p, w->q.p, true, overlay);
+        k_update<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, ne, w->sc.p,
+                                                          (double*)w->partial.p);
+        k_pupdate<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, ne, w->sc.p);
+    }
+    static void jacobi(fdb_system* sys, SweepWork* w, bool overlay) {
+        k_jacobi<F><<<grid_for(w->N * F, kBlock), kBlock, 0, sys->stream>>>(sys->diag_hq.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                                                                         w->coef.p, overlay, w->N, w->sc.p, w->dinv.p);
+    }
+    static void set_rhs(fdb_system* sys, SweepWork* w, const int32_t* nodes, const double2* q, int n_src, double2* dst) {
+        FDB_CUDA(cudaMemsetAsync(dst, 0, (size_t)w->N * F * sizeof(double2), sys->stream));
+        if (n_src) k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, w->sc.p, dst);
+    }
+    static void broadcast_last(fdb_system* sys, SweepWork* w, int slot) {
+        k_broadcast_last<F><<<grid_for(w->N * F, kBlock), kBlock, 0, sys->stream>>>(w->x.p, w->N, slot);
+    }
+    static void start(fdb_system* sys, SweepWork* w, int n_live) {
+        k_start<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, w->N * F, n_live, w->sc.p, (double*)w->partial.p);
+    }
+    static void resnorm(fdb_system* sys, SweepWork* w, const double2* b, const double2* q) {
+        k_resnorm<F><<<egrid(w), kBlock, 0, sys->stream>>>(b, q, w->N * F, w->sc.p, (double*)w->partial.p);
+    }
+    static void gather(fdb_system* sys, SweepWork* w, const int32_t* nodes, const double* wts, int n_rcv) {
+        k_gather_rcv<F><<<grid_for((int64_t)n_rcv * F, 128), 128, 0, sys->stream>>>(w->x.p, nodes, wts, n_rcv, w->rcv_out.p);
+    }
+    static void export_pn(fdb_system* sys, SweepWork* w) {
+        const int rpb = kBlock / F;
+        k_export<F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>(w->x.p, w->N, w->stage.p);
+    }
+};
+
+#define FDB_DISPATCH_F(F, CALL)                                   \
+    switch (F) {                                                  \
+        case 1: Launch<1>::CALL; break;                           \
+        case 2: Launch<2>::CALL; break;                           \
+        case 4: Launch<4>::CALL; break;                           \
+        case 8: Launch<8>::CALL; break;                           \
+        case 16: Launch<16>::CALL; break;                         \
+        default: throw Error("femder_b200: batch must be 1, 2, 4, 8 or 16"); \
+    }
+
+static SweepWork* get_work(fdb_system* sys, int F) {
+    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16, "batch must be 1, 2, 4, 8 or 16");
+    FDB_REQUIRE(sys->have_pattern && sys->have_hq, "pattern and H/Q values must be set before the sweep");
+    SweepWork* w = sys->work;
+    if (w && (w->F != F || w->N != sys->n_nodes || w->n_groups != sys->n_groups)) {
+        free_sweep_work(w);
+        w = sys->work = nullptr;
+    }
+    if (!w) {
+        w = new SweepWork();
+        sys->work = w;
+        w->F = F;
+        w->N = sys->n_nodes;
+        w->n_groups = sys->n_groups;
+        w->grid = sys->num_sms * 8;
+        const size_t n = (size_t)w->N * F;
+        w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n);
+        w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
+        w->partial.alloc((size_t)w->grid * F * 2);  // 3 doubles per (block, f) fit in 2 double2
+        w->sc.alloc(1);
+        w->sc.zero(sys->stream);
+    }
+    // dummies so kernels always receive valid pointers
+    if (!sys->ov_ptr.p) {
+        sys->ov_ptr.alloc(sys->n_nodes + 1);
+        sys->ov_ptr.zero(sys->stream);
+        sys->ov_cg.alloc(1);
+        sys->ov_val.alloc(1);
+        sys->n_ov = 0;
+    }
+    return w;
+}
+
+static void load_batch_scalars(fdb_system* sys, SweepWork* w, int F, int n_live, const double* omega, const double* mu_batch /* [n_groups][F] complex */,
+                               double tol, double src_norm2) {
+    Scalars h;
+    memset(&h, 0, sizeof(h));
+    std::vector<double2> coef((size_t)std::max(1, w->n_groups) * F, make_double2(0.0, 0.0));
+    for (int f = 0; f < F; ++f) {
+        const double om = omega[std::min(f, n_live - 1)];
+        h.w2[f] = om * om;
+        h.rhs_scale[f] = make_double2(0.0, -om);
+        h.bb[f] = om * om * src_norm2;
+        for (int g = 0; g < w->n_groups; ++g) {
+            const double mr = mu_batch[((size_t)g * F + f) * 2], mi = mu_batch[((size_t)g * F + f) * 2 + 1];
+            coef[(size_t)g * F + f] = make_double2(-om * mi, om * mr);  // 1j*om*(mr + 1j*mi)
+        }
+    }
+    h.tol2 = tol * tol;
+    FDB_CUDA(cudaMemcpyAsync(w->sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, sys->stream));
+    FDB_CUDA(cudaMemcpyAsync(w->coef.p, coef.data(), coef.size() * sizeof(double2), cudaMemcpyHostToDevice, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));  // host buffers go out of scope
+}
+
+static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool overlay) {
+    if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay) return;
+    if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    FDB_CUDA(cudaStreamBeginCapture(sys->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        for (int i = 0; i < iters; ++i) { FDB_DISPATCH_F(F, iteration(sys, w, overlay)); }
+    } catch (...) {
+        cudaStreamEndCapture(sys->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    FDB_CUDA(cudaStreamEndCapture(sys->stream, &g));
+    cudaError_t e = cudaGraphInstantiate(&w->graph, g, 0);
+    cudaGraphDestroy(g);
+    FDB_CUDA(e);
+    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay;
+}
+
+void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res) {
+    FDB_REQUIRE(prm && res, "null argument");
+    FDB_REQUIRE(prm->n_freq >= 0 && prm->n_src >= 0 && prm->n_rcv >= 0, "negative count");
+    FDB_REQUIRE(prm->tol > 0 && prm->max_iter > 0, "tol and max_iter must be positive");
+    const int F = prm->batch;
+    SweepWork* w = get_work(sys, F);
+    const int64_t N = w->N;
+    const int ng = sys->n_groups;
+    FDB_REQUIRE(ng == 0 || prm->mu != nullptr, "mu is required when the system has boundary groups");
+    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0;
+    const int check_every = std::max(1, prm->check_every);
+    cudaStream_t s = sys->stream;
+
+    // inputs to the host (they may be device pointers)
+    std::vector<double> omega(prm->n_freq), mu((size_t)ng * prm->n_freq * 2);
+    if (prm->n_freq) FDB_CUDA(cudaMemcpy(omega.data(), prm->omega, omega.size() * sizeof(double), cudaMemcpyDefault));
+    if (!mu.empty()) FDB_CUDA(cudaMemcpy(mu.data(), prm->mu, mu.size() * sizeof(double), cudaMemcpyDefault));
+    std::vector<int32_t> src_nodes(prm->n_src);
+    std::vector<double2> src_q(prm->n_src);
+    if (prm->n_src) {
+        FDB_CUDA(cudaMemcpy(src_nodes.data(), prm->src_nodes, prm->n_src * sizeof(int32_t), cudaMemcpyDefault));
+        FDB_CUDA(cudaMemcpy(src_q.data(), prm->src_q, prm->n_src * sizeof(double2), cudaMemcpyDefault));
+    }
+    // q[node] = S.q (assignment: a later source on the same node overwrites, FEM_3D.py:1298-1300)
+    std::vector<int32_t> u_nodes;
+    std::vector<double2> u_q;
+    for (int64_t i = 0; i < prm->n_src; ++i) {
+        FDB_REQUIRE(src_nodes[i] >= 0 && src_nodes[i] < N, "source node out of range");
+        bool found = false;
+        for (size_t j = 0; j < u_nodes.size(); ++j)
+            if (u_nodes[j] == src_nodes[i]) { u_q[j] = src_q[i]; found = true; }
+        if (!found) { u_nodes.push_back(src_nodes[i]); u_q.push_back(src_q[i]); }
+    }
+    double src_norm2 = 0;
+    for (auto& v : u_q) src_norm2 += v.x * v.x + v.y * v.y;
+    const int n_src = (int)u_nodes.size();
+    DevBuf<int32_t> d_src_nodes; DevBuf<double2> d_src_q;
+    d_src_nodes.alloc(std::max(1, n_src)); d_src_q.alloc(std::max(1, n_src));
+    if (n_src) {
+        FDB_CUDA(cudaMemcpyAsync(d_src_nodes.p, u_nodes.data(), n_src * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        FDB_CUDA(cudaMemcpyAsync(d_src_q.p, u_q.data(), n_src * sizeof(double2), cudaMemcpyHostToDevice, s));
+    }
+    const int n_rcv = (int)prm->n_rcv;
+    DevBuf<int32_t> d_rcv_nodes; DevBuf<double> d_rcv_w;
+    if (n_rcv) {
+        FDB_REQUIRE(prm->rcv_nodes && prm->rcv_w, "receiver arrays missing");
+        std::vector<int32_t> rn((size_t)n_rcv * 4);
+        FDB_CUDA(cudaMemcpy(rn.data(), prm->rcv_nodes, rn.size() * sizeof(int32_t), cudaMemcpyDefault));
+        for (auto v : rn) FDB_REQUIRE(v >= 0 && v < N, "receiver node out of range");
+        d_rcv_nodes.alloc(rn.size()); d_rcv_w.alloc(rn.size());
+        FDB_CUDA(cudaMemcpyAsync(d_rcv_nodes.p, rn.data(), rn.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        FDB_CUDA(cudaMemcpyAsync(d_rcv_w.p, prm->rcv_w, rn.size() * sizeof(double), cudaMemcpyDefault, s));
+        w->rcv_out.alloc((size_t)F * n_rcv);
+    }
+    if (res->pN) w->stage.alloc((size_t)F * N);
+    FDB_CUDA(cudaStreamSynchronize(s));
+
+    cudaEvent_t ev0, ev1;
+    FDB_CUDA(cudaEventCreate(&ev0));
+    FDB_CUDA(cudaEventCreate(&ev1));
+    FDB_CUDA(cudaEventRecord(ev0, s));
+    int64_t n_spmv = 0, n_kernels = 0;
+    int n_unconv = 0;
+    bool have_prev = false;
+    std::vector<double> mu_batch((size_t)std::max(1, ng) * F * 2);
+    std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
+
+    for (int64_t f0 = 0; f0 < prm->n_freq; f0 += F) {
+        const int n_live = (int)std::min<int64_t>(F, prm->n_freq - f0);
+        for (int g = 0; g < ng; ++g)
+            for (int f = 0; f < F; ++f) {
+                const int64_t src = f0 + std::min(f, n_live - 1);
+                mu_batch[((size_t)g * F + f) * 2] = mu[((size_t)g * prm->n_freq + src) * 2];
+                mu_batch[((size_t)g * F + f) * 2 + 1] = mu[((size_t)g * prm->n_freq + src) * 2 + 1];
+            }
+        load_batch_scalars(sys, w, F, n_live, omega.data() + f0, mu_batch.data(), prm->tol, src_norm2);
+        FDB_DISPATCH_F(F, jacobi(sys, w, has_overlay));
+        FDB_DISPATCH_F(F, set_rhs(sys, w, d_src_nodes.p, d_src_q.p, n_src, w->r.p));
+        n_kernels += 2;
+        if (prm->warm_start && have_prev) {
+            FDB_DISPATCH_F(F, broadcast_last(sys, w, F - 1));
+            FDB_DISPATCH_F(F, spmv(sys, w, w->x.p, w->q.p, false, has_overlay));
+            k_sub<<<std::min<int64_t>(grid_for(N * F, kBlock), w->grid), kBlock, 0, s>>>(w->r.p, w->q.p, N * F);
+            n_spmv += 1; n_kernels += 3;
+        } else {
+            w->x.zero(s);
+        }
+        FDB_DISPATCH_F(F, start(sys, w, n_live));
+        n_kernels += 1;
+        FDB_CUDA(cudaGetLastError());
+
+        ensure_graph(sys, w, F, check_every, has_overlay);
+        Scalars h;
+        int it = 0;
+        while (true) {
+            FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+            FDB_CUDA(cudaStreamSynchronize(s));
+            bool any = false;
+            for (int f = 0; f < n_live; ++f) any = any || h.active[f];
+            if (!any || it >= prm->max_iter) break;
+            FDB_CUDA(cudaGraphLaunch(w->graph, s));
+            it += check_every;
+            n_spmv += check_every;
+            n_kernels += 3 * (int64_t)check_every;
+        }
+        // true residual of what is returned: ||b - G x|| / ||b||
+        FDB_DISPATCH_F(F, spmv(sys, w, w->x.p, w->q.p, false, has_overlay));
+        FDB_DISPATCH_F(F, set_rhs(sys, w, d_src_nodes.p, d_src_q.p, n_src, w->p.p));
+        FDB_DISPATCH_F(F, resnorm(sys, w, w->p.p, w->q.p));
+        n_spmv += 1; n_kernels += 3;
+        Scalars hf;
+        FDB_CUDA(cudaMemcpyAsync(&hf, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+        if (n_rcv) {
+            FDB_DISPATCH_F(F, gather(sys, w, d_rcv_nodes.p, d_rcv_w.p, n_rcv));
+            n_kernels += 1;
+            FDB_CUDA(cudaMemcpyAsync(rcv_host.data(), w->rcv_out.p, (size_t)F * n_rcv * sizeof(double2), cudaMemcpyDeviceToHost, s));
+        }
+        if (res->pN) {
+            FDB_DISPATCH_F(F, export_pn(sys, w));
+            n_kernels += 1;
+            FDB_CUDA(cudaMemcpyAsync(res->pN + (size_t)f0 * N * 2, w->stage.p, (size_t)n_live * N * sizeof(double2), cudaMemcpyDefault, s));
+        }
+        FDB_CUDA(cudaStreamSynchronize(s));
+        for (int f = 0; f < n_live; ++f) {
+            const double rel = (hf.bb[f] > 0) ? sqrt(hf.rr[f] / hf.bb[f]) : 0.0;
+            if (res->iters) res->iters[f0 + f] = h.iters[f];
+            if (res->relres) res->relres[f0 + f] = rel;
+            if (h.active[f] || !(rel <= 10 * prm->tol)) ++n_unconv;
+        }
+        if (n_rcv && res->pR)
+            for (int f = 0; f < n_live; ++f)
+                FDB_CUDA(cudaMemcpy(res->pR + ((size_t)(f0 + f) * n_rcv) * 2, rcv_host.data() + (size_t)f * n_rcv,
+                                    (size_t)n_rcv * sizeof(double2), cudaMemcpyDefault));
+        have_prev = true;
+        if (n_live < F) have_prev = false;
+    }
+    FDB_CUDA(cudaEventRecord(ev1, s));
+    FDB_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    FDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    res->seconds = ms * 1e-3;
+    res->n_spmv = n_spmv;
+    res->n_kernels = n_kernels;
+    res->n_unconverged = n_unconv;
+}
+
+int64_t spmv_algorithmic_bytes(fdb_system* sys, int F) {
+    // indptr + (indices + H + Q) once + overlay + x read and y write per frequency
+    const int64_t N = sys->n_nodes, Z = sys->vol.nnz;
+    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    return 4 * (N + 1) + Z * 20 + (has_overlay ? 4 * (N + 1) + sys->n_ov * 16 : 0) + 32 * N * F;
+}
+
+void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, const double* x, double* y) {
+    SweepWork* w = get_work(sys, F);
+    const int ng = sys->n_groups;
+    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0;
+    std::vector<double> om(F), m((size_t)std::max(1, ng) * F * 2, 0.0);
+    FDB_CUDA(cudaMemcpy(om.data(), omega, F * sizeof(double), cudaMemcpyDefault));
+    if (ng) {
+        FDB_REQUIRE(mu != nullptr, "mu is required when the system has boundary groups");
+        FDB_CUDA(cudaMemcpy(m.data(), mu, (size_t)ng * F * 2 * sizeof(double), cudaMemcpyDefault));
+    }
+    load_batch_scalars(sys, w, F, F, om.data(), m.data(), 1.0, 0.0);
+    const size_t n = (size_t)w->N * F;
+    FDB_CUDA(cudaMemcpyAsync(w->p.p, x, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
+    FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, false, has_overlay));
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaMemcpyAsync(y, w->q.p, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
+}
+
+__global__ void k_fill_pattern(double2* __restrict__ v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = (double)(i % 1024) * (1.0 / 1024.0);
+        v[i] = make_double2(0.5 + t, 0.25 - t);
+    }
+}
+
+void run_spmv_bench(fdb_system* sys, int F, int reps, double* ms_per_launch, int64_t* bytes) {
+    SweepWork* w = get_work(sys, F);
+    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    std::vector<double> om(F), m((size_t)std::max(1, sys->n_groups) * F * 2, 0.0);
+    for (int f = 0; f < F; ++f) om[f] = 2.0 * 3.141592653589793 * (100.0 + f);
+    for (size_t i = 0; i < m.size(); i += 2) m[i] = 1e-4;
+    load_batch_scalars(sys, w, F, F, om.data(), m.data(), 1.0, 0.0);
+    const int64_t n = w->N * F;
+    k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->p.p, n);
+    for (int i = 0; i < 3; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
+    cudaEvent_t e0, e1;
+    FDB_CUDA(cudaEventCreate(&e0));
+    FDB_CUDA(cudaEventCreate(&e1));
+    FDB_CUDA(cudaEventRecord(e0, sys->stream));
+    for (int i = 0; i < reps; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
+    FDB_CUDA(cudaEventRecord(e1, sys->stream));
+    FDB_CUDA(cudaEventSynchronize(e1));
+    FDB_CUDA(cudaGetLastError());
+    float ms = 0;
+    FDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F);
+}
+
+}  // namespace fdb

@@ -1,0 +1,260 @@
+"""``FEM3D`` - drop-in for the hot path of the reference's ``femder.FEM_3D.FEM3D`` (``FEM_3D.py:1136-1432``,
+``2042-2090``): same constructor, same ``compute()`` / ``evaluate()`` calls, same attributes left behind
+(``H, Q`` scipy csc, ``A`` list of csc ordered by sorted ``mu`` keys, ``q`` csc (N,1), ``areas``, ``pN``
+(n_freq, N) complex128, ``pR``, ``t``), with the assembly and the per-frequency solve running on the B200
+through ``libfemder_b200.so``.  There is no CPU fallback.
+
+Differences from the reference, all deliberate:
+* Tet4 ``H, Q`` are float64 csc; the reference rounds them to complex64 (``fem_numerical.py:307-312``).
+  ``compat_complex64=True`` reproduces that rounding (values rounded to float32 before the solve).
+* every frequency is solved by Jacobi-preconditioned COCG to ``tol`` instead of a PARDISO factorisation.
+* a surface group without a boundary condition raises ``KeyError`` as in the reference (``FEM_3D.py:1310``);
+  ``mu`` keys are paired with their own group instead of by position.
+* the velocity-BC and equivalent-fluid branches (``FEM_3D.py:1320-1347, 1367-1421``) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+from scipy.sparse import csc_matrix
+
+from . import sharding
+from .system import System
+
+
+def p2SPL(p):
+    """``FEM_3D.py:240-242``."""
+    SPL = 10 * np.log10(0.5 * p * np.conj(p) / (2e-5) ** 2)
+    return np.real(SPL)
+
+
+def closest_node(nodes, node):
+    """``FEM_3D.py:220-224``."""
+    nodes = np.asarray(nodes)
+    deltas = nodes - node
+    dist_2 = np.einsum("ij,ij->i", deltas, deltas)
+    return int(np.argmin(dist_2))
+
+
+def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
+    """(nodes[4], weights[4]) with p(coord) = sum_j w_j p[node_j], following ``evaluate`` (``FEM_3D.py:2077-2086``):
+    the closest node if it lies within ``interpolation_tolerance``, otherwise linear Tet4 interpolation in the
+    tetrahedron found the way ``coord_interpolation`` / ``which_tetra`` do (``FEM_3D.py:173-218``): candidates are
+    the elements containing the closest node, the last candidate passing the barycentric test wins, and when
+    none passes the reference's ``-1`` sentinel selects the last candidate."""
+    nos = np.asarray(nos, dtype=np.float64)
+    coord = np.asarray(coord, dtype=np.float64)
+    n = closest_node(nos, coord)
+    if np.linalg.norm(coord - nos[n]) < interpolation_tolerance:
+        return np.array([n, n, n, n], dtype=np.int32), np.array([1.0, 0.0, 0.0, 0.0])
+    ev = np.asarray(elem_vol)
+    cand = np.where((ev == n).any(axis=1))[0]
+    if len(cand) == 0:
+        raise ValueError("receiver's closest node belongs to no volume element")
+    corners = ev[cand][:, :4].astype(np.int64)
+    hit = -1
+    lam_hit = None
+    for t in range(len(cand)):
+        o = nos[corners[t, 0]]
+        M = np.stack([nos[corners[t, 1]] - o, nos[corners[t, 2]] - o, nos[corners[t, 3]] - o], axis=1)
+        try:
+            lam = np.linalg.solve(M, coord - o)
+        except np.linalg.LinAlgError:
+            continue
+        if np.all(lam >= 0) and np.all(lam <= 1) and lam.sum() <= 1:
+            hit, lam_hit = t, lam
+    if hit < 0:
+        hit = len(cand) - 1
+        o = nos[corners[hit, 0]]
+        M = np.stack([nos[corners[hit, 1]] - o, nos[corners[hit, 2]] - o, nos[corners[hit, 3]] - o], axis=1)
+        lam_hit = np.linalg.solve(M, coord - o)
+    w = np.array([1.0 - lam_hit.sum(), lam_hit[0], lam_hit[1], lam_hit[2]])
+    return corners[hit].astype(np.int32), w
+
+
+class FEM3D:
+    def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=50000, batch=8,
+                 check_every=32, warm_start=False, compat_complex64=False):
+        self.BC = BC
+        if BC is not None:
+            self.mu = BC.mu
+            self.v = BC.v
+        else:
+            self.mu = {}
+            self.v = {}
+        self.freq = AC.freq
+        self.w = AC.w
+        self.AC = AC
+        self.AP = AP
+        self.c0 = AP.c0
+        self.rho0 = AP.rho0
+        self.S = S
+        self.R = R
+        if Grid is not None:
+            self.grid = Grid
+            self.nos = Grid.nos
+            self.elem_surf = Grid.elem_surf
+            self.elem_vol = Grid.elem_vol
+            self.domain_index_surf = Grid.domain_index_surf
+            self.domain_index_vol = Grid.domain_index_vol
+            self.number_ID_faces = Grid.number_ID_faces
+            self.number_ID_vol = Grid.number_ID_vol
+            self.NumNosC = Grid.NumNosC
+            self.NumElemC = Grid.NumElemC
+            self.order = Grid.order
+            self.path_to_geo = getattr(Grid, "path_to_geo", None)
+            self.path_to_geo_unrolled = getattr(Grid, "path_to_geo_unrolled", None)
+        self.npg = 4
+        self.pR = None
+        self.pN = None
+        self.F_n = None
+        self.Vc = None
+        self.H = None
+        self.Q = None
+        self.A = None
+        self.rho = {}
+        self.c = {}
+        if BC is not None and (len(getattr(BC, "rhoc", {})) > 0 or len(getattr(BC, "cc", {})) > 0):
+            raise NotImplementedError("equivalent-fluid domains (BC.rhoc / BC.cc, FEM_3D.py:1367-1421) are outside "
+                                      "the B200 hot path")
+        # solver controls (no counterpart in the reference, which uses a direct solver)
+        self.tol = tol
+        self.max_iter = max_iter
+        self.batch = batch
+        self.check_every = check_every
+        self.warm_start = warm_start
+        self.compat_complex64 = compat_complex64
+        self.stats = None
+        self._device = device
+        self._stream = stream
+        self._sys = None
+        self._sys_key = None
+
+    # ---- reference properties (FEM_3D.py:1220-1238) ------------------------------------------
+    @property
+    def spl(self):
+        return p2SPL(self.pR)
+
+    @property
+    def avg_spl(self):
+        return np.mean(self.spl, axis=1)
+
+    @property
+    def spl_S(self):
+        return p2SPL(self.pR.T / (1j * self.w * self.rho0)).T
+
+    @property
+    def avg_spl_S(self):
+        return np.mean(self.spl_S, axis=1)
+
+    # ---- device system -----------------------------------------------------------------------
+    def _system(self):
+        rank, world, local_rank = sharding.dist_info()
+        dev = self._device if self._device is not None else (local_rank if world > 1 else 0)
+        if self._sys is None:
+            self._sys = System(dev, self._stream)
+        return self._sys
+
+    def _ensure_volume(self, sys):
+        key = (id(self.nos), id(self.elem_vol), self.NumNosC, self.NumElemC)
+        if self._sys_key != key:
+            sys.set_volume_mesh(self.nos, self.elem_vol)
+            self._sys_key = key
+            return True
+        return False
+
+    # ---- compute (FEM_3D.py:1242-1432) -------------------------------------------------------
+    def compute(self, timeit=True, printless=True, keep_pN=True):
+        """Assemble (once; ``H`` is the cache test as in the reference) and sweep every frequency.
+
+        ``keep_pN=False`` is an addition for meshes whose ``(n_freq, N)`` pressure array is not wanted on the
+        host (1M DOF x 481 frequencies = 7.7 GB): only the receiver pressures ``pR`` are returned."""
+        then = time.time()
+        if len(self.v) > 0:
+            raise NotImplementedError("velocity boundary conditions (FEM_3D.py:1320-1347) are outside the B200 hot path")
+        sys = self._system()
+        N = self.NumNosC
+        new_mesh = self._ensure_volume(sys)
+        q = np.zeros([N, 1], dtype=np.complex128)
+
+        group_ids = np.sort([*self.mu]) if self.BC is not None else np.array([], dtype=np.int64)
+        if self.BC is not None:
+            for bl in self.number_ID_faces:
+                if bl not in self.mu:
+                    raise KeyError(bl)  # FEM_3D.py:1310 indexes self.mu[bl] for every surface group
+        sys.set_surface_mesh(self.elem_surf, self.domain_index_surf, group_ids)
+        self.areas = sys.heron_areas().astype(np.complex128)  # compute_areas returns complex128 (FEM_3D.py:743)
+
+        if self.H is None or new_mesh:
+            sys.assemble_volume(self.rho0, self.c0)
+            if self.compat_complex64:
+                H, Q = sys.get_HQ_values()
+                sys.set_HQ_values(H.astype(np.float32).astype(np.float64), Q.astype(np.float32).astype(np.float64))
+            self.H, self.Q = sys.get_HQ()
+            if self.compat_complex64:
+                self.H = self.H.astype(np.complex64)
+                self.Q = self.Q.astype(np.complex64)
+        if self.BC is not None:
+            sys.assemble_surface()
+            self.A = sys.get_A(drop_zeros=(self.order == 2))
+
+        src_nodes, src_q = [], []
+        if self.S is not None:
+            for ii in range(len(self.S.coord)):
+                n = closest_node(self.nos, self.S.coord[ii, :])
+                q[n] = np.asarray(self.S.q[ii]).ravel()[0]
+                src_nodes.append(n)
+                src_q.append(complex(np.asarray(self.S.q[ii]).ravel()[0]))
+        self.q = csc_matrix(q)
+
+        nf = len(self.freq)
+        w = np.asarray(self.w, dtype=np.float64)
+        mu = np.zeros((len(group_ids), nf), dtype=np.complex128)
+        for i, g in enumerate(group_ids):
+            mu[i] = np.asarray(self.mu[g]).ravel()[:nf]
+
+        rcv_nodes = rcv_w = None
+        if self.R is not None and not keep_pN:
+            st = [receiver_stencil(self.nos, self.elem_vol, c) for c in np.atleast_2d(self.R.coord)]
+            rcv_nodes = np.array([s[0] for s in st], dtype=np.int32)
+            rcv_w = np.array([s[1] for s in st], dtype=np.float64)
+
+        rank, world, _ = sharding.dist_info()
+        owned = sharding.owned_frequencies(nf, self.batch, rank, world)
+        pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
+                                  tol=self.tol, max_iter=self.max_iter, batch=self.batch,
+                                  check_every=self.check_every, warm_start=self.warm_start)
+        self.stats = stats
+        if world > 1:
+            pN = sharding.gather_rows(pN, owned, nf) if keep_pN else None
+            pR = sharding.gather_rows(pR, owned, nf) if pR is not None else None
+            it = sharding.gather_rows(stats.iters[:, None], owned, nf)
+            rr = sharding.gather_rows(stats.relres[:, None], owned, nf)
+            self.iters, self.relres = it[:, 0], rr[:, 0]
+        else:
+            self.iters, self.relres = stats.iters, stats.relres
+        self.pN = pN
+        if pR is not None:
+            self.pR = pR
+        self.t = time.time() - then
+        if timeit:
+            if self.t <= 60:
+                print(f"Time taken: {self.t} s")
+            else:
+                print(f"Time taken: {self.t / 60} min")
+
+    # ---- evaluate (FEM_3D.py:2042-2090) ------------------------------------------------------
+    def evaluate(self, R, interpolation_tolerance=0.001, plot=False):
+        self.R = R
+        if self.pN is None:
+            raise RuntimeError("evaluate() needs pN: call compute() (with keep_pN=True) first")
+        cols = []
+        for i in range(len(R.coord)):
+            nodes, wts = receiver_stencil(self.nos, self.elem_vol, R.coord[i, :], interpolation_tolerance)
+            if wts[0] == 1.0 and not wts[1:].any():
+                cols.append(self.pN[:, nodes[0]])
+            else:
+                cols.append(self.pN[:, nodes.astype(np.int64)] @ wts)
+        self.pR = np.asarray(cols).T.reshape(self.pN.shape[0], len(R.coord))
+        return self.pR

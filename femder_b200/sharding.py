@@ -1,0 +1,55 @@
+"""Frequency sharding across ranks: frequencies are independent systems over the same H, Q, A.
+
+One process per GPU.  Each rank owns whole batches (the fused-SpMV width) dealt round-robin, because the
+iteration count rises with frequency and contiguous blocks would leave the last rank with the expensive
+end of the sweep.  There is no collective on the solve path; the result rows are gathered once at the end.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def owned_frequencies(n_freq, batch, rank, world):
+    """Indices (ascending) of the frequencies rank ``rank`` of ``world`` solves."""
+    if world <= 1:
+        return np.arange(n_freq, dtype=np.int64)
+    n_batches = (n_freq + batch - 1) // batch
+    mine = np.arange(rank, n_batches, world, dtype=np.int64)
+    idx = (mine[:, None] * batch + np.arange(batch, dtype=np.int64)[None, :]).ravel()
+    return idx[idx < n_freq]
+
+
+def dist_info():
+    """(rank, world, local_rank) from torch.distributed if initialised, else from the torchrun environment
+    only when a process group exists; a plain single process is (0, 1, 0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+    except ImportError:
+        pass
+    return 0, 1, 0
+
+
+def gather_rows(local_rows, owned, n_freq, group=None):
+    """All ranks contribute ``local_rows`` (len(owned), ...) and get back the full (n_freq, ...) array.
+    Host-side gather of python objects: the payload is receiver pressures (small) or, on request, pN rows."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, (np.asarray(owned), None if local_rows is None else np.asarray(local_rows)), group=group)
+    first = next((p[1] for p in parts if p[1] is not None and len(p[0])), None)
+    if first is None:
+        return None
+    out = np.zeros((n_freq,) + first.shape[1:], dtype=first.dtype)
+    seen = np.zeros(n_freq, dtype=bool)
+    for idx, rows in parts:
+        if rows is None or len(idx) == 0:
+            continue
+        out[idx] = rows
+        seen[idx] = True
+    if not seen.all():
+        raise RuntimeError("frequency sharding left rows unsolved")
+    return out

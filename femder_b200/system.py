@@ -1,0 +1,287 @@
+"""``System``: one mesh on one B200, a thin object layer over the C ABI handle ``fdb_system``.
+
+Everything numerical happens in ``libfemder_b200.so``; this file only shapes numpy / scipy objects into
+the plain pointers the ABI takes and back into the types the reference leaves behind
+(scipy ``csc_matrix`` with int32 indices, ``complex128`` ndarrays).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.sparse import csc_matrix
+
+from . import _lib
+from ._lib import SweepParams, SweepResult, check, ptr
+
+VALID_BATCH = (1, 2, 4, 8, 16)
+
+
+def _i32(a):
+    a = np.asarray(a)
+    if a.dtype != np.int32:
+        if a.size and (a.max() > np.iinfo(np.int32).max or a.min() < 0):
+            raise ValueError("index does not fit int32")
+        a = a.astype(np.int32)
+    return np.ascontiguousarray(a)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+class SweepStats:
+    def __init__(self, iters, relres, seconds, n_spmv, n_kernels, n_unconverged):
+        self.iters = iters
+        self.relres = relres
+        self.seconds = seconds
+        self.n_spmv = n_spmv
+        self.n_kernels = n_kernels
+        self.n_unconverged = n_unconverged
+
+    def __repr__(self):
+        it = self.iters
+        return (f"SweepStats(n_freq={len(it)}, iters[min/mean/max]={it.min() if len(it) else 0}/"
+                f"{it.mean() if len(it) else 0:.0f}/{it.max() if len(it) else 0}, max_relres="
+                f"{self.relres.max() if len(it) else 0:.2e}, seconds={self.seconds:.3f}, "
+                f"n_unconverged={self.n_unconverged})")
+
+
+class System:
+    def __init__(self, device=0, stream=None):
+        """``stream``: a ``cudaStream_t`` as int (e.g. ``torch.cuda.Stream().cuda_stream``); it must not be the
+        legacy default stream because the sweep captures CUDA graphs on it.  ``None`` -> library-owned stream."""
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.fdb_system_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = int(device)
+        self.n_nodes = 0
+        self.n_elem = 0
+        self.nper = 0
+        self.nnz = 0
+        self.n_groups = 0
+        self.n_tri = 0
+        self.nper_s = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.fdb_system_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._lib.fdb_synchronize(self._h))
+
+    # ---- volume -------------------------------------------------------------------------------
+    def set_volume_mesh(self, nos, elem_vol):
+        nos = _f64(nos)
+        conn = _i32(elem_vol)
+        if nos.ndim != 2 or nos.shape[1] != 3:
+            raise ValueError("nos must be (N, 3)")
+        if conn.ndim != 2 or conn.shape[1] not in (4, 10):
+            raise ValueError("elem_vol must be (E, 4) or (E, 10)")
+        check(self._lib.fdb_set_volume_mesh(self._h, nos.shape[0], ptr(nos), conn.shape[0], conn.shape[1], ptr(conn)))
+        self.n_nodes, self.n_elem, self.nper = nos.shape[0], conn.shape[0], conn.shape[1]
+        nnz = C.c_int64()
+        check(self._lib.fdb_pattern_nnz(self._h, C.byref(nnz)))
+        self.nnz = nnz.value
+
+    def set_pattern(self, indptr, indices):
+        indptr, indices = _i32(indptr), _i32(indices)
+        check(self._lib.fdb_set_pattern(self._h, len(indptr) - 1, len(indices), ptr(indptr), ptr(indices)))
+        self.n_nodes, self.nnz, self.n_elem, self.nper = len(indptr) - 1, len(indices), 0, 0
+
+    def pattern(self):
+        indptr = np.empty(self.n_nodes + 1, dtype=np.int32)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        check(self._lib.fdb_pattern_get(self._h, ptr(indptr), ptr(indices)))
+        return indptr, indices
+
+    def elem2nnz(self):
+        m = np.empty((self.n_elem, self.nper, self.nper), dtype=np.int32)
+        check(self._lib.fdb_elem2nnz_get(self._h, ptr(m)))
+        return m
+
+    def assemble_volume(self, rho0, c0):
+        check(self._lib.fdb_assemble_volume(self._h, float(np.real(rho0)), float(np.real(c0))))
+
+    def get_HQ_values(self):
+        H = np.empty(self.nnz, dtype=np.float64)
+        Q = np.empty(self.nnz, dtype=np.float64)
+        check(self._lib.fdb_get_HQ(self._h, ptr(H), ptr(Q)))
+        return H, Q
+
+    def get_HQ(self):
+        """scipy csc (N, N) float64, canonical int32 indices: the types ``compute()`` leaves in ``self.H/Q``."""
+        indptr, indices = self.pattern()
+        H, Q = self.get_HQ_values()
+        N = self.n_nodes
+        # the pattern is symmetric and the values are those of a symmetric operator stored by rows:
+        # CSR(row r, col c) of the operator is CSC(row c, col r), both equal by symmetry of the entries' positions
+        return (csc_matrix((H, indices, indptr), shape=(N, N)), csc_matrix((Q, indices.copy(), indptr.copy()), shape=(N, N)))
+
+    def set_HQ_values(self, H, Q):
+        H, Q = _f64(H), _f64(Q)
+        if len(H) != self.nnz or len(Q) != self.nnz:
+            raise ValueError("H/Q value arrays must have nnz entries")
+        check(self._lib.fdb_set_HQ(self._h, ptr(H), ptr(Q)))
+
+    def element_matrices(self):
+        n2 = self.nper * self.nper
+        He = np.empty((n2, self.n_elem), dtype=np.float64)
+        Qe = np.empty((n2, self.n_elem), dtype=np.float64)
+        check(self._lib.fdb_get_element_matrices(self._h, ptr(He), ptr(Qe)))
+        return He.reshape(self.nper, self.nper, self.n_elem), Qe.reshape(self.nper, self.nper, self.n_elem)
+
+    # ---- surface ------------------------------------------------------------------------------
+    def set_surface_mesh(self, elem_surf, domain_index_surf, group_ids):
+        """``group_ids``: the sorted boundary-condition keys (``np.sort([*mu])``, FEM_3D.py:1283)."""
+        conn = _i32(elem_surf)
+        if conn.ndim != 2 or conn.shape[1] not in (3, 6):
+            raise ValueError("elem_surf must be (T, 3) or (T, 6)")
+        group_ids = np.asarray(group_ids)
+        dom = np.asarray(domain_index_surf)
+        grp = np.full(len(conn), -1, dtype=np.int32)
+        for i, g in enumerate(group_ids):
+            grp[dom == g] = i
+        check(self._lib.fdb_set_surface_mesh(self._h, conn.shape[0], conn.shape[1], ptr(conn), ptr(grp), len(group_ids)))
+        self.n_tri, self.nper_s, self.n_groups = conn.shape[0], conn.shape[1], len(group_ids)
+
+    def heron_areas(self):
+        a = np.empty(self.n_tri, dtype=np.float64)
+        check(self._lib.fdb_heron_areas(self._h, ptr(a)))
+        return a
+
+    def assemble_surface(self):
+        check(self._lib.fdb_assemble_surface(self._h))
+
+    def get_A(self, drop_zeros=False):
+        """list of csc (N, N) float64, one per group, each with its own pattern (entries its triangles touch)."""
+        nnz_b = C.c_int64()
+        check(self._lib.fdb_surface_nnz(self._h, C.byref(nnz_b)))
+        Zb = nnz_b.value
+        N = self.n_nodes
+        indptr = np.empty(N + 1, dtype=np.int32)
+        indices = np.empty(Zb, dtype=np.int32)
+        check(self._lib.fdb_surface_pattern_get(self._h, ptr(indptr), ptr(indices)))
+        vals = np.empty((self.n_groups, Zb), dtype=np.float64)
+        touched = np.empty((self.n_groups, Zb), dtype=np.uint8)
+        check(self._lib.fdb_surface_get(self._h, ptr(vals), ptr(touched)))
+        rows = np.repeat(np.arange(N, dtype=np.int32), np.diff(indptr))
+        out = []
+        for g in range(self.n_groups):
+            keep = touched[g].astype(bool)
+            if drop_zeros:
+                keep &= vals[g] != 0.0
+            cnt = np.bincount(rows[keep], minlength=N)
+            ip = np.zeros(N + 1, dtype=np.int32)
+            np.cumsum(cnt, out=ip[1:])
+            out.append(csc_matrix((vals[g][keep], indices[keep], ip), shape=(N, N)))
+        return out
+
+    def set_surface_matrices(self, A_list):
+        """Solver-only use: give A_g as scipy matrices (any pattern); they are merged on one union pattern."""
+        N = self.n_nodes
+        ng = len(A_list)
+        if ng == 0:
+            ip = np.zeros(N + 1, dtype=np.int32)
+            check(self._lib.fdb_set_surface(self._h, 0, 0, ptr(ip), None, None))
+            self.n_groups = 0
+            return
+        mats = [csc_matrix(A).astype(np.float64).T.tocsc() for A in A_list]  # CSC of A^T == CSR of A
+        for m in mats:
+            m.sort_indices()
+        union = None
+        for m in mats:
+            p = csc_matrix((np.ones(m.nnz), m.indices, m.indptr), shape=(N, N))
+            union = p if union is None else union + p
+        union = union.tocsc()
+        union.sort_indices()
+        ip, ix = union.indptr.astype(np.int32), union.indices.astype(np.int32)
+        vals = np.zeros((ng, len(ix)), dtype=np.float64)
+        cols = np.repeat(np.arange(N), np.diff(ip))
+        key_u = cols.astype(np.int64) * N + ix
+        for g, m in enumerate(mats):
+            cm = np.repeat(np.arange(N), np.diff(m.indptr))
+            key = cm.astype(np.int64) * N + m.indices
+            pos = np.searchsorted(key_u, key)
+            vals[g, pos] = m.data
+        check(self._lib.fdb_set_surface(self._h, ng, len(ix), ptr(ip), ptr(ix), ptr(vals)))
+        self.n_groups = ng
+
+    # ---- sweep --------------------------------------------------------------------------------
+    def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
+              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None):
+        """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
+
+        mu: (n_groups, n_freq) complex.  Returns (pN or None, pR or None, SweepStats)."""
+        if batch not in VALID_BATCH:
+            raise ValueError(f"batch must be one of {VALID_BATCH}")
+        omega = _f64(np.atleast_1d(omega))
+        nf = len(omega)
+        mu = _c128(np.asarray(mu).reshape(self.n_groups, nf)) if self.n_groups else None
+        src_nodes = _i32(np.atleast_1d(src_nodes))
+        src_q = _c128(np.atleast_1d(src_q).ravel())
+        if len(src_q) != len(src_nodes):
+            raise ValueError("src_nodes and src_q differ in length")
+        prm = SweepParams()
+        prm.n_freq = nf
+        prm.omega = ptr(omega)
+        prm.mu = ptr(mu) if mu is not None else None
+        prm.n_src = len(src_nodes)
+        prm.src_nodes = ptr(src_nodes)
+        prm.src_q = ptr(src_q)
+        prm.tol = float(tol)
+        prm.max_iter = int(max_iter)
+        prm.batch = int(batch)
+        prm.check_every = int(check_every)
+        prm.warm_start = int(bool(warm_start))
+        prm.precond = 0
+        n_rcv = 0
+        if rcv_nodes is not None:
+            rcv_nodes = _i32(np.asarray(rcv_nodes).reshape(-1, 4))
+            rcv_w = _f64(np.asarray(rcv_w).reshape(-1, 4))
+            n_rcv = len(rcv_nodes)
+        prm.n_rcv = n_rcv
+        prm.rcv_nodes = ptr(rcv_nodes) if n_rcv else None
+        prm.rcv_w = ptr(rcv_w) if n_rcv else None
+        res = SweepResult()
+        pN = None
+        if pN_out is not None:
+            pN = pN_out
+        elif want_pN:
+            pN = np.empty((nf, self.n_nodes), dtype=np.complex128)
+        pR = np.empty((nf, n_rcv), dtype=np.complex128) if n_rcv else None
+        iters = np.zeros(nf, dtype=np.int32)
+        relres = np.zeros(nf, dtype=np.float64)
+        res.pN = ptr(pN)
+        res.pR = ptr(pR)
+        res.iters = ptr(iters)
+        res.relres = ptr(relres)
+        check(self._lib.fdb_sweep(self._h, C.byref(prm), C.byref(res)))
+        return pN, pR, SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged)
+
+    def spmv(self, omega, mu, x):
+        """y = G_f x for a batch; x is (N, F) complex128."""
+        x = _c128(x)
+        F = x.shape[1]
+        omega = _f64(np.atleast_1d(omega))
+        mu = _c128(np.asarray(mu).reshape(self.n_groups, F)) if self.n_groups else None
+        y = np.empty_like(x)
+        check(self._lib.fdb_spmv(self._h, F, ptr(omega), ptr(mu) if mu is not None else None, ptr(x), ptr(y)))
+        return y
+
+    def spmv_bench(self, batch, reps):
+        ms = C.c_double()
+        nbytes = C.c_int64()
+        check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value

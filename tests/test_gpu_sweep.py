@@ -1,0 +1,180 @@
+"""-m gpu: K5 fused SpMV, K6 COCG sweep, K7 receivers through the C ABI against the oracle's direct solve."""
+import numpy as np
+import pytest
+
+from oracle import femder_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_rows(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+def _solver_system(H, Q, A_list):
+    """Feed the solver the given matrices (e.g. the reference's own arrays) - assembly is not involved."""
+    from femder_b200 import System
+    s = System(0)
+    Hc = H.tocsc().astype(np.float64) if not np.iscomplexobj(H.data) else H.tocsc().real.astype(np.float64)
+    Qc = Q.tocsc().astype(np.float64) if not np.iscomplexobj(Q.data) else Q.tocsc().real.astype(np.float64)
+    Hc.sort_indices(); Qc.sort_indices()
+    assert np.array_equal(Hc.indices, Qc.indices)
+    s.set_pattern(Hc.indptr, Hc.indices)      # symmetric pattern: CSC arrays are the CSR arrays
+    s.set_HQ_values(Hc.data, Qc.data)
+    s.set_surface_matrices(A_list)
+    return s
+
+
+@pytest.mark.parametrize("F", [1, 2, 4, 8, 16])
+def test_spmv_matches_scipy(gpu_lib, golden, F):
+    g = golden
+    s = _solver_system(g.H, g.Q, g.A)
+    rng = np.random.default_rng(F)
+    x = rng.standard_normal((g.N, F)) + 1j * rng.standard_normal((g.N, F))
+    freq = np.linspace(30.0, 400.0, F)
+    w = 2 * np.pi * freq
+    mu = np.array([np.resize(g.mu[int(k)], F) * (1 + 0.1 * np.arange(F)) for k in g.group_ids])
+    y = s.spmv(w, mu, x)
+    Hd, Qd = g.H.astype(np.complex128), g.Q.astype(np.complex128)
+    for f in range(F):
+        G = O.system_matrix(Hd, Qd, g.A, mu[:, f], w[f])
+        ref = G @ x[:, f]
+        assert np.linalg.norm(y[:, f] - ref) / np.linalg.norm(ref) < 1e-13
+
+
+def test_sweep_on_reference_matrices(gpu_lib, golden):
+    """Solver parity on identical inputs: the reference's own H, Q, A arrays in, its pN out (north star: relative
+    L2 error <= 1e-6, receiver SPL within 0.01 dB)."""
+    g = golden
+    s = _solver_system(g.H, g.Q, g.A)
+    w = 2 * np.pi * g.freq
+    mu = np.array([g.mu[int(k)] for k in g.group_ids])
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    pN, _, st = s.sweep(w, mu, src, g.src_q, tol=1e-10, batch=4, max_iter=20000)
+    assert st.n_unconverged == 0, st
+    assert _rel_rows(pN, g.pN).max() < 1e-6
+    pR = O.evaluate(g.grid.nos, g.grid.elem_vol, pN, g.rcv)
+    assert np.abs(O.p2SPL(pR) - O.p2SPL(g.pR)).max() < 0.01
+
+
+@pytest.mark.parametrize("batch", [1, 2, 8, 16])
+def test_sweep_batches_agree(gpu_lib, batch):
+    from conftest import Golden
+    g = Golden("tet4_shoebox_jitter")
+    s = _solver_system(g.H, g.Q, g.A)
+    freq = np.arange(20.0, 31.0)  # 11 frequencies: ragged last batch for every width
+    w = 2 * np.pi * freq
+    mu = np.array([np.resize(g.mu[int(k)], len(freq)) for k in g.group_ids])
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    pN, _, st = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=batch)
+    assert st.n_unconverged == 0
+    muo = {int(k): mu[i] for i, k in enumerate(g.group_ids)}
+    ref = O.solve_sweep(g.H.astype(np.complex128), g.Q.astype(np.complex128), g.A, muo, g.group_ids, freq,
+                        O.source_vector(g.grid.nos, g.src, g.src_q))
+    assert _rel_rows(pN, ref).max() < 1e-7
+
+
+def test_sweep_empty_and_single(gpu_lib):
+    from conftest import Golden
+    g = Golden("tet4_cplx_room")
+    s = _solver_system(g.H, g.Q, g.A)
+    mu = np.array([g.mu[int(k)] for k in g.group_ids])
+    pN, pR, st = s.sweep(np.array([]), mu[:, :0], [3], [1e-4])
+    assert pN.shape == (0, g.N) and len(st.iters) == 0
+    pN, _, st = s.sweep(2 * np.pi * g.freq[:1], mu[:, :1], [3], [1e-4], tol=1e-10)
+    assert pN.shape == (1, g.N) and st.n_unconverged == 0
+    # no source: zero right-hand side -> zero solution, zero iterations
+    pN, _, st = s.sweep(2 * np.pi * g.freq[:2], mu[:, :2], [], [], tol=1e-10)
+    assert not pN.any() and st.iters.max() == 0
+
+
+def test_sources_overwrite_and_linearity(gpu_lib):
+    from conftest import Golden
+    g = Golden("tet4_cplx_room")
+    s = _solver_system(g.H, g.Q, g.A)
+    w = 2 * np.pi * g.freq[:2]
+    mu = np.array([g.mu[int(k)][:2] for k in g.group_ids])
+    a, _, _ = s.sweep(w, mu, [5], [1e-4], tol=1e-12)
+    b, _, _ = s.sweep(w, mu, [40], [2e-4j], tol=1e-12)
+    ab, _, _ = s.sweep(w, mu, [5, 40], [1e-4, 2e-4j], tol=1e-12)
+    assert _rel_rows(ab, a + b).max() < 1e-8                       # linearity in q
+    dup, _, _ = s.sweep(w, mu, [5, 5], [7.0, 1e-4], tol=1e-12)      # q[node] = S.q: the later source overwrites
+    assert _rel_rows(dup, a).max() < 1e-8
+    # reciprocity p(S->R) = p(R->S) for the symmetric operator
+    assert abs(a[0, 40] - s.sweep(w, mu, [40], [1e-4], tol=1e-12)[0][0, 5]) / abs(a[0, 40]) < 1e-7
+
+
+def test_receivers_only_mode_matches_pN(gpu_lib):
+    from conftest import Golden
+    from femder_b200 import receiver_stencil
+    g = Golden("tet4_shoebox_jitter")
+    s = _solver_system(g.H, g.Q, g.A)
+    w = 2 * np.pi * g.freq
+    mu = np.array([g.mu[int(k)] for k in g.group_ids])
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    coords = np.concatenate([g.rcv, g.rcv_off])
+    st = [receiver_stencil(g.grid.nos, g.grid.elem_vol, c) for c in coords]
+    nodes = np.array([t[0] for t in st]); wts = np.array([t[1] for t in st])
+    pN, pR, stats = s.sweep(w, mu, src, g.src_q, nodes, wts, tol=1e-11, batch=2)
+    ref = O.evaluate(g.grid.nos, g.grid.elem_vol, pN, coords)
+    assert np.abs(pR - ref).max() / np.abs(ref).max() < 1e-13
+    assert np.array_equal(pR[:, 0], pN[:, nodes[0, 0]])            # on-node receiver: exact copy
+    _, pR2, _ = s.sweep(w, mu, src, g.src_q, nodes, wts, want_pN=False, tol=1e-11, batch=2)
+    assert np.array_equal(pR, pR2)
+    # against the reference's own evaluate() output, on its own pN
+    gold = np.concatenate([g.pR, g.pR_off], axis=1)
+    assert np.abs(O.p2SPL(pR) - O.p2SPL(gold)).max() < 0.01
+
+
+def test_warm_start_and_determinism(gpu_lib):
+    from conftest import Golden
+    g = Golden("tet4_shoebox_jitter")
+    s = _solver_system(g.H, g.Q, g.A)
+    freq = np.arange(50.0, 66.0)
+    w = 2 * np.pi * freq
+    mu = np.array([np.resize(g.mu[int(k)], len(freq)) for k in g.group_ids])
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    cold, _, st0 = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=4, warm_start=False)
+    cold2, _, _ = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=4, warm_start=False)
+    assert np.array_equal(cold, cold2)                              # deterministic reductions
+    warm, _, st1 = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=4, warm_start=True)
+    assert st1.n_unconverged == 0 and _rel_rows(warm, cold).max() < 1e-8
+
+
+def test_unconverged_is_reported(gpu_lib):
+    from conftest import Golden
+    g = Golden("tet4_shoebox_jitter")
+    s = _solver_system(g.H, g.Q, g.A)
+    mu = np.array([g.mu[int(k)] for k in g.group_ids])
+    _, _, st = s.sweep(2 * np.pi * g.freq, mu, [3], [1e-4], tol=1e-12, max_iter=4, check_every=2)
+    assert st.n_unconverged == len(g.freq) and st.iters.max() <= 6 and st.relres.min() > 1e-12
+
+
+def test_config1_size_residual_and_oracle(gpu_lib):
+    """Config 1 mesh (21 735 DOF, rigid): GPU assembly + sweep vs the oracle's direct solve on a frequency sample,
+    and the size-independent property ||b - G x|| / ||b|| <= tol checked with scipy on every frequency solved."""
+    from femder_b200 import System
+    from femder_b200.mesh import shoebox_tet4
+    grid = shoebox_tet4(26, 34, 22, jitter=0.2)
+    c0, rho0 = 343.0, 1.21
+    s = System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.set_surface_mesh(grid.elem_surf, grid.domain_index_surf, np.arange(2, 8))
+    s.assemble_volume(rho0, c0)
+    s.assemble_surface()
+    H, Q = s.get_HQ()
+    A = s.get_A()
+    freq = np.array([20.0, 63.0, 125.0, 200.0])
+    w = 2 * np.pi * freq
+    mu = np.zeros((6, len(freq)), dtype=complex)
+    mu[5] = 0.02 / (c0 * rho0)
+    src = grid.closest_node([1.0, 1.0, 1.2])
+    pN, _, st = s.sweep(w, mu, [src], [1e-4], tol=1e-9, batch=4, max_iter=50000)
+    assert st.n_unconverged == 0, st
+    q = np.zeros(grid.NumNosC, dtype=complex); q[src] = 1e-4
+    for n in range(len(freq)):
+        G = O.system_matrix(H, Q, A, mu[:, n], w[n])
+        b = -1j * w[n] * q
+        assert np.linalg.norm(b - G @ pN[n]) / np.linalg.norm(b) < 1e-8
+    ref = O.solve_sweep(H, Q, A, {k + 2: mu[k] for k in range(6)}, np.arange(2, 8), freq[[0, 3]], q)
+    assert _rel_rows(pN[[0, 3]], ref).max() < 1e-6
