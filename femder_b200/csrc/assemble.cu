@@ -344,6 +344,64 @@ void extract_diagonal(fdb_system* sys) {
     k_diag<<<grid_for(sys->n_nodes, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p,
                                                                   sys->n_nodes, sys->diag_hq.p);
     FDB_CUDA(cudaGetLastError());
+    build_sell(sys);
+}
+
+// SELL-8: the layout the SpMV streams.  A warp's rows read the same k of one slice together, so the column
+// index and (H, Q) loads of a warp are contiguous (one or two sectors) instead of one sector per row.
+__global__ void k_sell_width(const int32_t* __restrict__ indptr, int64_t n_rows, int64_t n_slices, int32_t* __restrict__ width) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    int w = 0;
+    for (int i = 0; i < 8; ++i) {
+        int64_t r = s * 8 + i;
+        if (r < n_rows) w = max(w, indptr[r + 1] - indptr[r]);
+    }
+    width[s] = w;
+}
+
+__global__ void k_sell_fill(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const double2* __restrict__ hq, int64_t n_rows, int64_t n_slices,
+                            const int32_t* __restrict__ sell_off, int32_t* __restrict__ sell_idx,
+                            double2* __restrict__ sell_hq) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slices * 8) return;
+    const int64_t s = t >> 3;
+    const int pos = (int)(t & 7);
+    const int64_t r = t;
+    const int off = sell_off[s], width = sell_off[s + 1] - off;
+    int b = 0, len = 0;
+    if (r < n_rows) { b = indptr[r]; len = indptr[r + 1] - b; }
+    const int32_t pad_col = (int32_t)min(r, n_rows - 1);
+    for (int k = 0; k < width; ++k) {
+        const int64_t o = ((int64_t)off + k) * 8 + pos;
+        if (k < len) {
+            sell_idx[o] = indices[b + k];
+            sell_hq[o] = hq[b + k];
+        } else {
+            sell_idx[o] = pad_col;
+            sell_hq[o] = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+void build_sell(fdb_system* sys) {
+    const int64_t N = sys->n_nodes;
+    const int64_t S = (N + 7) / 8;
+    sys->n_slices = S;
+    DevBuf<int32_t> width;
+    width.alloc(S);
+    k_sell_width<<<grid_for(S, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, N, S, width.p);
+    sys->sell_off.alloc(S + 1);
+    int64_t tot = 0;
+    exclusive_scan_i32(width.p, sys->sell_off.p, S, &tot, sys->stream);
+    FDB_REQUIRE(tot * 8 < 2147483647LL, "SELL layout exceeds int32 indexing");
+    sys->sell_entries = tot * 8;
+    sys->sell_idx.alloc(tot ? tot * 8 : 1);
+    sys->sell_hq.alloc(tot ? tot * 8 : 1);
+    k_sell_fill<<<grid_for(S * 8, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p, N, S,
+                                                               sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p);
+    FDB_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -99,6 +99,13 @@ struct fdb_system {
     fdb::DevBuf<double2> hq;         // [nnz] (H, Q) interleaved: the layout the SpMV streams
     bool have_hq = false;
     fdb::DevBuf<double2> diag_hq;    // [n_nodes] diagonal of H and Q
+    // SELL-8 copy of (indices, hq) the SpMV streams: slice s = rows 8s..8s+7, entry k of row r at
+    // (sell_off[s] + k)*8 + r%8; rows shorter than the slice width are padded with (col = row, 0, 0)
+    int64_t n_slices = 0;
+    int64_t sell_entries = 0;
+    fdb::DevBuf<int32_t> sell_off;   // [n_slices+1] in units of 8 entries
+    fdb::DevBuf<int32_t> sell_idx;   // [sell_entries]
+    fdb::DevBuf<double2> sell_hq;    // [sell_entries]
 
     // surface
     int64_t n_tri = 0;
@@ -135,6 +142,7 @@ void heron_areas(fdb_system* sys);
 void assemble_surface(fdb_system* sys);
 void build_overlay(fdb_system* sys);
 void extract_diagonal(fdb_system* sys);
+void build_sell(fdb_system* sys);
 void interleave_hq(fdb_system* sys, const double* H, const double* Q);
 void deinterleave_hq(fdb_system* sys, double* H, double* Q);
 

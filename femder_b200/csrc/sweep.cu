@@ -13,6 +13,8 @@
 //                  contiguous 16*F-byte segment (a full 128-byte line at F = 8)
 #include "common.cuh"
 #include "../../include/femder_b200.h"
+#include <algorithm>
+#include <cstdlib>
 
 namespace fdb {
 
@@ -48,6 +50,7 @@ struct SweepWork {
     int graph_iters = 0;
     int graph_F = 0;
     bool graph_overlay = false;
+    int spmv_cfg = 0;
 };
 
 void free_sweep_work(SweepWork* w) {
@@ -81,11 +84,11 @@ __device__ __forceinline__ double warp_sum_by_f(double v) {
 }
 
 // Block partials -> partial[blockIdx.x][f][slot]; the last block to arrive adds the partials of all blocks
-// in a fixed order (deterministic) and calls `fin(f, total_slot0, total_slot1)` from one thread per f.
-template <int F, int NV, typename Fin>
+// in a fixed order (deterministic) and calls `fin(f, totals)` from one thread per f.
+template <int F, int NV, int BLOCK, typename Fin>
 __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
                                                       unsigned int* __restrict__ ticket, Fin fin) {
-    __shared__ double s_red[kBlock / 32][kMaxF][NV];
+    __shared__ double s_red[BLOCK / 32][kMaxF][NV];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double w[NV];
@@ -100,7 +103,7 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double s = 0;
-            for (int k = 0; k < kBlock / 32; ++k) s += s_red[k][threadIdx.x][i];
+            for (int k = 0; k < BLOCK / 32; ++k) s += s_red[k][threadIdx.x][i];
             partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
         }
     }
@@ -113,8 +116,8 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // kBlock threads: group g = tid / F ... each f gets kBlock/F threads striding over the blocks
-    constexpr int TPF = kBlock / F;
+    // each f gets BLOCK/F threads striding over the blocks, then a fixed-order sum over those threads
+    constexpr int TPF = BLOCK / F;
     const int f = threadIdx.x % F, j = threadIdx.x / F;
     double acc[NV];
 #pragma unroll
@@ -123,7 +126,7 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
     }
-    __shared__ double s_fin[kBlock][NV];
+    __shared__ double s_fin[BLOCK][NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) s_fin[threadIdx.x][i] = acc[i];
     __syncthreads();
@@ -142,41 +145,82 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
 
 // ------------------------------------------------------------------------------------------------
 // K5: y[row][f] = sum_k (H_k - w2_f Q_k) x[col_k][f] + sum_ov (coef[g][f] * A_ov) x[col_ov][f]
-// lanes: (row in warp, f); F lanes share one row's matrix entries (broadcast loads)
+//
+// lanes = (row in warp, f): 32/F rows per warp.  The matrix is streamed from the SELL-8 copy, so the F-lane
+// groups of a warp read consecutive entries (coalesced, each byte fetched once).  The x gather of one
+// (row, k) is one contiguous 16*F-byte segment.  Every block owns one contiguous range of rows, so the x
+// lines of neighbouring mesh lines / planes are re-used out of L1 instead of being re-fetched from L2.
 // DOT: also accumulate x[row]^T y[row] (unconjugated) -> sc.pq
 // ------------------------------------------------------------------------------------------------
-template <int F, bool DOT, bool OVERLAY>
-__global__ void __launch_bounds__(kBlock) k_spmv(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                  const double2* __restrict__ hq, const int32_t* __restrict__ ov_ptr,
-                                                  const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
-                                                  const double2* __restrict__ coef, const double2* __restrict__ x,
-                                                  double2* __restrict__ y, int64_t n_rows, Scalars* __restrict__ sc,
-                                                  double* __restrict__ partial) {
-    constexpr int RPB = kBlock / F;  // rows per block pass
-    const int f = threadIdx.x % F;
-    const int rl = threadIdx.x / F;
+// launch shapes (threads per block, resident blocks per SM); FDB_SPMV_CFG picks one at run time (tuning aid)
+struct SpmvCfg { int block, per_sm; };
+constexpr SpmvCfg kSpmvCfgs[] = {{512, 2}, {512, 3}, {256, 4}, {1024, 1}, {256, 6}};
+constexpr int kSpmvMaxBlock = 1024;
+
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <int F, bool DOT, bool OVERLAY, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
+       const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
+       const double2* __restrict__ coef, const double2* __restrict__ x, double2* __restrict__ y, int64_t n_rows,
+       Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int RPW = 32 / F;                 // rows per warp
+    constexpr int NWARP = BLOCK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = lane % F;
+    const int rl = lane / F;
     const double w2 = sc->w2[f];
+    const int64_t n_groups = (n_rows + RPW - 1) / RPW;
+    const int64_t gpb = (n_groups + gridDim.x - 1) / gridDim.x;   // contiguous groups per block
+    const int64_t g0 = (int64_t)blockIdx.x * gpb;
+    const int64_t g1 = min(g0 + gpb, n_groups);
     double dot[2] = {0.0, 0.0};
-    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < n_rows; row0 += (int64_t)gridDim.x * RPB) {
-        const int64_t row = row0 + rl;
+    for (int64_t g = g0 + warp; g < g1; g += NWARP) {
+        const int64_t row = g * RPW + rl;
         if (row < n_rows) {
+            const int64_t slice = row >> 3;
+            const int off = sell_off[slice];
+            const int width = sell_off[slice + 1] - off;
+            const int32_t* ip = sell_idx + ((int64_t)off * 8 + (row & 7));
+            const double2* mp = sell_hq + ((int64_t)off * 8 + (row & 7));
             double2 acc = make_double2(0.0, 0.0);
-            const int kb = indptr[row], ke = indptr[row + 1];
-            for (int k = kb; k < ke; ++k) {
-                const int c = __ldg(&indices[k]);
-                const double2 m = __ldg(&hq[k]);
-                const double g = m.x - w2 * m.y;
-                const double2 xv = x[(int64_t)c * F + f];
-                acc.x += g * xv.x;
-                acc.y += g * xv.y;
+            int k = 0;
+            for (; k + 4 <= width; k += 4) {
+                int c[4];
+                double2 m[4], xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) c[u] = __ldg(ip + (k + u) * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xv[u] = __ldg(&x[(int64_t)c[u] * F + f]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m[u] = ld_stream(mp + (k + u) * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double gk = m[u].x - w2 * m[u].y;
+                    acc.x += gk * xv[u].x;
+                    acc.y += gk * xv[u].y;
+                }
+            }
+            for (; k < width; ++k) {
+                const int c = __ldg(ip + k * 8);
+                const double2 m = ld_stream(mp + k * 8);
+                const double2 xv = __ldg(&x[(int64_t)c * F + f]);
+                const double gk = m.x - w2 * m.y;
+                acc.x += gk * xv.x;
+                acc.y += gk * xv.y;
             }
             if (OVERLAY) {
                 const int ob = ov_ptr[row], oe = ov_ptr[row + 1];
-                for (int k = ob; k < oe; ++k) {
-                    const int2 cg = ov_cg[k];
-                    const double a = ov_val[k];
+                for (int o = ob; o < oe; ++o) {
+                    const int2 cg = ov_cg[o];
+                    const double a = ov_val[o];
                     const double2 cf = coef[cg.y * F + f];
-                    const double2 xv = x[(int64_t)cg.x * F + f];
+                    const double2 xv = __ldg(&x[(int64_t)cg.x * F + f]);
                     const double2 t = cmul(make_double2(cf.x * a, cf.y * a), xv);
                     acc.x += t.x;
                     acc.y += t.y;
@@ -184,7 +228,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(const int32_t* __restrict__ ind
             }
             y[row * F + f] = acc;
             if (DOT) {
-                const double2 xv = x[row * F + f];
+                const double2 xv = __ldg(&x[row * F + f]);
                 const double2 d = cmul(xv, acc);
                 dot[0] += d.x;
                 dot[1] += d.y;
@@ -192,7 +236,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(const int32_t* __restrict__ ind
         }
     }
     if (DOT) {
-        block_reduce_finalize<F, 2>(dot, partial, &sc->ticket[0], [&](int ff, const double* tot) {
+        block_reduce_finalize<F, 2, BLOCK>(dot, partial, &sc->ticket[0], [&](int ff, const double* tot) {
             sc->pq[ff] = make_double2(tot[0], tot[1]);
         });
     }
@@ -232,7 +276,7 @@ __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, doub
         v[1] += rz.y;
         v[2] += rv.x * rv.x + rv.y * rv.y;
     }
-    block_reduce_finalize<F, 3>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
+    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
         if (sc->active[ff]) {
             const double2 rho_old = sc->rho[ff];
             const double2 rho_new = make_double2(tot[0], tot[1]);
@@ -341,7 +385,7 @@ __global__ void __launch_bounds__(kBlock) k_start(double2* __restrict__ p, const
         v[1] += rz.y;
         v[2] += rv.x * rv.x + rv.y * rv.y;
     }
-    block_reduce_finalize<F, 3>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
+    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
         sc->rho[ff] = make_double2(tot[0], tot[1]);
         sc->rr[ff] = tot[2];
         sc->beta[ff] = make_double2(0.0, 0.0);
@@ -360,7 +404,7 @@ __global__ void __launch_bounds__(kBlock) k_resnorm(const double2* __restrict__ 
         const double dx = bv.x - qv.x, dy = bv.y - qv.y;
         v[0] += dx * dx + dy * dy;
     }
-    block_reduce_finalize<F, 1>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rr[ff] = tot[0]; });
+    block_reduce_finalize<F, 1, kBlock>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rr[ff] = tot[0]; });
 }
 
 // K7: pR[f][i] = sum_j w[i][j] x[node[i][j]][f]
@@ -403,18 +447,30 @@ __global__ void __launch_bounds__(kBlock) k_export(const double2* __restrict__ x
 // ------------------------------------------------------------------------------------------------
 template <int F>
 struct Launch {
-    static void spmv(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+    template <int BLOCK, int MINB>
+    static void spmv_cfg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
         const int64_t N = w->N;
-        const int rpb = kBlock / F;
-        int grid = (int)std::min<int64_t>((N + rpb - 1) / rpb, (int64_t)w->grid);
+        const int rpw = 32 / F;
+        const int64_t groups = (N + rpw - 1) / rpw;
+        const int64_t per_block = BLOCK / 32;
+        int grid = (int)std::min<int64_t>((groups + per_block - 1) / per_block, (int64_t)sys->num_sms * MINB);
         auto args = [&](auto kern) {
-            kern<<<grid, kBlock, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p, sys->ov_ptr.p, sys->ov_cg.p,
-                                                  sys->ov_val.p, w->coef.p, x, y, N, w->sc.p, (double*)w->partial.p);
+            kern<<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p, sys->ov_cg.p,
+                                                 sys->ov_val.p, w->coef.p, x, y, N, w->sc.p, (double*)w->partial.p);
         };
         if (dot) {
-            if (overlay) args(k_spmv<F, true, true>); else args(k_spmv<F, true, false>);
+            if (overlay) args(k_spmv<F, true, true, BLOCK, MINB>); else args(k_spmv<F, true, false, BLOCK, MINB>);
         } else {
-            if (overlay) args(k_spmv<F, false, true>); else args(k_spmv<F, false, false>);
+            if (overlay) args(k_spmv<F, false, true, BLOCK, MINB>); else args(k_spmv<F, false, false, BLOCK, MINB>);
+        }
+    }
+    static void spmv(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+        switch (w->spmv_cfg) {
+            case 1: spmv_cfg<kSpmvCfgs[1].block, kSpmvCfgs[1].per_sm>(sys, w, x, y, dot, overlay); break;
+            case 2: spmv_cfg<kSpmvCfgs[2].block, kSpmvCfgs[2].per_sm>(sys, w, x, y, dot, overlay); break;
+            case 3: spmv_cfg<kSpmvCfgs[3].block, kSpmvCfgs[3].per_sm>(sys, w, x, y, dot, overlay); break;
+            case 4: spmv_cfg<kSpmvCfgs[4].block, kSpmvCfgs[4].per_sm>(sys, w, x, y, dot, overlay); break;
+            default: spmv_cfg<kSpmvCfgs[0].block, kSpmvCfgs[0].per_sm>(sys, w, x, y, dot, overlay); break;
         }
     }
     static int egrid(SweepWork* w) {
@@ -478,6 +534,7 @@ static SweepWork* get_work(fdb_system* sys, int F) {
         w->N = sys->n_nodes;
         w->n_groups = sys->n_groups;
         w->grid = sys->num_sms * 8;
+        if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(4, atoi(e)));
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
@@ -688,6 +745,7 @@ int64_t spmv_algorithmic_bytes(fdb_system* sys, int F) {
     // indptr + (indices + H + Q) once + overlay + x read and y write per frequency
     const int64_t N = sys->n_nodes, Z = sys->vol.nnz;
     const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    // counted on the CSR sizes (the algorithm's bytes); the SELL-8 copy the kernel streams adds padding on top
     return 4 * (N + 1) + Z * 20 + (has_overlay ? 4 * (N + 1) + sys->n_ov * 16 : 0) + 32 * N * F;
 }
 

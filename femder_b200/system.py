@@ -135,6 +135,27 @@ class System:
             raise ValueError("H/Q value arrays must have nnz entries")
         check(self._lib.fdb_set_HQ(self._h, ptr(H), ptr(Q)))
 
+    def set_HQ(self, H, Q):
+        """Solver-only use: take H and Q as scipy sparse matrices (e.g. the reference's own csc arrays, complex64
+        with zero imaginary part for Tet4).  They are converted to CSR explicitly: the reference's float32
+        accumulation leaves H(r,c) != H(c,r) in the last bits, so its CSC arrays are not its CSR arrays."""
+        from scipy.sparse import csr_matrix
+        mats = []
+        for M in (H, Q):
+            M = csr_matrix(M)
+            if np.iscomplexobj(M.data):
+                if M.data.imag.any():
+                    raise ValueError("H and Q must be real (air-only path)")
+                M = M.real
+            M = M.astype(np.float64)
+            M.sort_indices()
+            mats.append(M)
+        Hr, Qr = mats
+        if not (np.array_equal(Hr.indptr, Qr.indptr) and np.array_equal(Hr.indices, Qr.indices)):
+            raise ValueError("H and Q must share one sparsity pattern")
+        self.set_pattern(Hr.indptr, Hr.indices)
+        self.set_HQ_values(Hr.data, Qr.data)
+
     def element_matrices(self):
         n2 = self.nper * self.nper
         He = np.empty((n2, self.n_elem), dtype=np.float64)

@@ -15,12 +15,7 @@ def _solver_system(H, Q, A_list):
     """Feed the solver the given matrices (e.g. the reference's own arrays) - assembly is not involved."""
     from femder_b200 import System
     s = System(0)
-    Hc = H.tocsc().astype(np.float64) if not np.iscomplexobj(H.data) else H.tocsc().real.astype(np.float64)
-    Qc = Q.tocsc().astype(np.float64) if not np.iscomplexobj(Q.data) else Q.tocsc().real.astype(np.float64)
-    Hc.sort_indices(); Qc.sort_indices()
-    assert np.array_equal(Hc.indices, Qc.indices)
-    s.set_pattern(Hc.indptr, Hc.indices)      # symmetric pattern: CSC arrays are the CSR arrays
-    s.set_HQ_values(Hc.data, Qc.data)
+    s.set_HQ(H, Q)
     s.set_surface_matrices(A_list)
     return s
 
