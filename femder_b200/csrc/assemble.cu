@@ -402,6 +402,9 @@ void build_sell(fdb_system* sys) {
     k_sell_fill<<<grid_for(S * 8, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p, N, S,
                                                                sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p);
     FDB_CUDA(cudaGetLastError());
+    sys->sell_off_host.resize(S + 1);
+    FDB_CUDA(cudaMemcpyAsync(sys->sell_off_host.data(), sys->sell_off.p, (S + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -106,6 +106,7 @@ struct fdb_system {
     fdb::DevBuf<int32_t> sell_off;   // [n_slices+1] in units of 8 entries
     fdb::DevBuf<int32_t> sell_idx;   // [sell_entries]
     fdb::DevBuf<double2> sell_hq;    // [sell_entries]
+    std::vector<int32_t> sell_off_host;
 
     // surface
     int64_t n_tri = 0;

@@ -50,7 +50,9 @@ struct SweepWork {
     int graph_iters = 0;
     int graph_F = 0;
     bool graph_overlay = false;
-    int spmv_cfg = 0;
+    int spmv_cfg = 0;             // FDB_SPMV_CFG: 0..3 bulk-copy pipeline shapes; 8..12 plain kernel launch shapes (tuning aid)
+    int tma_stage_entries[2] = {0, 0};
+    int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
 };
 
 void free_sweep_work(SweepWork* w) {
@@ -83,30 +85,12 @@ __device__ __forceinline__ double warp_sum_by_f(double v) {
     return v;
 }
 
-// Block partials -> partial[blockIdx.x][f][slot]; the last block to arrive adds the partials of all blocks
-// in a fixed order (deterministic) and calls `fin(f, totals)` from one thread per f.
+// The last block to arrive adds the per-block partials partial[b][f][slot] of all blocks in a fixed order
+// (deterministic) and calls `fin(f, totals)` from one thread per f.  Call with the block's partials already
+// written by threads that then reach this point (all threads of the block must call it).
 template <int F, int NV, int BLOCK, typename Fin>
-__device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
-                                                      unsigned int* __restrict__ ticket, Fin fin) {
-    __shared__ double s_red[BLOCK / 32][kMaxF][NV];
+__device__ __forceinline__ void finalize_last_block(double* __restrict__ partial, unsigned int* __restrict__ ticket, Fin fin) {
     __shared__ bool s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double w[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) w[i] = warp_sum_by_f<F>(v[i]);
-    if (lane < F) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s_red[warp][lane][i] = w[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < F) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double s = 0;
-            for (int k = 0; k < BLOCK / 32; ++k) s += s_red[k][threadIdx.x][i];
-            partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
-        }
-    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -122,9 +106,11 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0;
-    for (int b = j; b < (int)gridDim.x; b += TPF) {
+    if (j < TPF) {
+        for (int b = j; b < (int)gridDim.x; b += TPF) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
+            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
+        }
     }
     __shared__ double s_fin[BLOCK][NV];
 #pragma unroll
@@ -143,6 +129,31 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
     }
 }
 
+// lanes = (.., f): per-thread values of frequency f = threadIdx.x % F -> block partial -> finalize
+template <int F, int NV, int BLOCK, typename Fin>
+__device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
+                                                      unsigned int* __restrict__ ticket, Fin fin) {
+    __shared__ double s_red[BLOCK / 32][kMaxF][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = warp_sum_by_f<F>(v[i]);
+    if (lane < F) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s_red[warp][lane][i] = w[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < F) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0;
+            for (int k = 0; k < BLOCK / 32; ++k) s += s_red[k][threadIdx.x][i];
+            partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
+        }
+    }
+    finalize_last_block<F, NV, BLOCK>(partial, ticket, fin);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: y[row][f] = sum_k (H_k - w2_f Q_k) x[col_k][f] + sum_ov (coef[g][f] * A_ov) x[col_ov][f]
 //
@@ -155,7 +166,6 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
 // launch shapes (threads per block, resident blocks per SM); FDB_SPMV_CFG picks one at run time (tuning aid)
 struct SpmvCfg { int block, per_sm; };
 constexpr SpmvCfg kSpmvCfgs[] = {{512, 2}, {512, 3}, {256, 4}, {1024, 1}, {256, 6}};
-constexpr int kSpmvMaxBlock = 1024;
 
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 v;
@@ -237,6 +247,220 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
     }
     if (DOT) {
         block_reduce_finalize<F, 2, BLOCK>(dot, partial, &sc->ticket[0], [&](int ff, const double* tot) {
+            sc->pq[ff] = make_double2(tot[0], tot[1]);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 (bulk-copy pipeline): same arithmetic as k_spmv.  A block owns a contiguous range of tiles (TS slices =
+// 8*TS rows).  The only dependent chain in an SpMV is column index -> x gather, so the column indices are what
+// gets staged: a producer warp issues one 1-D bulk copy per tile (cp.async.bulk, the tile's indices are
+// contiguous in the SELL-8 array) into an NST-deep shared-memory ring, completion on an mbarrier, several
+// tiles ahead of the consumers.  NWARP consumer warps wait on the "full" barrier, read indices from shared
+// memory, gather x through L1 with 256-bit loads, stream (H,Q) straight from HBM with L1 bypassed (no
+// dependency, issued with the gathers) and release the stage on the "empty" barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct __align__(32) d4 { double a, b, c, d; };   // two complex numbers = one 256-bit access (LDG/STG.E.256 on sm_100)
+__device__ __forceinline__ d4 ld256(const double2* p) {
+    d4 v;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st256(double2* p, const d4& v) { *reinterpret_cast<d4*>(p) = v; }
+// Scheduling fence: everything loaded into v[0..3] is "redefined" here, so the compiler cannot start consuming
+// the first gather before the last one of the batch has been issued (keeps the whole batch in flight).
+__device__ __forceinline__ void hold4(d4* v) {
+    asm volatile("" : "+d"(v[0].a), "+d"(v[0].b), "+d"(v[0].c), "+d"(v[0].d), "+d"(v[1].a), "+d"(v[1].b), "+d"(v[1].c),
+                 "+d"(v[1].d), "+d"(v[2].a), "+d"(v[2].b), "+d"(v[2].c), "+d"(v[2].d), "+d"(v[3].a), "+d"(v[3].b),
+                 "+d"(v[3].c), "+d"(v[3].d));
+}
+
+// lanes = (row in warp, frequency pair): F/2 lanes per row, 64/F rows per warp; each lane carries two
+// frequencies, so one 256-bit load per lane gathers x[col][0..F) of a row as one contiguous 16*F-byte segment.
+template <int F, bool DOT, bool OVERLAY, int NWARP, int TS, int NST, int KB>
+__global__ void __launch_bounds__((NWARP + 1) * 32)
+k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
+           const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
+           const double2* __restrict__ coef, const double2* __restrict__ x, double2* __restrict__ y, int64_t n_rows,
+           int64_t n_slices, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int BLOCK = (NWARP + 1) * 32;
+    constexpr int LPR = F / 2;          // lanes per row
+    constexpr int RPW = 32 / LPR;       // rows per warp
+    constexpr int NPASS = (TS * 8 + NWARP * RPW - 1) / (NWARP * RPW);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* s_hq = reinterpret_cast<double2*>(smem_raw);                                                    // [NST][stage_entries]
+    int32_t* s_idx = reinterpret_cast<int32_t*>(smem_raw + (size_t)NST * stage_entries * sizeof(double2));   // [NST][stage_entries]
+    __shared__ uint64_t full_bar[NST], empty_bar[NST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], NWARP);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n_tiles = (n_slices + TS - 1) / TS;
+    const int64_t tpb = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tpb;
+    const int64_t t1 = min(t0 + tpb, n_tiles);
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+
+    if (warp == NWARP) {
+        // ===== producer warp: one elected lane streams the tiles of this block into the ring =====
+        if (lane == 0) {
+            int i = 0;
+            for (int64_t t = t0; t < t1; ++t, ++i) {
+                const int st = i % NST;
+                const uint32_t ph = (uint32_t)((i / NST) & 1);
+                mbar_wait(&empty_bar[st], ph ^ 1u);
+                const int64_t sl0 = t * TS, sl1 = min(sl0 + TS, n_slices);
+                const int64_t e0 = (int64_t)sell_off[sl0] * 8, e1 = (int64_t)sell_off[sl1] * 8;
+                const uint32_t n = (uint32_t)(e1 - e0);
+                if (n) {
+                    mbar_expect_tx(&full_bar[st], n * 20u);
+                    bulk_g2s(s_hq + (size_t)st * stage_entries, sell_hq + e0, n * 16u, &full_bar[st]);
+                    bulk_g2s(s_idx + (size_t)st * stage_entries, sell_idx + e0, n * 4u, &full_bar[st]);
+                } else {
+                    mbar_arrive(&full_bar[st]);
+                }
+            }
+        }
+    } else {
+        // ===== consumer warps =====
+        const int fq = lane % LPR;
+        const int rl = lane / LPR;
+        const double w2a = sc->w2[2 * fq], w2b = sc->w2[2 * fq + 1];
+        const double2* xq = x + 2 * fq;
+        int i = 0;
+        for (int64_t t = t0; t < t1; ++t, ++i) {
+            const int st = i % NST;
+            const uint32_t ph = (uint32_t)((i / NST) & 1);
+            const int64_t row0 = t * TS * 8;
+            const int tile_off = sell_off[t * TS];
+            int off_r[NPASS], wid_r[NPASS], ob_r[NPASS], oe_r[NPASS];
+#pragma unroll
+            for (int np = 0; np < NPASS; ++np) {
+                const int64_t row = row0 + (np * NWARP + warp) * RPW + rl;
+                off_r[np] = 0; wid_r[np] = 0; ob_r[np] = 0; oe_r[np] = 0;
+                if ((np * NWARP + warp) * RPW + rl < TS * 8 && row < n_rows) {
+                    const int64_t slice = row >> 3;
+                    const int o = sell_off[slice];
+                    off_r[np] = o - tile_off;
+                    wid_r[np] = sell_off[slice + 1] - o;
+                    if (OVERLAY) { ob_r[np] = ov_ptr[row]; oe_r[np] = ov_ptr[row + 1]; }
+                }
+            }
+            mbar_wait(&full_bar[st], ph);
+            const double2* thq = s_hq + (size_t)st * stage_entries;
+            const int32_t* tix = s_idx + (size_t)st * stage_entries;
+#pragma unroll
+            for (int np = 0; np < NPASS; ++np) {
+                const int rin = (np * NWARP + warp) * RPW + rl;
+                const int64_t row = row0 + rin;
+                if (rin >= TS * 8 || row >= n_rows) continue;
+                const int base = off_r[np] * 8 + (int)(row & 7);
+                const int width = wid_r[np];
+                double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;   // two frequencies
+                // software pipeline of depth KB: the gather of entry k+KB is issued as entry k is consumed, so
+                // KB-1 256-bit gathers per lane stay in flight whatever the compiler's schedule
+                d4 xv[KB];
+#pragma unroll
+                for (int u = 0; u < KB; ++u) {
+                    const int c = (u < width) ? tix[base + u * 8] : (int)row;
+                    xv[u] = ld256(xq + (int64_t)c * F);
+                }
+                for (int k0 = 0; k0 < width; k0 += KB) {
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) {
+                        const int k = k0 + u;
+                        if (k < width) {
+                            const double2 m = thq[base + k * 8];
+                            const double ga = m.x - w2a * m.y, gb = m.x - w2b * m.y;
+                            ar += ga * xv[u].a; ai += ga * xv[u].b;
+                            br += gb * xv[u].c; bi += gb * xv[u].d;
+                        }
+                        if (k + KB < width) {
+                            const int c = tix[base + (k + KB) * 8];
+                            xv[u] = ld256(xq + (int64_t)c * F);
+                        }
+                    }
+                }
+                if (OVERLAY) {
+                    for (int o = ob_r[np]; o < oe_r[np]; ++o) {
+                        const int2 cg = ov_cg[o];
+                        const double a = ov_val[o];
+                        const double2 ca = coef[cg.y * F + 2 * fq], cb = coef[cg.y * F + 2 * fq + 1];
+                        const d4 xv = ld256(xq + (int64_t)cg.x * F);
+                        const double2 ta = cmul(make_double2(ca.x * a, ca.y * a), make_double2(xv.a, xv.b));
+                        const double2 tb = cmul(make_double2(cb.x * a, cb.y * a), make_double2(xv.c, xv.d));
+                        ar += ta.x; ai += ta.y; br += tb.x; bi += tb.y;
+                    }
+                }
+                d4 out; out.a = ar; out.b = ai; out.c = br; out.d = bi;
+                st256(y + row * F + 2 * fq, out);
+                if (DOT) {
+                    const d4 xv = ld256(xq + row * F);
+                    dot[0] += xv.a * ar - xv.b * ai; dot[1] += xv.a * ai + xv.b * ar;
+                    dot[2] += xv.c * br - xv.d * bi; dot[3] += xv.c * bi + xv.d * br;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+    }
+    if (DOT) {
+        // lanes sharing fq hold the two frequencies 2fq, 2fq+1
+        __shared__ double s_red[NWARP][kMaxF][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 16; o >= LPR; o >>= 1) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+        }
+        if (warp < NWARP && lane < LPR) {
+            s_red[warp][2 * lane][0] = dot[0]; s_red[warp][2 * lane][1] = dot[1];
+            s_red[warp][2 * lane + 1][0] = dot[2]; s_red[warp][2 * lane + 1][1] = dot[3];
+        }
+        __syncthreads();
+        if (threadIdx.x < F) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double sum = 0;
+                for (int k = 0; k < NWARP; ++k) sum += s_red[k][threadIdx.x][i];
+                partial[((int64_t)blockIdx.x * F + threadIdx.x) * 2 + i] = sum;
+            }
+        }
+        finalize_last_block<F, 2, BLOCK>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
             sc->pq[ff] = make_double2(tot[0], tot[1]);
         });
     }
@@ -464,8 +688,60 @@ struct Launch {
             if (overlay) args(k_spmv<F, false, true, BLOCK, MINB>); else args(k_spmv<F, false, false, BLOCK, MINB>);
         }
     }
+    template <int NWARP, int TS, int NST, int KB>
+    static bool spmv_tma(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+        const int64_t N = w->N, S = sys->n_slices;
+        const int64_t n_tiles = (S + TS - 1) / TS;
+        // largest tile (entries) decides the stage size
+        static_assert(NWARP >= 1 && (NWARP + 1) * 32 <= 1024, "block too large");
+        if (w->tma_stage_entries[TS == 8 ? 0 : 1] == 0) {
+            int64_t mx = 0;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int64_t a0 = sys->sell_off_host[t * TS], a1 = sys->sell_off_host[std::min<int64_t>((t + 1) * TS, S)];
+                mx = std::max(mx, (a1 - a0) * 8);
+            }
+            w->tma_stage_entries[TS == 8 ? 0 : 1] = (int)std::max<int64_t>(mx, 8);
+        }
+        const int stage_entries = w->tma_stage_entries[TS == 8 ? 0 : 1];
+        const size_t smem = (size_t)NST * stage_entries * 20;
+        if (smem > 100 * 1024) return false;  // rows too long for this tile shape: use the plain kernel
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / ((NWARP + 1) * 32), (150 * 1024) / (smem + 8192)));
+        if (w->spmv_bps > 0) per_sm = std::min(per_sm, w->spmv_bps);
+        int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sys->num_sms * per_sm);
+        auto launch = [&](auto kern) {
+            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, (NWARP + 1) * 32, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p,
+                                                               sys->ov_cg.p, sys->ov_val.p, w->coef.p, x, y, N, S, stage_entries,
+                                                               w->sc.p, (double*)w->partial.p);
+        };
+        if (dot) {
+            if (overlay) launch(k_spmv_tma<F, true, true, NWARP, TS, NST, KB>); else launch(k_spmv_tma<F, true, false, NWARP, TS, NST, KB>);
+        } else {
+            if (overlay) launch(k_spmv_tma<F, false, true, NWARP, TS, NST, KB>); else launch(k_spmv_tma<F, false, false, NWARP, TS, NST, KB>);
+        }
+        return true;
+    }
     static void spmv(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
-        switch (w->spmv_cfg) {
+        if constexpr (F >= 2) {
+            if (w->spmv_cfg < 8) {
+                // rows per tile = 8*TS; a warp covers 64/F rows per pass
+                constexpr int RPW = 64 / F;
+                constexpr int W8 = (64 / RPW < 16) ? 64 / RPW : 16;     // consumer warps for an 8-slice tile
+                constexpr int W16 = (128 / RPW < 16) ? 128 / RPW : 16;  // ... for a 16-slice tile
+                bool ok;
+                switch (w->spmv_cfg) {
+                    case 1: ok = spmv_tma<W8, 8, 2, 4>(sys, w, x, y, dot, overlay); break;
+                    case 2: ok = spmv_tma<W8, 8, 3, 8>(sys, w, x, y, dot, overlay); break;
+                    case 3: ok = spmv_tma<W8, 8, 2, 8>(sys, w, x, y, dot, overlay); break;
+                    default: ok = spmv_tma<W16, 16, 2, 8>(sys, w, x, y, dot, overlay); break;  // measured best at F = 4, 8
+                }
+                if (ok) return;
+            }
+        }
+        spmv_ldg(sys, w, x, y, dot, overlay);
+    }
+    static void spmv_ldg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+        switch (w->spmv_cfg - 8) {
             case 1: spmv_cfg<kSpmvCfgs[1].block, kSpmvCfgs[1].per_sm>(sys, w, x, y, dot, overlay); break;
             case 2: spmv_cfg<kSpmvCfgs[2].block, kSpmvCfgs[2].per_sm>(sys, w, x, y, dot, overlay); break;
             case 3: spmv_cfg<kSpmvCfgs[3].block, kSpmvCfgs[3].per_sm>(sys, w, x, y, dot, overlay); break;
@@ -534,7 +810,8 @@ static SweepWork* get_work(fdb_system* sys, int F) {
         w->N = sys->n_nodes;
         w->n_groups = sys->n_groups;
         w->grid = sys->num_sms * 8;
-        if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(4, atoi(e)));
+        if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
+        if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
