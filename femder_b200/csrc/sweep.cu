@@ -29,8 +29,10 @@ struct __align__(16) Scalars {
     double bb[kMaxF];      // ||b||^2
     double w2[kMaxF];      // omega^2
     double2 rhs_scale[kMaxF];  // -1j*omega
+    double rt[kMaxF];      // ||b - G x||^2 of the returned solution (true residual check)
     int active[kMaxF];
     int iters[kMaxF];
+    int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
     double tol2;
     unsigned int ticket[4];
 };
@@ -40,7 +42,7 @@ struct SweepWork {
     int64_t N = 0;
     int n_groups = 0;
     int grid = 0;
-    DevBuf<double2> x, r, p, q, dinv;  // [N][F]
+    DevBuf<double2> x, r, p, q, dinv, tmp;  // [N][F]
     DevBuf<double2> coef;              // [n_groups][F]  1j*omega*mu
     DevBuf<double2> partial;           // [grid][F][2]
     DevBuf<Scalars> sc;
@@ -470,22 +472,38 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
 // K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
 // finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
 // ------------------------------------------------------------------------------------------------
-template <int F>
+// Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the batch): the diagonal is rebuilt from
+// (H_rr, Q_rr) - 16 bytes per ROW instead of 16 bytes per (row, frequency); otherwise the precomputed 1/diag is read.
+template <int F, bool ONFLY>
+__device__ __forceinline__ double2 jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                                int64_t i, double w2, double2 rv) {
+    if (ONFLY) {
+        const double2 d = __ldg(&diag_hq[i / F]);
+        const double g = d.x - w2 * d.y;
+        const double inv = (g == 0.0) ? 1.0 : 1.0 / g;
+        return make_double2(rv.x * inv, rv.y * inv);
+    } else {
+        return cmul(dinv[i], rv);
+    }
+}
+
+template <int F, bool ONFLY>
 __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, double2* __restrict__ r,
                                                     const double2* __restrict__ p, const double2* __restrict__ q,
-                                                    const double2* __restrict__ dinv, int64_t n_elems,
-                                                    Scalars* __restrict__ sc, double* __restrict__ partial) {
+                                                    const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                                    int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
     const int f = threadIdx.x % F;
     const bool act = sc->active[f] != 0;
+    const double w2 = sc->w2[f];
     double2 alpha = make_double2(0.0, 0.0);
     if (act) {
         const double2 pq = sc->pq[f];
         if (pq.x != 0.0 || pq.y != 0.0) alpha = cdiv(sc->rho[f], pq);
     }
     double v[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        double2 rv = r[i];
-        if (act) {
+    if (act) {
+        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+            double2 rv = r[i];
             const double2 pv = p[i], qv = q[i];
             double2 xv = x[i];
             const double2 ap = cmul(alpha, pv), aq = cmul(alpha, qv);
@@ -493,12 +511,12 @@ __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, doub
             rv.x -= aq.x; rv.y -= aq.y;
             x[i] = xv;
             r[i] = rv;
+            const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, rv);
+            const double2 rz = cmul(rv, z);
+            v[0] += rz.x;
+            v[1] += rz.y;
+            v[2] += rv.x * rv.x + rv.y * rv.y;
         }
-        const double2 z = cmul(dinv[i], rv);
-        const double2 rz = cmul(rv, z);
-        v[0] += rz.x;
-        v[1] += rz.y;
-        v[2] += rv.x * rv.x + rv.y * rv.y;
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
         if (sc->active[ff]) {
@@ -518,23 +536,25 @@ __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, doub
     });
 }
 
-// K6b: p = dinv*r + beta p
-template <int F>
+// K6b: p = z + beta p
+template <int F, bool ONFLY>
 __global__ void __launch_bounds__(kBlock) k_pupdate(double2* __restrict__ p, const double2* __restrict__ r,
-                                                     const double2* __restrict__ dinv, int64_t n_elems,
-                                                     const Scalars* __restrict__ sc) {
+                                                     const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                                     int64_t n_elems, const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
     const double2 beta = sc->beta[f];
+    const double w2 = sc->w2[f];
     if (!sc->active[f]) return;  // frozen frequency: p is not used while alpha = 0
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const double2 z = cmul(dinv[i], r[i]);
+        const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
         const double2 bp = cmul(beta, p[i]);
         p[i] = make_double2(z.x + bp.x, z.y + bp.y);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// set-up kernels for one batch
+// slot (re)load kernels: a batch slot whose frequency converged is reloaded with the next frequency of the
+// sweep while the other slots keep iterating ("continuous batching").  These touch only slots with reset[f] != 0.
 // ------------------------------------------------------------------------------------------------
 // dinv[row][f] = 1 / (H_rr - w2_f Q_rr + sum_ov,col==row coef[g][f] A)
 template <int F>
@@ -545,7 +565,7 @@ __global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ d
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t row = i / F;
     const int f = (int)(i % F);
-    if (row >= n_rows) return;
+    if (row >= n_rows || !sc->reset[f]) return;
     const double2 d = diag_hq[row];
     double2 g = make_double2(d.x - sc->w2[f] * d.y, 0.0);
     if (overlay) {
@@ -563,29 +583,35 @@ __global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ d
     dinv[i] = zero ? make_double2(1.0, 0.0) : cdiv(make_double2(1.0, 0.0), g);
 }
 
-// r[node][f] = rhs_scale[f] * q_s   (one thread per (source, f); sources are unique nodes)
+// reset slots: r = 0, and x = 0 unless the previous solution of the slot is kept as the starting guess
 template <int F>
-__global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, int n_src,
-                          const Scalars* __restrict__ sc, double2* __restrict__ r) {
+__global__ void __launch_bounds__(kBlock) k_slot_clear(double2* __restrict__ x, double2* __restrict__ r, bool keep_x,
+                                                        int64_t n_elems, const Scalars* __restrict__ sc) {
+    const int f = threadIdx.x % F;
+    if (!sc->reset[f]) return;
+    const double2 z = make_double2(0.0, 0.0);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        r[i] = z;
+        if (!keep_x) x[i] = z;
+    }
+}
+
+// dst[node][f] = rhs_scale[f] * q_s   (one thread per (source, f); sources are unique nodes); ALL: every slot
+template <int F>
+__global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, int n_src, bool all,
+                          const Scalars* __restrict__ sc, double2* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_src * F) return;
     const int s = i / F, f = i % F;
-    r[(int64_t)src_nodes[s] * F + f] = cmul(sc->rhs_scale[f], src_q[s]);
+    if (all || sc->reset[f]) dst[(int64_t)src_nodes[s] * F + f] = cmul(sc->rhs_scale[f], src_q[s]);
 }
 
-// warm start: x[row][f] = x[row][F-1] for every f
+// reset slots: r = r - q    (r holds b on entry; q = G x0)
 template <int F>
-__global__ void k_broadcast_last(double2* __restrict__ x, int64_t n_rows, int src_slot) {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n_rows * F) return;
-    const int64_t row = i / F;
-    const int f = (int)(i % F);
-    const double2 v = x[row * F + src_slot];
-    if (f != src_slot) x[i] = v;
-}
-
-// r = r - q    (r holds b on entry; q = G x0)
-__global__ void k_sub(double2* __restrict__ r, const double2* __restrict__ q, int64_t n) {
+__global__ void __launch_bounds__(kBlock) k_sub(double2* __restrict__ r, const double2* __restrict__ q, int64_t n,
+                                                 const Scalars* __restrict__ sc) {
+    const int f = threadIdx.x % F;
+    if (!sc->reset[f]) return;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
         double2 a = r[i];
         const double2 b = q[i];
@@ -594,31 +620,39 @@ __global__ void k_sub(double2* __restrict__ r, const double2* __restrict__ q, in
     }
 }
 
-// p = dinv r ; rho = r^T p ; rr = ||r||^2 ; activate every frequency whose residual is above tolerance
-template <int F>
+// reset slots: p = z ; rho = r^T z ; rr = ||r||^2 ; activate the slot if its residual is above tolerance
+template <int F, bool ONFLY>
 __global__ void __launch_bounds__(kBlock) k_start(double2* __restrict__ p, const double2* __restrict__ r,
-                                                   const double2* __restrict__ dinv, int64_t n_elems, int n_live,
-                                                   Scalars* __restrict__ sc, double* __restrict__ partial) {
+                                                   const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                                   int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    const int f = threadIdx.x % F;
+    const bool rs = sc->reset[f] != 0;
+    const double w2 = sc->w2[f];
     double v[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const double2 rv = r[i];
-        const double2 z = cmul(dinv[i], rv);
-        p[i] = z;
-        const double2 rz = cmul(rv, z);
-        v[0] += rz.x;
-        v[1] += rz.y;
-        v[2] += rv.x * rv.x + rv.y * rv.y;
+    if (rs) {
+        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+            const double2 rv = r[i];
+            const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, rv);
+            p[i] = z;
+            const double2 rz = cmul(rv, z);
+            v[0] += rz.x;
+            v[1] += rz.y;
+            v[2] += rv.x * rv.x + rv.y * rv.y;
+        }
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
+        if (!sc->reset[ff]) return;
         sc->rho[ff] = make_double2(tot[0], tot[1]);
         sc->rr[ff] = tot[2];
         sc->beta[ff] = make_double2(0.0, 0.0);
+        sc->pq[ff] = make_double2(0.0, 0.0);
         sc->iters[ff] = 0;
-        sc->active[ff] = (ff < n_live && tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
+        sc->active[ff] = (tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
+        sc->reset[ff] = 0;
     });
 }
 
-// true residual norm: rr = ||b - q||^2 with b = r_buf (rebuilt rhs), q = G x
+// true residual norm of what is returned: rt = ||b - q||^2 with b rebuilt, q = G x
 template <int F>
 __global__ void __launch_bounds__(kBlock) k_resnorm(const double2* __restrict__ b, const double2* __restrict__ q,
                                                      int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
@@ -628,7 +662,7 @@ __global__ void __launch_bounds__(kBlock) k_resnorm(const double2* __restrict__ 
         const double dx = bv.x - qv.x, dy = bv.y - qv.y;
         v[0] += dx * dx + dy * dy;
     }
-    block_reduce_finalize<F, 1, kBlock>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rr[ff] = tot[0]; });
+    block_reduce_finalize<F, 1, kBlock>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rt[ff] = tot[0]; });
 }
 
 // K7: pR[f][i] = sum_j w[i][j] x[node[i][j]][f]
@@ -755,26 +789,50 @@ struct Launch {
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
         const int64_t ne = w->N * F;
         spmv(sys, w, w->p.p, w->q.p, true, overlay);
-        k_update<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, ne, w->sc.p,
-                                                          (double*)w->partial.p);
-        k_pupdate<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, ne, w->sc.p);
+        if (overlay) {
+            k_update<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, sys->diag_hq.p, ne,
+                                                                    w->sc.p, (double*)w->partial.p);
+            k_pupdate<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+        } else {
+            k_update<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, sys->diag_hq.p, ne,
+                                                                   w->sc.p, (double*)w->partial.p);
+            k_pupdate<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+        }
     }
-    static void jacobi(fdb_system* sys, SweepWork* w, bool overlay) {
-        k_jacobi<F><<<grid_for(w->N * F, kBlock), kBlock, 0, sys->stream>>>(sys->diag_hq.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
-                                                                         w->coef.p, overlay, w->N, w->sc.p, w->dinv.p);
+    // (re)load the slots flagged in sc.reset; returns the number of kernels launched
+    static void reload(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+        const int64_t ne = w->N * F;
+        int nk = 0;
+        if (overlay) {
+            k_jacobi<F><<<grid_for(ne, kBlock), kBlock, 0, sys->stream>>>(sys->diag_hq.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                                                                       w->coef.p, overlay, w->N, w->sc.p, w->dinv.p);
+            ++nk;
+        }
+        k_slot_clear<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, keep_x, ne, w->sc.p);
+        ++nk;
+        if (n_src) {
+            k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, false, w->sc.p, w->r.p);
+            ++nk;
+        }
+        if (keep_x) {
+            spmv(sys, w, w->x.p, w->q.p, false, overlay);
+            k_sub<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->r.p, w->q.p, ne, w->sc.p);
+            nk += 2;
+        }
+        if (overlay)
+            k_start<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+        else
+            k_start<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+        *n_launched = nk + 1;
     }
-    static void set_rhs(fdb_system* sys, SweepWork* w, const int32_t* nodes, const double2* q, int n_src, double2* dst) {
-        FDB_CUDA(cudaMemsetAsync(dst, 0, (size_t)w->N * F * sizeof(double2), sys->stream));
-        if (n_src) k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, w->sc.p, dst);
-    }
-    static void broadcast_last(fdb_system* sys, SweepWork* w, int slot) {
-        k_broadcast_last<F><<<grid_for(w->N * F, kBlock), kBlock, 0, sys->stream>>>(w->x.p, w->N, slot);
-    }
-    static void start(fdb_system* sys, SweepWork* w, int n_live) {
-        k_start<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, w->N * F, n_live, w->sc.p, (double*)w->partial.p);
-    }
-    static void resnorm(fdb_system* sys, SweepWork* w, const double2* b, const double2* q) {
-        k_resnorm<F><<<egrid(w), kBlock, 0, sys->stream>>>(b, q, w->N * F, w->sc.p, (double*)w->partial.p);
+    // rt[f] = ||b_f - G_f x_f||^2 for every slot (q and tmp are free between iterations)
+    static void true_residual(fdb_system* sys, SweepWork* w, bool overlay, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+        const int64_t ne = w->N * F;
+        spmv(sys, w, w->x.p, w->q.p, false, overlay);
+        FDB_CUDA(cudaMemsetAsync(w->tmp.p, 0, (size_t)ne * sizeof(double2), sys->stream));
+        if (n_src) k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, true, w->sc.p, w->tmp.p);
+        k_resnorm<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->tmp.p, w->q.p, ne, w->sc.p, (double*)w->partial.p);
+        *n_launched = 3;
     }
     static void gather(fdb_system* sys, SweepWork* w, const int32_t* nodes, const double* wts, int n_rcv) {
         k_gather_rcv<F><<<grid_for((int64_t)n_rcv * F, 128), 128, 0, sys->stream>>>(w->x.p, nodes, wts, n_rcv, w->rcv_out.p);
@@ -813,7 +871,7 @@ static SweepWork* get_work(fdb_system* sys, int F) {
         if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         const size_t n = (size_t)w->N * F;
-        w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n);
+        w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
         w->partial.alloc((size_t)w->grid * F * 2);  // 3 doubles per (block, f) fit in 2 double2
         w->sc.alloc(1);
@@ -830,25 +888,22 @@ static SweepWork* get_work(fdb_system* sys, int F) {
     return w;
 }
 
-static void load_batch_scalars(fdb_system* sys, SweepWork* w, int F, int n_live, const double* omega, const double* mu_batch /* [n_groups][F] complex */,
-                               double tol, double src_norm2) {
-    Scalars h;
-    memset(&h, 0, sizeof(h));
-    std::vector<double2> coef((size_t)std::max(1, w->n_groups) * F, make_double2(0.0, 0.0));
-    for (int f = 0; f < F; ++f) {
-        const double om = omega[std::min(f, n_live - 1)];
-        h.w2[f] = om * om;
-        h.rhs_scale[f] = make_double2(0.0, -om);
-        h.bb[f] = om * om * src_norm2;
-        for (int g = 0; g < w->n_groups; ++g) {
-            const double mr = mu_batch[((size_t)g * F + f) * 2], mi = mu_batch[((size_t)g * F + f) * 2 + 1];
-            coef[(size_t)g * F + f] = make_double2(-om * mi, om * mr);  // 1j*om*(mr + 1j*mi)
-        }
+// host mirror of one slot's frequency-dependent constants
+static void fill_slot(Scalars& h, std::vector<double2>& coef, int F, int n_groups, int slot, double om, const double* mu /* [n_groups] complex */,
+                      double src_norm2) {
+    h.w2[slot] = om * om;
+    h.rhs_scale[slot] = make_double2(0.0, -om);   // b = -1j*w*q
+    h.bb[slot] = om * om * src_norm2;
+    for (int g = 0; g < n_groups; ++g) {
+        const double mr = mu ? mu[2 * g] : 0.0, mi = mu ? mu[2 * g + 1] : 0.0;
+        coef[(size_t)g * F + slot] = make_double2(-om * mi, om * mr);  // 1j*om*(mr + 1j*mi)
     }
-    h.tol2 = tol * tol;
+}
+
+static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, const std::vector<double2>& coef) {
     FDB_CUDA(cudaMemcpyAsync(w->sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, sys->stream));
     FDB_CUDA(cudaMemcpyAsync(w->coef.p, coef.data(), coef.size() * sizeof(double2), cudaMemcpyHostToDevice, sys->stream));
-    FDB_CUDA(cudaStreamSynchronize(sys->stream));  // host buffers go out of scope
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));  // pageable host buffers: be done before they change
 }
 
 static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool overlay) {
@@ -870,6 +925,8 @@ static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool o
     w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay;
 }
 
+// The sweep.  F slots iterate together; a slot whose frequency has converged is reloaded with the next frequency
+// of the list while the others keep going, so no bandwidth is spent on finished systems.
 void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res) {
     FDB_REQUIRE(prm && res, "null argument");
     FDB_REQUIRE(prm->n_freq >= 0 && prm->n_src >= 0 && prm->n_rcv >= 0, "negative count");
@@ -879,14 +936,21 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     const int64_t N = w->N;
     const int ng = sys->n_groups;
     FDB_REQUIRE(ng == 0 || prm->mu != nullptr, "mu is required when the system has boundary groups");
-    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0;
     const int check_every = std::max(1, prm->check_every);
+    const int64_t nf = prm->n_freq;
     cudaStream_t s = sys->stream;
 
     // inputs to the host (they may be device pointers)
-    std::vector<double> omega(prm->n_freq), mu((size_t)ng * prm->n_freq * 2);
-    if (prm->n_freq) FDB_CUDA(cudaMemcpy(omega.data(), prm->omega, omega.size() * sizeof(double), cudaMemcpyDefault));
+    std::vector<double> omega(nf), mu((size_t)ng * nf * 2);
+    if (nf) FDB_CUDA(cudaMemcpy(omega.data(), prm->omega, omega.size() * sizeof(double), cudaMemcpyDefault));
     if (!mu.empty()) FDB_CUDA(cudaMemcpy(mu.data(), prm->mu, mu.size() * sizeof(double), cudaMemcpyDefault));
+    // a sweep whose admittances are all exactly zero (rigid walls) has no boundary term: the overlay is skipped
+    bool overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0;
+    if (overlay) {
+        bool any = false;
+        for (double v : mu) any = any || (v != 0.0);
+        overlay = any;
+    }
     std::vector<int32_t> src_nodes(prm->n_src);
     std::vector<double2> src_q(prm->n_src);
     if (prm->n_src) {
@@ -933,53 +997,81 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     FDB_CUDA(cudaEventRecord(ev0, s));
     int64_t n_spmv = 0, n_kernels = 0;
     int n_unconv = 0;
-    bool have_prev = false;
-    std::vector<double> mu_batch((size_t)std::max(1, ng) * F * 2);
-    std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
 
-    for (int64_t f0 = 0; f0 < prm->n_freq; f0 += F) {
-        const int n_live = (int)std::min<int64_t>(F, prm->n_freq - f0);
-        for (int g = 0; g < ng; ++g)
-            for (int f = 0; f < F; ++f) {
-                const int64_t src = f0 + std::min(f, n_live - 1);
-                mu_batch[((size_t)g * F + f) * 2] = mu[((size_t)g * prm->n_freq + src) * 2];
-                mu_batch[((size_t)g * F + f) * 2 + 1] = mu[((size_t)g * prm->n_freq + src) * 2 + 1];
-            }
-        load_batch_scalars(sys, w, F, n_live, omega.data() + f0, mu_batch.data(), prm->tol, src_norm2);
-        FDB_DISPATCH_F(F, jacobi(sys, w, has_overlay));
-        FDB_DISPATCH_F(F, set_rhs(sys, w, d_src_nodes.p, d_src_q.p, n_src, w->r.p));
-        n_kernels += 2;
-        if (prm->warm_start && have_prev) {
-            FDB_DISPATCH_F(F, broadcast_last(sys, w, F - 1));
-            FDB_DISPATCH_F(F, spmv(sys, w, w->x.p, w->q.p, false, has_overlay));
-            k_sub<<<std::min<int64_t>(grid_for(N * F, kBlock), w->grid), kBlock, 0, s>>>(w->r.p, w->q.p, N * F);
-            n_spmv += 1; n_kernels += 3;
-        } else {
-            w->x.zero(s);
+    Scalars h;
+    memset(&h, 0, sizeof(h));
+    h.tol2 = prm->tol * prm->tol;
+    std::vector<double2> coef((size_t)std::max(1, ng) * F, make_double2(0.0, 0.0));
+    std::vector<double> mu_f((size_t)std::max(1, ng) * 2);
+    std::vector<int64_t> slot_freq(F, -1);
+    std::vector<char> slot_used(F, 0);   // has the slot held a frequency before (its x is a usable starting guess)
+    std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
+    int64_t next = 0;
+    int n_busy = 0;
+
+    auto assign = [&](int slot) {
+        if (next >= nf) {
+            slot_freq[slot] = -1;
+            h.active[slot] = 0;
+            h.reset[slot] = 0;
+            return false;
         }
-        FDB_DISPATCH_F(F, start(sys, w, n_live));
-        n_kernels += 1;
+        const int64_t fi = next++;
+        for (int g = 0; g < ng; ++g) {
+            mu_f[2 * g] = mu[((size_t)g * nf + fi) * 2];
+            mu_f[2 * g + 1] = mu[((size_t)g * nf + fi) * 2 + 1];
+        }
+        fill_slot(h, coef, F, ng, slot, omega[fi], ng ? mu_f.data() : nullptr, src_norm2);
+        slot_freq[slot] = fi;
+        h.reset[slot] = 1;
+        h.active[slot] = 0;
+        h.iters[slot] = 0;
+        ++n_busy;
+        return true;
+    };
+
+    // empty slots still need finite constants
+    for (int f = 0; f < F; ++f) fill_slot(h, coef, F, ng, f, 1.0, nullptr, 0.0);
+    bool any_reset = false;
+    for (int f = 0; f < F; ++f) any_reset = assign(f) || any_reset;
+    if (nf > 0) ensure_graph(sys, w, F, check_every, overlay);
+
+    while (n_busy > 0) {
+        if (any_reset) {
+            // slots that held a solution before can start from it (warm start from the slot's previous frequency)
+            bool keep_x = prm->warm_start != 0;
+            for (int f = 0; f < F; ++f)
+                if (h.reset[f] && !slot_used[f]) keep_x = false;
+            upload_scalars(sys, w, h, coef);
+            int nk = 0;
+            FDB_DISPATCH_F(F, reload(sys, w, overlay, keep_x, d_src_nodes.p, d_src_q.p, n_src, &nk));
+            n_kernels += nk;
+            if (keep_x) ++n_spmv;
+            for (int f = 0; f < F; ++f)
+                if (h.reset[f]) slot_used[f] = 1;
+            any_reset = false;
+        } else {
+            upload_scalars(sys, w, h, coef);
+        }
+        FDB_CUDA(cudaGraphLaunch(w->graph, s));
+        n_spmv += check_every;
+        n_kernels += 3 * (int64_t)check_every;
+        FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+        FDB_CUDA(cudaStreamSynchronize(s));
         FDB_CUDA(cudaGetLastError());
 
-        ensure_graph(sys, w, F, check_every, has_overlay);
-        Scalars h;
-        int it = 0;
-        while (true) {
-            FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
-            FDB_CUDA(cudaStreamSynchronize(s));
-            bool any = false;
-            for (int f = 0; f < n_live; ++f) any = any || h.active[f];
-            if (!any || it >= prm->max_iter) break;
-            FDB_CUDA(cudaGraphLaunch(w->graph, s));
-            it += check_every;
-            n_spmv += check_every;
-            n_kernels += 3 * (int64_t)check_every;
+        bool finished_any = false;
+        std::vector<char> done(F, 0);
+        for (int f = 0; f < F; ++f) {
+            if (slot_freq[f] < 0) continue;
+            if (!h.active[f] || h.iters[f] >= prm->max_iter) { done[f] = 1; finished_any = true; }
         }
-        // true residual of what is returned: ||b - G x|| / ||b||
-        FDB_DISPATCH_F(F, spmv(sys, w, w->x.p, w->q.p, false, has_overlay));
-        FDB_DISPATCH_F(F, set_rhs(sys, w, d_src_nodes.p, d_src_q.p, n_src, w->p.p));
-        FDB_DISPATCH_F(F, resnorm(sys, w, w->p.p, w->q.p));
-        n_spmv += 1; n_kernels += 3;
+        if (!finished_any) continue;
+
+        // true residual of what is returned, receivers, full pressure rows - only for the finished slots
+        int nk = 0;
+        FDB_DISPATCH_F(F, true_residual(sys, w, overlay, d_src_nodes.p, d_src_q.p, n_src, &nk));
+        n_kernels += nk; n_spmv += 1;
         Scalars hf;
         FDB_CUDA(cudaMemcpyAsync(&hf, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         if (n_rcv) {
@@ -990,21 +1082,25 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         if (res->pN) {
             FDB_DISPATCH_F(F, export_pn(sys, w));
             n_kernels += 1;
-            FDB_CUDA(cudaMemcpyAsync(res->pN + (size_t)f0 * N * 2, w->stage.p, (size_t)n_live * N * sizeof(double2), cudaMemcpyDefault, s));
+            for (int f = 0; f < F; ++f)
+                if (done[f])
+                    FDB_CUDA(cudaMemcpyAsync(res->pN + (size_t)slot_freq[f] * N * 2, w->stage.p + (size_t)f * N, (size_t)N * sizeof(double2),
+                                             cudaMemcpyDefault, s));
         }
         FDB_CUDA(cudaStreamSynchronize(s));
-        for (int f = 0; f < n_live; ++f) {
-            const double rel = (hf.bb[f] > 0) ? sqrt(hf.rr[f] / hf.bb[f]) : 0.0;
-            if (res->iters) res->iters[f0 + f] = h.iters[f];
-            if (res->relres) res->relres[f0 + f] = rel;
+        for (int f = 0; f < F; ++f) {
+            if (!done[f]) continue;
+            const int64_t fi = slot_freq[f];
+            const double rel = (hf.bb[f] > 0) ? sqrt(hf.rt[f] / hf.bb[f]) : 0.0;
+            if (res->iters) res->iters[fi] = h.iters[f];
+            if (res->relres) res->relres[fi] = rel;
             if (h.active[f] || !(rel <= 10 * prm->tol)) ++n_unconv;
-        }
-        if (n_rcv && res->pR)
-            for (int f = 0; f < n_live; ++f)
-                FDB_CUDA(cudaMemcpy(res->pR + ((size_t)(f0 + f) * n_rcv) * 2, rcv_host.data() + (size_t)f * n_rcv,
+            if (n_rcv && res->pR)
+                FDB_CUDA(cudaMemcpy(res->pR + ((size_t)fi * n_rcv) * 2, rcv_host.data() + (size_t)f * n_rcv,
                                     (size_t)n_rcv * sizeof(double2), cudaMemcpyDefault));
-        have_prev = true;
-        if (n_live < F) have_prev = false;
+            --n_busy;
+            any_reset = assign(f) || any_reset;
+        }
     }
     FDB_CUDA(cudaEventRecord(ev1, s));
     FDB_CUDA(cudaEventSynchronize(ev1));
@@ -1018,7 +1114,24 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     res->n_unconverged = n_unconv;
 }
 
-int64_t spmv_algorithmic_bytes(fdb_system* sys, int F) {
+// one-batch constants for the stand-alone SpMV entry points
+static void load_batch_scalars(fdb_system* sys, SweepWork* w, int F, const double* omega, const double* mu_batch /* [n_groups][F] complex */) {
+    Scalars h;
+    memset(&h, 0, sizeof(h));
+    std::vector<double2> coef((size_t)std::max(1, w->n_groups) * F, make_double2(0.0, 0.0));
+    std::vector<double> mu_f((size_t)std::max(1, w->n_groups) * 2);
+    for (int f = 0; f < F; ++f) {
+        for (int g = 0; g < w->n_groups; ++g) {
+            mu_f[2 * g] = mu_batch[((size_t)g * F + f) * 2];
+            mu_f[2 * g + 1] = mu_batch[((size_t)g * F + f) * 2 + 1];
+        }
+        fill_slot(h, coef, F, w->n_groups, f, omega[f], w->n_groups ? mu_f.data() : nullptr, 0.0);
+    }
+    h.tol2 = 1.0;
+    upload_scalars(sys, w, h, coef);
+}
+
+int64_t spmv_algorithmic_bytes(fdb_system* sys, int F, bool with_boundary) {
     // indptr + (indices + H + Q) once + overlay + x read and y write per frequency
     const int64_t N = sys->n_nodes, Z = sys->vol.nnz;
     const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
@@ -1036,7 +1149,7 @@ void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, con
         FDB_REQUIRE(mu != nullptr, "mu is required when the system has boundary groups");
         FDB_CUDA(cudaMemcpy(m.data(), mu, (size_t)ng * F * 2 * sizeof(double), cudaMemcpyDefault));
     }
-    load_batch_scalars(sys, w, F, F, om.data(), m.data(), 1.0, 0.0);
+    load_batch_scalars(sys, w, F, om.data(), m.data());
     const size_t n = (size_t)w->N * F;
     FDB_CUDA(cudaMemcpyAsync(w->p.p, x, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
     FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, false, has_overlay));
@@ -1052,13 +1165,21 @@ __global__ void k_fill_pattern(double2* __restrict__ v, int64_t n) {
     }
 }
 
-void run_spmv_bench(fdb_system* sys, int F, int reps, double* ms_per_launch, int64_t* bytes) {
+void run_spmv_enqueue(fdb_system* sys, int F, int reps, bool with_boundary, int64_t* bytes) {
     SweepWork* w = get_work(sys, F);
-    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    const bool has_overlay = with_boundary && sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    for (int i = 0; i < reps; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
+    FDB_CUDA(cudaGetLastError());
+    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary);
+}
+
+void run_spmv_bench(fdb_system* sys, int F, int reps, bool with_boundary, double* ms_per_launch, int64_t* bytes) {
+    SweepWork* w = get_work(sys, F);
+    const bool has_overlay = with_boundary && sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
     std::vector<double> om(F), m((size_t)std::max(1, sys->n_groups) * F * 2, 0.0);
     for (int f = 0; f < F; ++f) om[f] = 2.0 * 3.141592653589793 * (100.0 + f);
     for (size_t i = 0; i < m.size(); i += 2) m[i] = 1e-4;
-    load_batch_scalars(sys, w, F, F, om.data(), m.data(), 1.0, 0.0);
+    load_batch_scalars(sys, w, F, om.data(), m.data());
     const int64_t n = w->N * F;
     k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->p.p, n);
     for (int i = 0; i < 3; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
@@ -1075,7 +1196,7 @@ void run_spmv_bench(fdb_system* sys, int F, int reps, double* ms_per_launch, int
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_per_launch) *ms_per_launch = ms / reps;
-    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F);
+    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary);
 }
 
 }  // namespace fdb

@@ -301,8 +301,14 @@ class System:
         check(self._lib.fdb_spmv(self._h, F, ptr(omega), ptr(mu) if mu is not None else None, ptr(x), ptr(y)))
         return y
 
-    def spmv_bench(self, batch, reps):
+    def spmv_bench(self, batch, reps, with_boundary=True):
         ms = C.c_double()
         nbytes = C.c_int64()
-        check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), C.byref(ms), C.byref(nbytes)))
+        check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), int(bool(with_boundary)), C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+    def spmv_enqueue(self, batch, reps, with_boundary=True):
+        """Enqueue ``reps`` SpMV launches on the system's stream without synchronising; returns algorithmic bytes."""
+        nbytes = C.c_int64()
+        check(self._lib.fdb_spmv_enqueue(self._h, int(batch), int(reps), int(bool(with_boundary)), C.byref(nbytes)))
+        return nbytes.value

@@ -117,8 +117,13 @@ int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* re
 /* y = G_f x for a batch of frequencies on caller data: x, y are [n_nodes][batch] complex. (K5 alone; parity) */
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu /* [n_groups][batch] complex */,
              const double* x, double* y);
-/* Time `reps` launches of K5 on resident synthetic vectors; returns mean milliseconds per launch. */
-int fdb_spmv_bench(fdb_system* sys, int batch, int reps, double* ms_per_launch, int64_t* algorithmic_bytes);
+/* Time `reps` launches of K5 on resident synthetic vectors; returns mean milliseconds per launch.
+ * with_boundary = 0 launches the variant a rigid-wall sweep uses (no admittance overlay). */
+int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int with_boundary, double* ms_per_launch, int64_t* algorithmic_bytes);
+/* Enqueue `reps` launches of K5 (with its dot-product epilogue, as the solver launches it) on the system's
+ * stream and return without synchronising, so the caller can bracket them with its own CUDA events.
+ * Call fdb_spmv_bench once before to fill the resident vectors. */
+int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int with_boundary, int64_t* algorithmic_bytes);
 
 #ifdef __cplusplus
 }
