@@ -23,13 +23,13 @@ class SweepParams(C.Structure):
     _fields_ = [("n_freq", C.c_int64), ("omega", C.c_void_p), ("mu", C.c_void_p), ("n_src", C.c_int64),
                 ("src_nodes", C.c_void_p), ("src_q", C.c_void_p), ("tol", C.c_double), ("max_iter", C.c_int32),
                 ("batch", C.c_int32), ("check_every", C.c_int32), ("warm_start", C.c_int32), ("precond", C.c_int32),
-                ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p)]
+                ("arithmetic", C.c_int32), ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p)]
 
 
 class SweepResult(C.Structure):
     _fields_ = [("pR", C.c_void_p), ("pN", C.c_void_p), ("iters", C.c_void_p), ("relres", C.c_void_p),
                 ("seconds", C.c_double), ("n_spmv", C.c_int64), ("n_kernels", C.c_int64),
-                ("n_unconverged", C.c_int32)]
+                ("n_unconverged", C.c_int32), ("real_arithmetic", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/femder_b200.h declares

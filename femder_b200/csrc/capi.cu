@@ -9,8 +9,8 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);
 void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, const double* x, double* y);
-void run_spmv_bench(fdb_system* sys, int F, int reps, bool with_boundary, double* ms_per_launch, int64_t* bytes);
-void run_spmv_enqueue(fdb_system* sys, int F, int reps, bool with_boundary, int64_t* bytes);
+void run_spmv_bench(fdb_system* sys, int F, int reps, int flags, double* ms_per_launch, int64_t* bytes);
+void run_spmv_enqueue(fdb_system* sys, int F, int reps, int flags, int64_t* bytes);
 
 struct DeviceGuard {
     int prev = 0;
@@ -343,19 +343,19 @@ int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu, 
     FDB_API_END
 }
 
-int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int with_boundary, double* ms_per_launch, int64_t* algorithmic_bytes) {
+int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int flags, double* ms_per_launch, int64_t* algorithmic_bytes) {
     FDB_API_BEGIN
     FDB_SYS(sys);
     FDB_REQUIRE(reps > 0, "reps must be positive");
-    fdb::run_spmv_bench(sys, batch, reps, with_boundary != 0, ms_per_launch, algorithmic_bytes);
+    fdb::run_spmv_bench(sys, batch, reps, flags, ms_per_launch, algorithmic_bytes);
     FDB_API_END
 }
 
-int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int with_boundary, int64_t* algorithmic_bytes) {
+int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int flags, int64_t* algorithmic_bytes) {
     FDB_API_BEGIN
     FDB_SYS(sys);
     FDB_REQUIRE(reps > 0, "reps must be positive");
-    fdb::run_spmv_enqueue(sys, batch, reps, with_boundary != 0, algorithmic_bytes);
+    fdb::run_spmv_enqueue(sys, batch, reps, flags, algorithmic_bytes);
     FDB_API_END
 }
 

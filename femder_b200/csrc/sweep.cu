@@ -15,6 +15,7 @@
 #include "../../include/femder_b200.h"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace fdb {
 
@@ -55,6 +56,8 @@ struct SweepWork {
     int spmv_cfg = 0;             // FDB_SPMV_CFG: 0..3 bulk-copy pipeline shapes; 8..12 plain kernel launch shapes (tuning aid)
     int tma_stage_entries[2] = {0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
+    bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
+    bool graph_real = false;
 };
 
 void free_sweep_work(SweepWork* w) {
@@ -78,6 +81,30 @@ __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
     const double d = b.x * b.x + b.y * b.y;
     return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
+
+// ---- value type of the Krylov vectors: double2 (complex sweep) or double (rigid-wall sweep, see run_sweep) ----
+// A rigid-wall system G = H - w^2 Q is real and b = -1j*w*q is purely imaginary for real q, so p = 1j*u with
+// G u = -w q: the whole solve runs in real arithmetic on half the bytes.  Scalars (alpha, beta, rho) stay double2.
+__device__ __forceinline__ double2 s_mul(double2 s, double2 v) { return cmul(s, v); }
+__device__ __forceinline__ double s_mul(double2 s, double v) { return s.x * v; }
+__device__ __forceinline__ double2 r_mul(double g, double2 v) { return make_double2(g * v.x, g * v.y); }
+__device__ __forceinline__ double r_mul(double g, double v) { return g * v; }
+__device__ __forceinline__ double2 v_mul(double2 a, double2 b) { return cmul(a, b); }
+__device__ __forceinline__ double v_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double2 v_dot(double2 a, double2 b) { return cmul(a, b); }   // unconjugated
+__device__ __forceinline__ double2 v_dot(double a, double b) { return make_double2(a * b, 0.0); }
+__device__ __forceinline__ double v_n2(double2 a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ double v_n2(double a) { return a * a; }
+__device__ __forceinline__ double2 v_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double v_add(double a, double b) { return a + b; }
+__device__ __forceinline__ double2 v_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double v_sub(double a, double b) { return a - b; }
+template <typename T> __device__ __forceinline__ T v_zero();
+template <> __device__ __forceinline__ double2 v_zero<double2>() { return make_double2(0.0, 0.0); }
+template <> __device__ __forceinline__ double v_zero<double>() { return 0.0; }
+// what leaves the solver is always complex: p = u (complex sweep) or p = 1j*u (real sweep)
+__device__ __forceinline__ double2 v_out(double2 a) { return a; }
+__device__ __forceinline__ double2 v_out(double a) { return make_double2(0.0, a); }
 
 // Sum `v` over the lanes that share lane % F, result valid in lanes 0..F-1.
 template <int F>
@@ -292,33 +319,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-struct __align__(32) d4 { double a, b, c, d; };   // two complex numbers = one 256-bit access (LDG/STG.E.256 on sm_100)
-__device__ __forceinline__ d4 ld256(const double2* p) {
-    d4 v;
-    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
-    return v;
+struct __align__(32) d4 { double v[4]; };   // one 256-bit access (LDG/STG.E.256 on sm_100): 2 complex or 4 real values
+__device__ __forceinline__ d4 ld256(const double* p) {
+    d4 r;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void st256(double2* p, const d4& v) { *reinterpret_cast<d4*>(p) = v; }
-// Scheduling fence: everything loaded into v[0..3] is "redefined" here, so the compiler cannot start consuming
-// the first gather before the last one of the batch has been issued (keeps the whole batch in flight).
-__device__ __forceinline__ void hold4(d4* v) {
-    asm volatile("" : "+d"(v[0].a), "+d"(v[0].b), "+d"(v[0].c), "+d"(v[0].d), "+d"(v[1].a), "+d"(v[1].b), "+d"(v[1].c),
-                 "+d"(v[1].d), "+d"(v[2].a), "+d"(v[2].b), "+d"(v[2].c), "+d"(v[2].d), "+d"(v[3].a), "+d"(v[3].b),
-                 "+d"(v[3].c), "+d"(v[3].d));
-}
+__device__ __forceinline__ void st256(double* p, const d4& r) { *reinterpret_cast<d4*>(p) = r; }
 
-// lanes = (row in warp, frequency pair): F/2 lanes per row, 64/F rows per warp; each lane carries two
-// frequencies, so one 256-bit load per lane gathers x[col][0..F) of a row as one contiguous 16*F-byte segment.
-template <int F, bool DOT, bool OVERLAY, int NWARP, int TS, int NST, int KB>
+// lanes = (row in warp, group of frequencies): every lane carries 32 bytes of a row's vector entry - two
+// frequencies of a complex sweep (CPX) or four of a real one - so one 256-bit load per lane gathers
+// x[col][0..F) of a row as one contiguous segment (128 bytes at F = 8 complex / F = 16 real).
+template <int F, bool CPX, bool DOT, bool OVERLAY, int NWARP, int TS, int NST, int KB>
 __global__ void __launch_bounds__((NWARP + 1) * 32)
 k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
            const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
-           const double2* __restrict__ coef, const double2* __restrict__ x, double2* __restrict__ y, int64_t n_rows,
+           const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
            int64_t n_slices, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
     constexpr int BLOCK = (NWARP + 1) * 32;
-    constexpr int LPR = F / 2;          // lanes per row
+    constexpr int EPL = CPX ? 2 : 4;    // frequencies per lane
+    constexpr int LPR = F / EPL;        // lanes per row
     constexpr int RPW = 32 / LPR;       // rows per warp
+    constexpr int DPR = CPX ? 2 * F : F;  // doubles per row of a vector
     constexpr int NPASS = (TS * 8 + NWARP * RPW - 1) / (NWARP * RPW);
+    static_assert(LPR >= 1 && LPR <= 32, "batch too small for this lane mapping");
+    static_assert(!(OVERLAY && !CPX), "a boundary term makes the system complex");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* s_hq = reinterpret_cast<double2*>(smem_raw);                                                    // [NST][stage_entries]
     int32_t* s_idx = reinterpret_cast<int32_t*>(smem_raw + (size_t)NST * stage_entries * sizeof(double2));   // [NST][stage_entries]
@@ -362,8 +387,10 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
         // ===== consumer warps =====
         const int fq = lane % LPR;
         const int rl = lane / LPR;
-        const double w2a = sc->w2[2 * fq], w2b = sc->w2[2 * fq + 1];
-        const double2* xq = x + 2 * fq;
+        double w2v[4];   // omega^2 of the frequency each of the lane's four doubles belongs to
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w2v[j] = sc->w2[CPX ? 2 * fq + (j >> 1) : 4 * fq + j];
+        const double* xq = x + 4 * fq;
         int i = 0;
         for (int64_t t = t0; t < t1; ++t, ++i) {
             const int st = i % NST;
@@ -393,14 +420,14 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
                 if (rin >= TS * 8 || row >= n_rows) continue;
                 const int base = off_r[np] * 8 + (int)(row & 7);
                 const int width = wid_r[np];
-                double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;   // two frequencies
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
                 // software pipeline of depth KB: the gather of entry k+KB is issued as entry k is consumed, so
                 // KB-1 256-bit gathers per lane stay in flight whatever the compiler's schedule
                 d4 xv[KB];
 #pragma unroll
                 for (int u = 0; u < KB; ++u) {
                     const int c = (u < width) ? tix[base + u * 8] : (int)row;
-                    xv[u] = ld256(xq + (int64_t)c * F);
+                    xv[u] = ld256(xq + (int64_t)c * DPR);
                 }
                 for (int k0 = 0; k0 < width; k0 += KB) {
 #pragma unroll
@@ -408,33 +435,45 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
                         const int k = k0 + u;
                         if (k < width) {
                             const double2 m = thq[base + k * 8];
-                            const double ga = m.x - w2a * m.y, gb = m.x - w2b * m.y;
-                            ar += ga * xv[u].a; ai += ga * xv[u].b;
-                            br += gb * xv[u].c; bi += gb * xv[u].d;
+                            if constexpr (CPX) {
+                                const double ga = m.x - w2v[0] * m.y, gb = m.x - w2v[2] * m.y;
+                                acc[0] += ga * xv[u].v[0]; acc[1] += ga * xv[u].v[1];
+                                acc[2] += gb * xv[u].v[2]; acc[3] += gb * xv[u].v[3];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[j] += (m.x - w2v[j] * m.y) * xv[u].v[j];
+                            }
                         }
                         if (k + KB < width) {
                             const int c = tix[base + (k + KB) * 8];
-                            xv[u] = ld256(xq + (int64_t)c * F);
+                            xv[u] = ld256(xq + (int64_t)c * DPR);
                         }
                     }
                 }
-                if (OVERLAY) {
+                if constexpr (OVERLAY) {
                     for (int o = ob_r[np]; o < oe_r[np]; ++o) {
                         const int2 cg = ov_cg[o];
                         const double a = ov_val[o];
                         const double2 ca = coef[cg.y * F + 2 * fq], cb = coef[cg.y * F + 2 * fq + 1];
-                        const d4 xv = ld256(xq + (int64_t)cg.x * F);
-                        const double2 ta = cmul(make_double2(ca.x * a, ca.y * a), make_double2(xv.a, xv.b));
-                        const double2 tb = cmul(make_double2(cb.x * a, cb.y * a), make_double2(xv.c, xv.d));
-                        ar += ta.x; ai += ta.y; br += tb.x; bi += tb.y;
+                        const d4 xo = ld256(xq + (int64_t)cg.x * DPR);
+                        const double2 ta = cmul(make_double2(ca.x * a, ca.y * a), make_double2(xo.v[0], xo.v[1]));
+                        const double2 tb = cmul(make_double2(cb.x * a, cb.y * a), make_double2(xo.v[2], xo.v[3]));
+                        acc[0] += ta.x; acc[1] += ta.y; acc[2] += tb.x; acc[3] += tb.y;
                     }
                 }
-                d4 out; out.a = ar; out.b = ai; out.c = br; out.d = bi;
-                st256(y + row * F + 2 * fq, out);
+                d4 out;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out.v[j] = acc[j];
+                st256(y + row * DPR + 4 * fq, out);
                 if (DOT) {
-                    const d4 xv = ld256(xq + row * F);
-                    dot[0] += xv.a * ar - xv.b * ai; dot[1] += xv.a * ai + xv.b * ar;
-                    dot[2] += xv.c * br - xv.d * bi; dot[3] += xv.c * bi + xv.d * br;
+                    const d4 xo = ld256(xq + row * DPR);
+                    if constexpr (CPX) {
+                        dot[0] += xo.v[0] * acc[0] - xo.v[1] * acc[1]; dot[1] += xo.v[0] * acc[1] + xo.v[1] * acc[0];
+                        dot[2] += xo.v[2] * acc[2] - xo.v[3] * acc[3]; dot[3] += xo.v[2] * acc[3] + xo.v[3] * acc[2];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dot[j] += xo.v[j] * acc[j];
+                    }
                 }
             }
             __syncwarp();
@@ -442,7 +481,7 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
         }
     }
     if (DOT) {
-        // lanes sharing fq hold the two frequencies 2fq, 2fq+1
+        // lanes sharing fq hold the same frequencies
         __shared__ double s_red[NWARP][kMaxF][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -450,8 +489,13 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
             for (int o = 16; o >= LPR; o >>= 1) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
         }
         if (warp < NWARP && lane < LPR) {
-            s_red[warp][2 * lane][0] = dot[0]; s_red[warp][2 * lane][1] = dot[1];
-            s_red[warp][2 * lane + 1][0] = dot[2]; s_red[warp][2 * lane + 1][1] = dot[3];
+            if constexpr (CPX) {
+                s_red[warp][2 * lane][0] = dot[0]; s_red[warp][2 * lane][1] = dot[1];
+                s_red[warp][2 * lane + 1][0] = dot[2]; s_red[warp][2 * lane + 1][1] = dot[3];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s_red[warp][4 * lane + j][0] = dot[j]; s_red[warp][4 * lane + j][1] = 0.0; }
+            }
         }
         __syncthreads();
         if (threadIdx.x < F) {
@@ -472,26 +516,26 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
 // K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
 // finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
 // ------------------------------------------------------------------------------------------------
-// Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the batch): the diagonal is rebuilt from
+// Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the sweep): the diagonal is rebuilt from
 // (H_rr, Q_rr) - 16 bytes per ROW instead of 16 bytes per (row, frequency); otherwise the precomputed 1/diag is read.
-template <int F, bool ONFLY>
-__device__ __forceinline__ double2 jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
-                                                int64_t i, double w2, double2 rv) {
-    if (ONFLY) {
+template <typename T, int F, bool ONFLY>
+__device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                          int64_t i, double w2, T rv) {
+    if constexpr (ONFLY) {
         const double2 d = __ldg(&diag_hq[i / F]);
         const double g = d.x - w2 * d.y;
         const double inv = (g == 0.0) ? 1.0 : 1.0 / g;
-        return make_double2(rv.x * inv, rv.y * inv);
+        return r_mul(inv, rv);
     } else {
-        return cmul(dinv[i], rv);
+        return s_mul(dinv[i], rv);   // complex sweeps only
     }
 }
 
-template <int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, double2* __restrict__ r,
-                                                    const double2* __restrict__ p, const double2* __restrict__ q,
-                                                    const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
-                                                    int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
+template <typename T, int F, bool ONFLY>
+__global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
+                                                    const T* __restrict__ q, const double2* __restrict__ dinv,
+                                                    const double2* __restrict__ diag_hq, int64_t n_elems,
+                                                    Scalars* __restrict__ sc, double* __restrict__ partial) {
     const int f = threadIdx.x % F;
     const bool act = sc->active[f] != 0;
     const double w2 = sc->w2[f];
@@ -503,19 +547,14 @@ __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, doub
     double v[3] = {0.0, 0.0, 0.0};
     if (act) {
         for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-            double2 rv = r[i];
-            const double2 pv = p[i], qv = q[i];
-            double2 xv = x[i];
-            const double2 ap = cmul(alpha, pv), aq = cmul(alpha, qv);
-            xv.x += ap.x; xv.y += ap.y;
-            rv.x -= aq.x; rv.y -= aq.y;
-            x[i] = xv;
+            const T rv = v_sub(r[i], s_mul(alpha, q[i]));
+            x[i] = v_add(x[i], s_mul(alpha, p[i]));
             r[i] = rv;
-            const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, rv);
-            const double2 rz = cmul(rv, z);
+            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, rv);
+            const double2 rz = v_dot(rv, z);
             v[0] += rz.x;
             v[1] += rz.y;
-            v[2] += rv.x * rv.x + rv.y * rv.y;
+            v[2] += v_n2(rv);
         }
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
@@ -537,8 +576,8 @@ __global__ void __launch_bounds__(kBlock) k_update(double2* __restrict__ x, doub
 }
 
 // K6b: p = z + beta p
-template <int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_pupdate(double2* __restrict__ p, const double2* __restrict__ r,
+template <typename T, int F, bool ONFLY>
+__global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ p, const T* __restrict__ r,
                                                      const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
                                                      int64_t n_elems, const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
@@ -546,9 +585,8 @@ __global__ void __launch_bounds__(kBlock) k_pupdate(double2* __restrict__ p, con
     const double w2 = sc->w2[f];
     if (!sc->active[f]) return;  // frozen frequency: p is not used while alpha = 0
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
-        const double2 bp = cmul(beta, p[i]);
-        p[i] = make_double2(z.x + bp.x, z.y + bp.y);
+        const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
+        p[i] = v_add(z, s_mul(beta, p[i]));
     }
 }
 
@@ -556,7 +594,7 @@ __global__ void __launch_bounds__(kBlock) k_pupdate(double2* __restrict__ p, con
 // slot (re)load kernels: a batch slot whose frequency converged is reloaded with the next frequency of the
 // sweep while the other slots keep iterating ("continuous batching").  These touch only slots with reset[f] != 0.
 // ------------------------------------------------------------------------------------------------
-// dinv[row][f] = 1 / (H_rr - w2_f Q_rr + sum_ov,col==row coef[g][f] A)
+// dinv[row][f] = 1 / (H_rr - w2_f Q_rr + sum_ov,col==row coef[g][f] A)      (complex sweeps with a boundary term)
 template <int F>
 __global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ diag_hq, const int32_t* __restrict__ ov_ptr,
                                                     const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
@@ -584,60 +622,56 @@ __global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ d
 }
 
 // reset slots: r = 0, and x = 0 unless the previous solution of the slot is kept as the starting guess
-template <int F>
-__global__ void __launch_bounds__(kBlock) k_slot_clear(double2* __restrict__ x, double2* __restrict__ r, bool keep_x,
-                                                        int64_t n_elems, const Scalars* __restrict__ sc) {
+template <typename T, int F>
+__global__ void __launch_bounds__(kBlock) k_slot_clear(T* __restrict__ x, T* __restrict__ r, bool keep_x, int64_t n_elems,
+                                                        const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
     if (!sc->reset[f]) return;
-    const double2 z = make_double2(0.0, 0.0);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        r[i] = z;
-        if (!keep_x) x[i] = z;
+        r[i] = v_zero<T>();
+        if (!keep_x) x[i] = v_zero<T>();
     }
 }
 
-// dst[node][f] = rhs_scale[f] * q_s   (one thread per (source, f); sources are unique nodes); ALL: every slot
-template <int F>
+// dst[node][f] = b = -1j*w_f*q_s (complex) or its imaginary part -w_f*q_s (real sweep); ALL: every slot
+__device__ __forceinline__ void store_rhs(double2* dst, double2 scale, double2 q) { *dst = cmul(scale, q); }
+__device__ __forceinline__ void store_rhs(double* dst, double2 scale, double2 q) { *dst = scale.y * q.x; }
+template <typename T, int F>
 __global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, int n_src, bool all,
-                          const Scalars* __restrict__ sc, double2* __restrict__ dst) {
+                          const Scalars* __restrict__ sc, T* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_src * F) return;
     const int s = i / F, f = i % F;
-    if (all || sc->reset[f]) dst[(int64_t)src_nodes[s] * F + f] = cmul(sc->rhs_scale[f], src_q[s]);
+    if (all || sc->reset[f]) store_rhs(&dst[(int64_t)src_nodes[s] * F + f], sc->rhs_scale[f], src_q[s]);
 }
 
 // reset slots: r = r - q    (r holds b on entry; q = G x0)
-template <int F>
-__global__ void __launch_bounds__(kBlock) k_sub(double2* __restrict__ r, const double2* __restrict__ q, int64_t n,
+template <typename T, int F>
+__global__ void __launch_bounds__(kBlock) k_sub(T* __restrict__ r, const T* __restrict__ q, int64_t n,
                                                  const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
     if (!sc->reset[f]) return;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-        double2 a = r[i];
-        const double2 b = q[i];
-        a.x -= b.x; a.y -= b.y;
-        r[i] = a;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) r[i] = v_sub(r[i], q[i]);
 }
 
 // reset slots: p = z ; rho = r^T z ; rr = ||r||^2 ; activate the slot if its residual is above tolerance
-template <int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_start(double2* __restrict__ p, const double2* __restrict__ r,
-                                                   const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
-                                                   int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
+template <typename T, int F, bool ONFLY>
+__global__ void __launch_bounds__(kBlock) k_start(T* __restrict__ p, const T* __restrict__ r, const double2* __restrict__ dinv,
+                                                   const double2* __restrict__ diag_hq, int64_t n_elems,
+                                                   Scalars* __restrict__ sc, double* __restrict__ partial) {
     const int f = threadIdx.x % F;
     const bool rs = sc->reset[f] != 0;
     const double w2 = sc->w2[f];
     double v[3] = {0.0, 0.0, 0.0};
     if (rs) {
         for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-            const double2 rv = r[i];
-            const double2 z = jacobi_apply<F, ONFLY>(dinv, diag_hq, i, w2, rv);
+            const T rv = r[i];
+            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, rv);
             p[i] = z;
-            const double2 rz = cmul(rv, z);
+            const double2 rz = v_dot(rv, z);
             v[0] += rz.x;
             v[1] += rz.y;
-            v[2] += rv.x * rv.x + rv.y * rv.y;
+            v[2] += v_n2(rv);
         }
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
@@ -653,51 +687,47 @@ __global__ void __launch_bounds__(kBlock) k_start(double2* __restrict__ p, const
 }
 
 // true residual norm of what is returned: rt = ||b - q||^2 with b rebuilt, q = G x
-template <int F>
-__global__ void __launch_bounds__(kBlock) k_resnorm(const double2* __restrict__ b, const double2* __restrict__ q,
-                                                     int64_t n_elems, Scalars* __restrict__ sc, double* __restrict__ partial) {
+template <typename T, int F>
+__global__ void __launch_bounds__(kBlock) k_resnorm(const T* __restrict__ b, const T* __restrict__ q, int64_t n_elems,
+                                                     Scalars* __restrict__ sc, double* __restrict__ partial) {
     double v[1] = {0.0};
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const double2 bv = b[i], qv = q[i];
-        const double dx = bv.x - qv.x, dy = bv.y - qv.y;
-        v[0] += dx * dx + dy * dy;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock)
+        v[0] += v_n2(v_sub(b[i], q[i]));
     block_reduce_finalize<F, 1, kBlock>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rt[ff] = tot[0]; });
 }
 
 // K7: pR[f][i] = sum_j w[i][j] x[node[i][j]][f]
-template <int F>
-__global__ void k_gather_rcv(const double2* __restrict__ x, const int32_t* __restrict__ nodes, const double* __restrict__ w,
+template <typename T, int F>
+__global__ void k_gather_rcv(const T* __restrict__ x, const int32_t* __restrict__ nodes, const double* __restrict__ w,
                              int n_rcv, double2* __restrict__ out /* [F][n_rcv] */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rcv * F) return;
     const int rc = i / F, f = i % F;
-    double2 acc = make_double2(0.0, 0.0);
+    T acc = v_zero<T>();
     bool first = true;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const double wt = w[rc * 4 + j];
         if (wt == 0.0) continue;
-        const double2 v = x[(int64_t)nodes[rc * 4 + j] * F + f];
+        const T v = x[(int64_t)nodes[rc * 4 + j] * F + f];
         if (first && wt == 1.0) { acc = v; first = false; continue; }  // on-node receiver: exact copy
-        acc.x += wt * v.x;
-        acc.y += wt * v.y;
+        acc = v_add(acc, r_mul(wt, v));
         first = false;
     }
-    out[(int64_t)f * n_rcv + rc] = acc;
+    out[(int64_t)f * n_rcv + rc] = v_out(acc);
 }
 
 // pN export: stage[f][row] = x[row][f]
-template <int F>
-__global__ void __launch_bounds__(kBlock) k_export(const double2* __restrict__ x, int64_t n_rows, double2* __restrict__ stage) {
-    __shared__ double2 tile[kBlock];
+template <typename T, int F>
+__global__ void __launch_bounds__(kBlock) k_export(const T* __restrict__ x, int64_t n_rows, double2* __restrict__ stage) {
+    __shared__ T tile[kBlock];
     constexpr int RPB = kBlock / F;
     const int64_t row0 = (int64_t)blockIdx.x * RPB;
     const int64_t i = row0 * F + threadIdx.x;
     if (i < n_rows * F) tile[threadIdx.x] = x[i];
     __syncthreads();
     const int f = threadIdx.x / RPB, rl = threadIdx.x % RPB;
-    if (row0 + rl < n_rows) stage[(int64_t)f * n_rows + row0 + rl] = tile[rl * F + f];
+    if (row0 + rl < n_rows) stage[(int64_t)f * n_rows + row0 + rl] = v_out(tile[rl * F + f]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,6 +735,7 @@ __global__ void __launch_bounds__(kBlock) k_export(const double2* __restrict__ x
 // ------------------------------------------------------------------------------------------------
 template <int F>
 struct Launch {
+    // ---- plain (LDG) SpMV: complex only; used for F = 1 and as the fallback when a tile does not fit shared memory
     template <int BLOCK, int MINB>
     static void spmv_cfg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
         const int64_t N = w->N;
@@ -722,58 +753,6 @@ struct Launch {
             if (overlay) args(k_spmv<F, false, true, BLOCK, MINB>); else args(k_spmv<F, false, false, BLOCK, MINB>);
         }
     }
-    template <int NWARP, int TS, int NST, int KB>
-    static bool spmv_tma(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
-        const int64_t N = w->N, S = sys->n_slices;
-        const int64_t n_tiles = (S + TS - 1) / TS;
-        // largest tile (entries) decides the stage size
-        static_assert(NWARP >= 1 && (NWARP + 1) * 32 <= 1024, "block too large");
-        if (w->tma_stage_entries[TS == 8 ? 0 : 1] == 0) {
-            int64_t mx = 0;
-            for (int64_t t = 0; t < n_tiles; ++t) {
-                const int64_t a0 = sys->sell_off_host[t * TS], a1 = sys->sell_off_host[std::min<int64_t>((t + 1) * TS, S)];
-                mx = std::max(mx, (a1 - a0) * 8);
-            }
-            w->tma_stage_entries[TS == 8 ? 0 : 1] = (int)std::max<int64_t>(mx, 8);
-        }
-        const int stage_entries = w->tma_stage_entries[TS == 8 ? 0 : 1];
-        const size_t smem = (size_t)NST * stage_entries * 20;
-        if (smem > 100 * 1024) return false;  // rows too long for this tile shape: use the plain kernel
-        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / ((NWARP + 1) * 32), (150 * 1024) / (smem + 8192)));
-        if (w->spmv_bps > 0) per_sm = std::min(per_sm, w->spmv_bps);
-        int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sys->num_sms * per_sm);
-        auto launch = [&](auto kern) {
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, (NWARP + 1) * 32, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p,
-                                                               sys->ov_cg.p, sys->ov_val.p, w->coef.p, x, y, N, S, stage_entries,
-                                                               w->sc.p, (double*)w->partial.p);
-        };
-        if (dot) {
-            if (overlay) launch(k_spmv_tma<F, true, true, NWARP, TS, NST, KB>); else launch(k_spmv_tma<F, true, false, NWARP, TS, NST, KB>);
-        } else {
-            if (overlay) launch(k_spmv_tma<F, false, true, NWARP, TS, NST, KB>); else launch(k_spmv_tma<F, false, false, NWARP, TS, NST, KB>);
-        }
-        return true;
-    }
-    static void spmv(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
-        if constexpr (F >= 2) {
-            if (w->spmv_cfg < 8) {
-                // rows per tile = 8*TS; a warp covers 64/F rows per pass
-                constexpr int RPW = 64 / F;
-                constexpr int W8 = (64 / RPW < 16) ? 64 / RPW : 16;     // consumer warps for an 8-slice tile
-                constexpr int W16 = (128 / RPW < 16) ? 128 / RPW : 16;  // ... for a 16-slice tile
-                bool ok;
-                switch (w->spmv_cfg) {
-                    case 1: ok = spmv_tma<W8, 8, 2, 4>(sys, w, x, y, dot, overlay); break;
-                    case 2: ok = spmv_tma<W8, 8, 3, 8>(sys, w, x, y, dot, overlay); break;
-                    case 3: ok = spmv_tma<W8, 8, 2, 8>(sys, w, x, y, dot, overlay); break;
-                    default: ok = spmv_tma<W16, 16, 2, 8>(sys, w, x, y, dot, overlay); break;  // measured best at F = 4, 8
-                }
-                if (ok) return;
-            }
-        }
-        spmv_ldg(sys, w, x, y, dot, overlay);
-    }
     static void spmv_ldg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
         switch (w->spmv_cfg - 8) {
             case 1: spmv_cfg<kSpmvCfgs[1].block, kSpmvCfgs[1].per_sm>(sys, w, x, y, dot, overlay); break;
@@ -783,64 +762,164 @@ struct Launch {
             default: spmv_cfg<kSpmvCfgs[0].block, kSpmvCfgs[0].per_sm>(sys, w, x, y, dot, overlay); break;
         }
     }
+
+    // ---- bulk-copy pipeline SpMV
+    template <int TS>
+    static int stage_entries(fdb_system* sys, SweepWork* w) {
+        int& cached = w->tma_stage_entries[TS == 8 ? 0 : 1];
+        if (cached == 0) {
+            const int64_t S = sys->n_slices, n_tiles = (S + TS - 1) / TS;
+            int64_t mx = 0;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int64_t a0 = sys->sell_off_host[t * TS], a1 = sys->sell_off_host[std::min<int64_t>((t + 1) * TS, S)];
+                mx = std::max(mx, (a1 - a0) * 8);
+            }
+            cached = (int)std::max<int64_t>(mx, 8);
+        }
+        return cached;
+    }
+    template <bool CPX, int NWARP, int TS, int NST, int KB>
+    static bool spmv_tma(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
+        static_assert(NWARP >= 1 && (NWARP + 1) * 32 <= 1024, "block too large");
+        const int64_t N = w->N, S = sys->n_slices;
+        const int64_t n_tiles = (S + TS - 1) / TS;
+        const int se = stage_entries<TS>(sys, w);
+        const size_t smem = (size_t)NST * se * 20;
+        if (smem > 100 * 1024) return false;  // rows too long for this tile shape: use the plain kernel
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / ((NWARP + 1) * 32), (150 * 1024) / (smem + 8192)));
+        if (w->spmv_bps > 0) per_sm = std::min(per_sm, w->spmv_bps);
+        int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sys->num_sms * per_sm);
+        auto launch = [&](auto kern) {
+            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, (NWARP + 1) * 32, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p,
+                                                               sys->ov_cg.p, sys->ov_val.p, w->coef.p, (const double*)x, (double*)y, N, S,
+                                                               se, w->sc.p, (double*)w->partial.p);
+        };
+        if constexpr (CPX) {
+            if (dot) {
+                if (overlay) launch(k_spmv_tma<F, true, true, true, NWARP, TS, NST, KB>);
+                else launch(k_spmv_tma<F, true, true, false, NWARP, TS, NST, KB>);
+            } else {
+                if (overlay) launch(k_spmv_tma<F, true, false, true, NWARP, TS, NST, KB>);
+                else launch(k_spmv_tma<F, true, false, false, NWARP, TS, NST, KB>);
+            }
+        } else {
+            if (dot) launch(k_spmv_tma<F, false, true, false, NWARP, TS, NST, KB>);
+            else launch(k_spmv_tma<F, false, false, false, NWARP, TS, NST, KB>);
+        }
+        return true;
+    }
+    template <bool CPX>
+    static bool spmv_tma_cfg(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
+        constexpr int LPR = CPX ? F / 2 : F / 4;              // lanes per row
+        if constexpr (LPR < 1) {
+            return false;
+        } else {
+            constexpr int RPW = 32 / LPR;                        // rows per warp and pass
+            constexpr int W8 = (64 / RPW < 16) ? (64 / RPW < 1 ? 1 : 64 / RPW) : 16;      // consumer warps for an 8-slice tile
+            constexpr int W16 = (128 / RPW < 16) ? (128 / RPW < 1 ? 1 : 128 / RPW) : 16;  // ... for a 16-slice tile
+            switch (w->spmv_cfg) {
+                case 1: return spmv_tma<CPX, W8, 8, 2, 4>(sys, w, x, y, dot, overlay);
+                case 2: return spmv_tma<CPX, W8, 8, 3, 8>(sys, w, x, y, dot, overlay);
+                case 3: return spmv_tma<CPX, W8, 8, 2, 8>(sys, w, x, y, dot, overlay);
+                default: return spmv_tma<CPX, W16, 16, 2, 8>(sys, w, x, y, dot, overlay);  // measured best at F = 4, 8
+            }
+        }
+    }
+    // can a real-arithmetic sweep run at this batch width on this mesh?
+    static bool real_supported(fdb_system* sys, SweepWork* w) {
+        if (F < 4 || w->spmv_cfg >= 8) return false;
+        return (size_t)2 * stage_entries<16>(sys, w) * 20 <= 100 * 1024 && (size_t)3 * stage_entries<8>(sys, w) * 20 <= 100 * 1024;
+    }
+    static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
+        if (w->real) {
+            if (!spmv_tma_cfg<false>(sys, w, x, y, dot, false)) throw Error("femder_b200: real-arithmetic SpMV not available for this mesh");
+            return;
+        }
+        if (w->spmv_cfg < 8 && spmv_tma_cfg<true>(sys, w, x, y, dot, overlay)) return;
+        spmv_ldg(sys, w, (const double2*)x, (double2*)y, dot, overlay);
+    }
+
     static int egrid(SweepWork* w) {
         return (int)std::min<int64_t>((w->N * F + kBlock - 1) / kBlock, (int64_t)w->grid);
     }
-    static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
+    template <typename T>
+    static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
         const int64_t ne = w->N * F;
-        spmv(sys, w, w->p.p, w->q.p, true, overlay);
+        T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *q = (T*)w->q.p;
+        spmv(sys, w, p, q, true, overlay);
         if (overlay) {
-            k_update<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, sys->diag_hq.p, ne,
-                                                                    w->sc.p, (double*)w->partial.p);
-            k_pupdate<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            if constexpr (std::is_same<T, double2>::value) {
+                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            }
         } else {
-            k_update<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, w->p.p, w->q.p, w->dinv.p, sys->diag_hq.p, ne,
-                                                                   w->sc.p, (double*)w->partial.p);
-            k_pupdate<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
         }
     }
-    // (re)load the slots flagged in sc.reset; returns the number of kernels launched
-    static void reload(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+    static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
+        if (w->real) iteration_t<double>(sys, w, false); else iteration_t<double2>(sys, w, overlay);
+    }
+    // (re)load the slots flagged in sc.reset
+    template <typename T>
+    static void reload_t(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
         const int64_t ne = w->N * F;
+        T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *qq = (T*)w->q.p;
         int nk = 0;
         if (overlay) {
             k_jacobi<F><<<grid_for(ne, kBlock), kBlock, 0, sys->stream>>>(sys->diag_hq.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
                                                                        w->coef.p, overlay, w->N, w->sc.p, w->dinv.p);
             ++nk;
         }
-        k_slot_clear<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->x.p, w->r.p, keep_x, ne, w->sc.p);
+        k_slot_clear<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, keep_x, ne, w->sc.p);
         ++nk;
         if (n_src) {
-            k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, false, w->sc.p, w->r.p);
+            k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, false, w->sc.p, r);
             ++nk;
         }
         if (keep_x) {
-            spmv(sys, w, w->x.p, w->q.p, false, overlay);
-            k_sub<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->r.p, w->q.p, ne, w->sc.p);
+            spmv(sys, w, x, qq, false, overlay);
+            k_sub<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(r, qq, ne, w->sc.p);
             nk += 2;
         }
-        if (overlay)
-            k_start<F, false><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-        else
-            k_start<F, true><<<egrid(w), kBlock, 0, sys->stream>>>(w->p.p, w->r.p, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+        if (overlay) {
+            if constexpr (std::is_same<T, double2>::value)
+                k_start<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+        } else {
+            k_start<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+        }
         *n_launched = nk + 1;
     }
+    static void reload(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+        if (w->real) reload_t<double>(sys, w, false, keep_x, nodes, q, n_src, n_launched);
+        else reload_t<double2>(sys, w, overlay, keep_x, nodes, q, n_src, n_launched);
+    }
     // rt[f] = ||b_f - G_f x_f||^2 for every slot (q and tmp are free between iterations)
-    static void true_residual(fdb_system* sys, SweepWork* w, bool overlay, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+    template <typename T>
+    static void true_residual_t(fdb_system* sys, SweepWork* w, bool overlay, const int32_t* nodes, const double2* q, int n_src) {
         const int64_t ne = w->N * F;
-        spmv(sys, w, w->x.p, w->q.p, false, overlay);
-        FDB_CUDA(cudaMemsetAsync(w->tmp.p, 0, (size_t)ne * sizeof(double2), sys->stream));
-        if (n_src) k_set_rhs<F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, true, w->sc.p, w->tmp.p);
-        k_resnorm<F><<<egrid(w), kBlock, 0, sys->stream>>>(w->tmp.p, w->q.p, ne, w->sc.p, (double*)w->partial.p);
+        T *x = (T*)w->x.p, *qq = (T*)w->q.p, *tmp = (T*)w->tmp.p;
+        spmv(sys, w, x, qq, false, overlay);
+        FDB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ne * sizeof(T), sys->stream));
+        if (n_src) k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, true, w->sc.p, tmp);
+        k_resnorm<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(tmp, qq, ne, w->sc.p, (double*)w->partial.p);
+    }
+    static void true_residual(fdb_system* sys, SweepWork* w, bool overlay, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+        if (w->real) true_residual_t<double>(sys, w, false, nodes, q, n_src); else true_residual_t<double2>(sys, w, overlay, nodes, q, n_src);
         *n_launched = 3;
     }
     static void gather(fdb_system* sys, SweepWork* w, const int32_t* nodes, const double* wts, int n_rcv) {
-        k_gather_rcv<F><<<grid_for((int64_t)n_rcv * F, 128), 128, 0, sys->stream>>>(w->x.p, nodes, wts, n_rcv, w->rcv_out.p);
+        const int g = grid_for((int64_t)n_rcv * F, 128);
+        if (w->real) k_gather_rcv<double, F><<<g, 128, 0, sys->stream>>>((const double*)w->x.p, nodes, wts, n_rcv, w->rcv_out.p);
+        else k_gather_rcv<double2, F><<<g, 128, 0, sys->stream>>>(w->x.p, nodes, wts, n_rcv, w->rcv_out.p);
     }
     static void export_pn(fdb_system* sys, SweepWork* w) {
         const int rpb = kBlock / F;
-        k_export<F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>(w->x.p, w->N, w->stage.p);
+        if (w->real) k_export<double, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>((const double*)w->x.p, w->N, w->stage.p);
+        else k_export<double2, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>(w->x.p, w->N, w->stage.p);
     }
+    static void query_real(fdb_system* sys, SweepWork* w, bool* ok) { *ok = real_supported(sys, w); }
 };
 
 #define FDB_DISPATCH_F(F, CALL)                                   \
@@ -907,7 +986,7 @@ static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, cons
 }
 
 static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool overlay) {
-    if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay) return;
+    if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay && w->graph_real == w->real) return;
     if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
     cudaGraph_t g = nullptr;
     FDB_CUDA(cudaStreamBeginCapture(sys->stream, cudaStreamCaptureModeThreadLocal));
@@ -922,7 +1001,7 @@ static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool o
     cudaError_t e = cudaGraphInstantiate(&w->graph, g, 0);
     cudaGraphDestroy(g);
     FDB_CUDA(e);
-    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay;
+    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real;
 }
 
 // The sweep.  F slots iterate together; a slot whose frequency has converged is reloaded with the next frequency
@@ -970,6 +1049,20 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     double src_norm2 = 0;
     for (auto& v : u_q) src_norm2 += v.x * v.x + v.y * v.y;
     const int n_src = (int)u_nodes.size();
+    // Real arithmetic when the systems are real (no boundary term) and the right-hand sides purely imaginary
+    // (real q): p = 1j*u with G u = -w q.  Same COCG recurrences on half the bytes.
+    {
+        bool real = !overlay && prm->arithmetic != 1;
+        for (auto& v : u_q) real = real && (v.y == 0.0);
+        w->real = false;
+        if (real) {
+            bool ok = false;
+            FDB_DISPATCH_F(F, query_real(sys, w, &ok));
+            real = ok;
+        }
+        w->real = real;
+        res->real_arithmetic = real ? 1 : 0;
+    }
     DevBuf<int32_t> d_src_nodes; DevBuf<double2> d_src_q;
     d_src_nodes.alloc(std::max(1, n_src)); d_src_q.alloc(std::max(1, n_src));
     if (n_src) {
@@ -1009,6 +1102,12 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     int64_t next = 0;
     int n_busy = 0;
 
+    // Frequencies are dispatched to the slots in descending order: the iteration count grows with frequency, and
+    // starting the expensive systems first leaves the cheap ones for the tail where slots begin to idle.
+    std::vector<int64_t> order(nf);
+    for (int64_t i = 0; i < nf; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return omega[a] > omega[b]; });
+
     auto assign = [&](int slot) {
         if (next >= nf) {
             slot_freq[slot] = -1;
@@ -1016,7 +1115,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             h.reset[slot] = 0;
             return false;
         }
-        const int64_t fi = next++;
+        const int64_t fi = order[next++];
         for (int g = 0; g < ng; ++g) {
             mu_f[2 * g] = mu[((size_t)g * nf + fi) * 2];
             mu_f[2 * g + 1] = mu[((size_t)g * nf + fi) * 2 + 1];
@@ -1131,12 +1230,22 @@ static void load_batch_scalars(fdb_system* sys, SweepWork* w, int F, const doubl
     upload_scalars(sys, w, h, coef);
 }
 
-int64_t spmv_algorithmic_bytes(fdb_system* sys, int F, bool with_boundary) {
+static bool bench_real(fdb_system* sys, SweepWork* w, int F, int flags) {
+    if (!(flags & 2)) return false;
+    FDB_REQUIRE(!(flags & 1), "the real-arithmetic SpMV has no boundary term");
+    bool ok = false;
+    w->real = false;
+    FDB_DISPATCH_F(F, query_real(sys, w, &ok));
+    FDB_REQUIRE(ok, "real-arithmetic SpMV needs batch >= 4 and tiles that fit shared memory");
+    return true;
+}
+
+int64_t spmv_algorithmic_bytes(fdb_system* sys, int F, bool with_boundary, bool real) {
     // indptr + (indices + H + Q) once + overlay + x read and y write per frequency
     const int64_t N = sys->n_nodes, Z = sys->vol.nnz;
     const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
     // counted on the CSR sizes (the algorithm's bytes); the SELL-8 copy the kernel streams adds padding on top
-    return 4 * (N + 1) + Z * 20 + (has_overlay ? 4 * (N + 1) + sys->n_ov * 16 : 0) + 32 * N * F;
+    return 4 * (N + 1) + Z * 20 + (has_overlay ? 4 * (N + 1) + sys->n_ov * 16 : 0) + (real ? 16 : 32) * N * F;
 }
 
 void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, const double* x, double* y) {
@@ -1149,6 +1258,7 @@ void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, con
         FDB_REQUIRE(mu != nullptr, "mu is required when the system has boundary groups");
         FDB_CUDA(cudaMemcpy(m.data(), mu, (size_t)ng * F * 2 * sizeof(double), cudaMemcpyDefault));
     }
+    w->real = false;
     load_batch_scalars(sys, w, F, om.data(), m.data());
     const size_t n = (size_t)w->N * F;
     FDB_CUDA(cudaMemcpyAsync(w->p.p, x, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
@@ -1165,16 +1275,20 @@ __global__ void k_fill_pattern(double2* __restrict__ v, int64_t n) {
     }
 }
 
-void run_spmv_enqueue(fdb_system* sys, int F, int reps, bool with_boundary, int64_t* bytes) {
+void run_spmv_enqueue(fdb_system* sys, int F, int reps, int flags, int64_t* bytes) {
     SweepWork* w = get_work(sys, F);
+    const bool with_boundary = (flags & 1) != 0;
+    w->real = bench_real(sys, w, F, flags);
     const bool has_overlay = with_boundary && sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
     for (int i = 0; i < reps; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
     FDB_CUDA(cudaGetLastError());
-    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary);
+    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary, w->real);
 }
 
-void run_spmv_bench(fdb_system* sys, int F, int reps, bool with_boundary, double* ms_per_launch, int64_t* bytes) {
+void run_spmv_bench(fdb_system* sys, int F, int reps, int flags, double* ms_per_launch, int64_t* bytes) {
     SweepWork* w = get_work(sys, F);
+    const bool with_boundary = (flags & 1) != 0;
+    w->real = bench_real(sys, w, F, flags);
     const bool has_overlay = with_boundary && sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
     std::vector<double> om(F), m((size_t)std::max(1, sys->n_groups) * F * 2, 0.0);
     for (int f = 0; f < F; ++f) om[f] = 2.0 * 3.141592653589793 * (100.0 + f);
@@ -1196,7 +1310,7 @@ void run_spmv_bench(fdb_system* sys, int F, int reps, bool with_boundary, double
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_per_launch) *ms_per_launch = ms / reps;
-    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary);
+    if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary, w->real);
 }
 
 }  // namespace fdb

@@ -74,7 +74,7 @@ def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
 
 
 class FEM3D:
-    def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=50000, batch=8,
+    def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=50000, batch="auto",
                  check_every=32, warm_start=False, compat_complex64=False):
         self.BC = BC
         if BC is not None:
@@ -221,7 +221,7 @@ class FEM3D:
             rcv_w = np.array([s[1] for s in st], dtype=np.float64)
 
         rank, world, _ = sharding.dist_info()
-        owned = sharding.owned_frequencies(nf, self.batch, rank, world)
+        owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch,
                                   check_every=self.check_every, warm_start=self.warm_start)

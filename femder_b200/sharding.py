@@ -1,8 +1,8 @@
 """Frequency sharding across ranks: frequencies are independent systems over the same H, Q, A.
 
-One process per GPU.  Each rank owns whole batches (the fused-SpMV width) dealt round-robin, because the
-iteration count rises with frequency and contiguous blocks would leave the last rank with the expensive
-end of the sweep.  There is no collective on the solve path; the result rows are gathered once at the end.
+One process per GPU.  Frequencies are dealt round-robin (``batch`` consecutive ones at a time; ``FEM3D`` deals
+single frequencies) because the iteration count rises with frequency and contiguous blocks would leave the last
+rank with the expensive end of the sweep.  Inside a rank the solver's slots refill continuously.  There is no collective on the solve path; the result rows are gathered once at the end.
 """
 from __future__ import annotations
 

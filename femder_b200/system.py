@@ -241,17 +241,22 @@ class System:
 
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
-              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None):
+              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False):
         """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
 
         mu: (n_groups, n_freq) complex.  Returns (pN or None, pR or None, SweepStats)."""
-        if batch not in VALID_BATCH:
-            raise ValueError(f"batch must be one of {VALID_BATCH}")
         omega = _f64(np.atleast_1d(omega))
         nf = len(omega)
         mu = _c128(np.asarray(mu).reshape(self.n_groups, nf)) if self.n_groups else None
         src_nodes = _i32(np.atleast_1d(src_nodes))
         src_q = _c128(np.atleast_1d(src_q).ravel())
+        if batch in (0, None, "auto"):
+            # a rigid-wall sweep with real sources runs in real arithmetic (half the bytes per frequency), where 16
+            # frequencies fill the 128-byte gather line that 8 complex ones do
+            real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex
+            batch = 16 if real else 8
+        if batch not in VALID_BATCH:
+            raise ValueError(f"batch must be one of {VALID_BATCH} or 'auto'")
         if len(src_q) != len(src_nodes):
             raise ValueError("src_nodes and src_q differ in length")
         prm = SweepParams()
@@ -267,6 +272,7 @@ class System:
         prm.check_every = int(check_every)
         prm.warm_start = int(bool(warm_start))
         prm.precond = 0
+        prm.arithmetic = 1 if force_complex else 0
         n_rcv = 0
         if rcv_nodes is not None:
             rcv_nodes = _i32(np.asarray(rcv_nodes).reshape(-1, 4))
@@ -289,7 +295,9 @@ class System:
         res.iters = ptr(iters)
         res.relres = ptr(relres)
         check(self._lib.fdb_sweep(self._h, C.byref(prm), C.byref(res)))
-        return pN, pR, SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged)
+        st = SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged)
+        st.real_arithmetic = bool(res.real_arithmetic)
+        return pN, pR, st
 
     def spmv(self, omega, mu, x):
         """y = G_f x for a batch; x is (N, F) complex128."""
@@ -301,14 +309,16 @@ class System:
         check(self._lib.fdb_spmv(self._h, F, ptr(omega), ptr(mu) if mu is not None else None, ptr(x), ptr(y)))
         return y
 
-    def spmv_bench(self, batch, reps, with_boundary=True):
+    def spmv_bench(self, batch, reps, with_boundary=True, real=False):
         ms = C.c_double()
         nbytes = C.c_int64()
-        check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), int(bool(with_boundary)), C.byref(ms), C.byref(nbytes)))
+        flags = 2 if real else int(bool(with_boundary))
+        check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), flags, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
 
-    def spmv_enqueue(self, batch, reps, with_boundary=True):
+    def spmv_enqueue(self, batch, reps, with_boundary=True, real=False):
         """Enqueue ``reps`` SpMV launches on the system's stream without synchronising; returns algorithmic bytes."""
         nbytes = C.c_int64()
-        check(self._lib.fdb_spmv_enqueue(self._h, int(batch), int(reps), int(bool(with_boundary)), C.byref(nbytes)))
+        flags = 2 if real else int(bool(with_boundary))
+        check(self._lib.fdb_spmv_enqueue(self._h, int(batch), int(reps), flags, C.byref(nbytes)))
         return nbytes.value

@@ -94,6 +94,7 @@ typedef struct fdb_sweep_params {
     int32_t check_every;      /* iterations between host convergence checks (one CUDA graph launch) */
     int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
     int32_t precond;          /* 0: Jacobi */
+    int32_t arithmetic;       /* 0: automatic (real arithmetic for rigid-wall sweeps with real sources), 1: always complex */
     int64_t n_rcv;            /* receivers: pR[n][i] = sum_j rcv_w[i][j] * p[n][rcv_nodes[i][j]] */
     const int32_t* rcv_nodes; /* [n_rcv][4] (unused slots: weight 0, any valid node) */
     const double* rcv_w;      /* [n_rcv][4] */
@@ -110,6 +111,7 @@ typedef struct fdb_sweep_result {
     int64_t n_spmv;   /* fused SpMV launches */
     int64_t n_kernels;/* all kernel launches of the sweep */
     int32_t n_unconverged;
+    int32_t real_arithmetic;  /* 1 if the sweep ran in real arithmetic (G real, b imaginary: p = 1j*u) */
 } fdb_sweep_result;
 
 int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);
@@ -118,12 +120,15 @@ int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* re
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu /* [n_groups][batch] complex */,
              const double* x, double* y);
 /* Time `reps` launches of K5 on resident synthetic vectors; returns mean milliseconds per launch.
- * with_boundary = 0 launches the variant a rigid-wall sweep uses (no admittance overlay). */
-int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int with_boundary, double* ms_per_launch, int64_t* algorithmic_bytes);
+ * flags: bit 0 = include the boundary (admittance) overlay; bit 1 = real-arithmetic variant (what a rigid-wall
+ * sweep with real sources launches; excludes bit 0). */
+#define FDB_SPMV_BOUNDARY 1
+#define FDB_SPMV_REAL 2
+int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int flags, double* ms_per_launch, int64_t* algorithmic_bytes);
 /* Enqueue `reps` launches of K5 (with its dot-product epilogue, as the solver launches it) on the system's
  * stream and return without synchronising, so the caller can bracket them with its own CUDA events.
  * Call fdb_spmv_bench once before to fill the resident vectors. */
-int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int with_boundary, int64_t* algorithmic_bytes);
+int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int flags, int64_t* algorithmic_bytes);
 
 #ifdef __cplusplus
 }
