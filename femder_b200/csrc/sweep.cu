@@ -696,6 +696,19 @@ __global__ void __launch_bounds__(kBlock) k_resnorm(const T* __restrict__ b, con
     block_reduce_finalize<F, 1, kBlock>(v, partial, &sc->ticket[3], [&](int ff, const double* tot) { sc->rt[ff] = tot[0]; });
 }
 
+// tail of a sweep: move the still-running slots of a batch of width Fs into a narrower batch of width Fd
+struct SlotMap { int src[kMaxF]; };
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_repack(const T* __restrict__ src, int Fs, T* __restrict__ dst, int Fd, SlotMap map,
+                                                    int64_t n_rows) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_rows * Fd; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t row = i / Fd;
+        const int j = (int)(i % Fd);
+        const int sj = map.src[j];
+        dst[i] = (sj >= 0) ? src[row * Fs + sj] : v_zero<T>();
+    }
+}
+
 // K7: pR[f][i] = sum_j w[i][j] x[node[i][j]][f]
 template <typename T, int F>
 __global__ void k_gather_rcv(const T* __restrict__ x, const int32_t* __restrict__ nodes, const double* __restrict__ w,
@@ -932,6 +945,8 @@ struct Launch {
         default: throw Error("femder_b200: batch must be 1, 2, 4, 8 or 16"); \
     }
 
+static SweepWork* new_work(fdb_system* sys, int F);
+
 static SweepWork* get_work(fdb_system* sys, int F) {
     FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16, "batch must be 1, 2, 4, 8 or 16");
     FDB_REQUIRE(sys->have_pattern && sys->have_hq, "pattern and H/Q values must be set before the sweep");
@@ -940,9 +955,14 @@ static SweepWork* get_work(fdb_system* sys, int F) {
         free_sweep_work(w);
         w = sys->work = nullptr;
     }
-    if (!w) {
+    if (!w) w = sys->work = new_work(sys, F);
+    return w;
+}
+
+static SweepWork* new_work(fdb_system* sys, int F) {
+    SweepWork* w = nullptr;
+    {
         w = new SweepWork();
-        sys->work = w;
         w->F = F;
         w->N = sys->n_nodes;
         w->n_groups = sys->n_groups;
@@ -1004,15 +1024,30 @@ static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool o
     w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real;
 }
 
+static void k_jacobi_launch(fdb_system* sys, SweepWork* w, int F) {
+    const int64_t ne = w->N * F;
+    auto go = [&](auto kern) {
+        kern<<<grid_for(ne, kBlock), kBlock, 0, sys->stream>>>(sys->diag_hq.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p, w->coef.p, true,
+                                                             w->N, w->sc.p, w->dinv.p);
+    };
+    switch (F) {
+        case 1: go(k_jacobi<1>); break;
+        case 2: go(k_jacobi<2>); break;
+        case 4: go(k_jacobi<4>); break;
+        case 8: go(k_jacobi<8>); break;
+        default: go(k_jacobi<16>); break;
+    }
+}
+
 // The sweep.  F slots iterate together; a slot whose frequency has converged is reloaded with the next frequency
 // of the list while the others keep going, so no bandwidth is spent on finished systems.
 void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res) {
     FDB_REQUIRE(prm && res, "null argument");
     FDB_REQUIRE(prm->n_freq >= 0 && prm->n_src >= 0 && prm->n_rcv >= 0, "negative count");
     FDB_REQUIRE(prm->tol > 0 && prm->max_iter > 0, "tol and max_iter must be positive");
-    const int F = prm->batch;
-    SweepWork* w = get_work(sys, F);
-    const int64_t N = w->N;
+    int F = prm->batch;
+    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16, "batch must be 1, 2, 4, 8 or 16");
+    const int64_t N = sys->n_nodes;
     const int ng = sys->n_groups;
     FDB_REQUIRE(ng == 0 || prm->mu != nullptr, "mu is required when the system has boundary groups");
     const int check_every = std::max(1, prm->check_every);
@@ -1051,18 +1086,19 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     const int n_src = (int)u_nodes.size();
     // Real arithmetic when the systems are real (no boundary term) and the right-hand sides purely imaginary
     // (real q): p = 1j*u with G u = -w q.  Same COCG recurrences on half the bytes.
-    {
-        bool real = !overlay && prm->arithmetic != 1;
-        for (auto& v : u_q) real = real && (v.y == 0.0);
-        w->real = false;
-        if (real) {
-            bool ok = false;
-            FDB_DISPATCH_F(F, query_real(sys, w, &ok));
-            real = ok;
-        }
-        w->real = real;
-        res->real_arithmetic = real ? 1 : 0;
+    bool real = !overlay && prm->arithmetic != 1 && F >= 4;
+    for (auto& v : u_q) real = real && (v.y == 0.0);
+    // no wider than the number of frequencies needs
+    while (F / 2 >= (real ? 4 : 1) && F / 2 >= nf) F /= 2;
+    SweepWork* w = get_work(sys, F);
+    w->real = false;
+    if (real) {
+        bool ok = false;
+        FDB_DISPATCH_F(F, query_real(sys, w, &ok));
+        real = ok;
     }
+    w->real = real;
+    res->real_arithmetic = real ? 1 : 0;
     DevBuf<int32_t> d_src_nodes; DevBuf<double2> d_src_q;
     d_src_nodes.alloc(std::max(1, n_src)); d_src_q.alloc(std::max(1, n_src));
     if (n_src) {
@@ -1160,7 +1196,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         FDB_CUDA(cudaGetLastError());
 
         bool finished_any = false;
-        std::vector<char> done(F, 0);
+        std::vector<char> done(kMaxF, 0);
         for (int f = 0; f < F; ++f) {
             if (slot_freq[f] < 0) continue;
             if (!h.active[f] || h.iters[f] >= prm->max_iter) { done[f] = 1; finished_any = true; }
@@ -1199,6 +1235,69 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                                     (size_t)n_rcv * sizeof(double2), cudaMemcpyDefault));
             --n_busy;
             any_reset = assign(f) || any_reset;
+        }
+
+        // Tail of the sweep: the queue is empty and slots fall idle, but the fused SpMV costs the same whatever the
+        // number of live slots.  Move the live slots into a narrower batch as soon as they fit one.
+        if (next >= nf && n_busy > 0 && !any_reset) {
+            int F2 = F;
+            const int fmin = w->real ? 4 : 1;
+            while (F2 / 2 >= fmin && F2 / 2 >= n_busy) F2 /= 2;
+            if (F2 < F) {
+                SweepWork* w2 = new_work(sys, F2);
+                w2->real = w->real;
+                SlotMap map;
+                Scalars h2;
+                memset(&h2, 0, sizeof(h2));
+                h2.tol2 = h.tol2;
+                std::vector<double2> coef2((size_t)std::max(1, ng) * F2, make_double2(0.0, 0.0));
+                std::vector<int64_t> freq2(F2, -1);
+                std::vector<char> used2(F2, 0);
+                int j = 0;
+                for (int f = 0; f < kMaxF; ++f) map.src[f] = -1;
+                for (int f = 0; f < F2; ++f) fill_slot(h2, coef2, F2, ng, f, 1.0, nullptr, 0.0);
+                for (int f = 0; f < F; ++f) {
+                    if (slot_freq[f] < 0) continue;
+                    map.src[j] = f;
+                    h2.rho[j] = h.rho[f]; h2.pq[j] = h.pq[f]; h2.beta[j] = h.beta[f]; h2.rr[j] = h.rr[f]; h2.bb[j] = h.bb[f];
+                    h2.w2[j] = h.w2[f]; h2.rhs_scale[j] = h.rhs_scale[f]; h2.active[j] = h.active[f]; h2.iters[j] = h.iters[f];
+                    for (int g = 0; g < ng; ++g) coef2[(size_t)g * F2 + j] = coef[(size_t)g * F + f];
+                    freq2[j] = slot_freq[f];
+                    used2[j] = 1;
+                    ++j;
+                }
+                const int rg = (int)std::min<int64_t>(grid_for(N * F2, kBlock), w->grid);
+                if (w->real) {
+                    k_repack<double><<<rg, kBlock, 0, s>>>((const double*)w->x.p, F, (double*)w2->x.p, F2, map, N);
+                    k_repack<double><<<rg, kBlock, 0, s>>>((const double*)w->r.p, F, (double*)w2->r.p, F2, map, N);
+                    k_repack<double><<<rg, kBlock, 0, s>>>((const double*)w->p.p, F, (double*)w2->p.p, F2, map, N);
+                } else {
+                    k_repack<double2><<<rg, kBlock, 0, s>>>(w->x.p, F, w2->x.p, F2, map, N);
+                    k_repack<double2><<<rg, kBlock, 0, s>>>(w->r.p, F, w2->r.p, F2, map, N);
+                    k_repack<double2><<<rg, kBlock, 0, s>>>(w->p.p, F, w2->p.p, F2, map, N);
+                }
+                n_kernels += 3;
+                if (overlay) {
+                    // the precomputed 1/diag depends on the slot's frequency: rebuild it for the moved slots
+                    for (int f = 0; f < j; ++f) h2.reset[f] = 1;
+                    upload_scalars(sys, w2, h2, coef2);
+                    k_jacobi_launch(sys, w2, F2);
+                    n_kernels += 1;
+                    for (int f = 0; f < j; ++f) h2.reset[f] = 0;
+                }
+                FDB_CUDA(cudaGetLastError());
+                FDB_CUDA(cudaStreamSynchronize(s));
+                free_sweep_work(w);
+                sys->work = w = w2;
+                F = F2;
+                h = h2;
+                coef.swap(coef2);
+                slot_freq.swap(freq2);
+                slot_used.swap(used2);
+                if (n_rcv) { w->rcv_out.alloc((size_t)F * n_rcv); rcv_host.resize((size_t)F * n_rcv); }
+                if (res->pN) w->stage.alloc((size_t)F * N);
+                ensure_graph(sys, w, F, check_every, overlay);
+            }
         }
     }
     FDB_CUDA(cudaEventRecord(ev1, s));

@@ -13,6 +13,7 @@ ap.add_argument("--shape", default="99,133,74")
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--rigid", type=int, default=1)
+ap.add_argument("--real", type=int, default=0)
 a = ap.parse_args()
 grid = fd.shoebox_tet4(*[int(t) for t in a.shape.split(",")])
 s = fd.System(0)
@@ -21,5 +22,5 @@ s.assemble_volume(1.21, 343.0)
 if not a.rigid:
     s.set_surface_mesh(grid.elem_surf, grid.domain_index_surf, np.arange(2, 8))
     s.assemble_surface()
-ms, nb = s.spmv_bench(a.batch, a.reps)
-print(f"spmv F={a.batch}: {ms*1e3:.1f} us, {nb/1e6:.1f} MB algorithmic, {nb/ms/1e6:.1f} GB/s")
+ms, nb = s.spmv_bench(a.batch, a.reps, with_boundary=not a.rigid, real=bool(a.real))
+print(f"spmv F={a.batch} real={a.real}: {ms*1e3:.1f} us, {nb/1e6:.1f} MB algorithmic, {nb/ms/1e6:.1f} GB/s")

@@ -1,0 +1,92 @@
+"""Turn the raw ncu output under gpurun_out/ into the committed summaries under profiles/ (run in the build container)."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GO = os.path.join(ROOT, "gpurun_out")
+R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(OUT, exist_ok=True)
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
+
+
+def launches():
+    p = os.path.join(GO, f"launches_{R}.csv")
+    if not os.path.isfile(p):
+        return
+    rows = [r for r in csv.reader(open(p)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        n = r[ki].split("(")[0]
+        agg[n][0] += 1
+        agg[n][1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(OUT, f"{R}_launches.md"), "w") as f:
+        f.write(f"# {R}: kernel launch list of `bench.py --steps 1 --warmup 3 --no-e2e --no-cpu`\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 900` (cold-cache, serialised launches: compare SHARES).\n\n"
+                "| kernel | launches | mean us | share of captured time |\n|---|---:|---:|---:|\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"| `{n}` | {c} | {t / c / 1000:.1f} | {t / tot:.3f} |\n")
+    with open(os.path.join(OUT, f"{R}_launches.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "gpu__time_duration_ns"])
+        for r in rows[1:]:
+            w.writerow([r[ki].split("(")[0], r[vi]])
+
+
+def capture(name, title):
+    rep = os.path.join(GO, f"{name}_{R}.ncu-rep")
+    if not os.path.isfile(rep):
+        return None
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, d = rows[0], rows[1], rows[2]
+    vals = {}
+    with open(os.path.join(OUT, f"{R}_{name}.md"), "w") as f:
+        f.write(f"# {R}: {title}\n\n`ncu --set full --clock-control none --import-source on`, one launch after warm-up, 1M-DOF config-4 mesh.\n\n"
+                f"kernel: `{d[hdr.index('Kernel Name')]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                f.write(f"| {k} | {d[i]} | {units[i]} |\n")
+                vals[k] = (d[i], units[i])
+    return vals
+
+
+def to_bytes(v):
+    x, u = float(v[0].replace(",", "")), v[1].lower()
+    return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+
+
+launches()
+v = capture("spmv_real16", "fused multi-frequency SpMV, batch 16, real arithmetic (the variant the rigid benchmark sweep launches)")
+capture("spmv_cpx8", "fused multi-frequency SpMV, batch 8, complex arithmetic (admittance sweeps)")
+if v:
+    tr = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
+    json.dump({"kernel": "k_spmv_tma<16, real>", "dram_bytes_per_launch": tr, "source": f"profiles/{R}_spmv_real16.md"},
+              open(os.path.join(OUT, "spmv_traffic.json"), "w"))
+print(os.listdir(OUT))

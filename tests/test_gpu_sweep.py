@@ -173,3 +173,69 @@ def test_config1_size_residual_and_oracle(gpu_lib):
         assert np.linalg.norm(b - G @ pN[n]) / np.linalg.norm(b) < 1e-8
     ref = O.solve_sweep(H, Q, A, {k + 2: mu[k] for k in range(6)}, np.arange(2, 8), freq[[0, 3]], q)
     assert _rel_rows(pN[[0, 3]], ref).max() < 1e-6
+
+
+def test_real_arithmetic_matches_complex(gpu_lib):
+    """Rigid walls + real sources: the sweep runs in real arithmetic (p = 1j*u); same answer as the complex path."""
+    from conftest import Golden
+    g = Golden("tet4_shoebox_rigid")
+    s = _solver_system(g.H, g.Q, g.A)
+    freq = np.arange(30.0, 47.0)       # 17 frequencies: refill of the 16 slots, then tail narrowing
+    w = 2 * np.pi * freq
+    mu = np.zeros((len(g.group_ids), len(freq)), dtype=complex)
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    a, _, sa = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=16)
+    b, _, sb = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=16, force_complex=True)
+    assert sa.real_arithmetic and not sb.real_arithmetic and sa.n_unconverged == 0 and sb.n_unconverged == 0
+    assert not a.real.any()                                # purely imaginary pressures, exactly
+    assert _rel_rows(a, b).max() < 1e-8
+    ref = O.solve_sweep(g.H.astype(np.complex128), g.Q.astype(np.complex128), [], {}, [], freq,
+                        O.source_vector(g.grid.nos, g.src, g.src_q))
+    assert _rel_rows(a, ref).max() < 1e-6
+    # a complex source amplitude or a non-zero admittance switches the real path off
+    _, _, sc = s.sweep(w[:2], mu[:, :2], src, [1e-4 + 1e-5j], tol=1e-9, batch=16)
+    assert not sc.real_arithmetic
+    mu2 = mu.copy(); mu2[0] = 1e-5
+    _, _, sd = s.sweep(w[:2], mu2[:, :2], src, g.src_q, tol=1e-9, batch=16)
+    assert not sd.real_arithmetic
+
+
+def test_results_land_at_their_frequency_index(gpu_lib):
+    """Slots are loaded in descending frequency order and refilled as they converge: outputs stay in input order."""
+    from conftest import Golden
+    g = Golden("tet4_cplx_room")
+    s = _solver_system(g.H, g.Q, g.A)
+    rng = np.random.default_rng(3)
+    freq = rng.permutation(np.linspace(25.0, 240.0, 23))
+    w = 2 * np.pi * freq
+    mu = np.array([np.resize(g.mu[int(k)], len(freq)) * rng.uniform(0.5, 2.0, len(freq)) for k in g.group_ids])
+    src = [O.closest_node(g.grid.nos, c) for c in g.src]
+    pN, _, st = s.sweep(w, mu, src, g.src_q, tol=1e-11, batch=4, check_every=8)
+    assert st.n_unconverged == 0
+    muo = {int(k): mu[i] for i, k in enumerate(g.group_ids)}
+    ref = O.solve_sweep(g.H.astype(np.complex128), g.Q.astype(np.complex128), g.A, muo, g.group_ids, freq,
+                        O.source_vector(g.grid.nos, g.src, g.src_q))
+    assert _rel_rows(pN, ref).max() < 1e-7
+
+
+def test_config2_tet10_admittance_wall(gpu_lib):
+    """Config 2 in the small: Tet10 shoebox (5 733 DOF) with a normalized-admittance wall, GPU assembly + sweep vs oracle."""
+    import femder_b200 as fd
+    grid = fd.to_tet10(fd.shoebox_tet4(8, 10, 6, jitter=0.15))
+    AP = fd.AirProperties()
+    AC = fd.AlgControls(AP, freq_vec=[20.0, 57.0, 101.0, 160.0, 200.0])
+    BC = fd.BC(AC, AP)
+    for t in range(2, 7):
+        BC.rigid(t)
+    BC.normalized_admittance(7, 0.02)
+    S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+    R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+    obj = fd.FEM3D(grid, S, R, AP, AC, BC, tol=1e-10)
+    obj.compute(timeit=False)
+    obj.evaluate(R)
+    ref = O.compute(grid, AC.freq, BC.mu, S.coord, S.q.ravel(), 343.0, 1.21)
+    assert np.array_equal(obj.H.indices, ref["H"].indices)
+    assert np.abs(obj.H.data - ref["H"].data).max() / np.abs(ref["H"].data).max() < 1e-12
+    assert np.abs(obj.A[-1].data - ref["A"][-1].data).max() / np.abs(ref["A"][-1].data).max() < 1e-12
+    assert _rel_rows(obj.pN, ref["pN"]).max() < 1e-6
+    assert np.abs(obj.spl - O.p2SPL(O.evaluate(grid.nos, grid.elem_vol, ref["pN"], R.coord))).max() < 0.01
