@@ -242,7 +242,7 @@ def run_ours(args):
         for g in group_ids:
             BC.rigid(int(g))
         obj = fd.FEM3D(grid, S, R, AP, AC, BC, device=local_rank, stream=stream.cuda_stream, tol=args.tol,
-                       max_iter=args.max_iter, batch=F, check_every=args.check_every)
+                       max_iter=args.max_iter, batch=F, check_every=args.check_every, shard=False)  # every rank runs its own step
         obj._sys = sysm            # reuse the device allocation; everything below is recomputed from the host buffers
         obj._sys_key = None        # force mesh upload + pattern build + assembly
         obj.compute(timeit=False, keep_pN=False)
@@ -296,7 +296,8 @@ def run_ours(args):
             BC1.rigid(int(g))
         S1 = fd.Source(coord=g1.nos[g1.closest_node(SRC)], q=[1e-4])
         R1 = fd.Receiver(coord=g1.nos[g1.closest_node(RCV)])
-        o1 = fd.FEM3D(g1, S1, R1, AP, AC1, BC1, device=local_rank, tol=args.tol, max_iter=args.max_iter, check_every=args.check_every)
+        o1 = fd.FEM3D(g1, S1, R1, AP, AC1, BC1, device=local_rank, tol=args.tol, max_iter=args.max_iter, check_every=args.check_every,
+                      shard=False)
         o1.compute(timeit=False, keep_pN=False)      # warm-up (graphs, allocations)
         o1.H = None
         t1 = time.perf_counter()

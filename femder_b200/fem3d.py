@@ -75,7 +75,7 @@ def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
 
 class FEM3D:
     def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=50000, batch="auto",
-                 check_every=32, warm_start=False, compat_complex64=False):
+                 check_every=32, warm_start=False, compat_complex64=False, shard=True):
         self.BC = BC
         if BC is not None:
             self.mu = BC.mu
@@ -125,6 +125,7 @@ class FEM3D:
         self.check_every = check_every
         self.warm_start = warm_start
         self.compat_complex64 = compat_complex64
+        self.shard = shard  # under torch.distributed: split the frequencies over the ranks and gather the rows at the end
         self.stats = None
         self._device = device
         self._stream = stream
@@ -151,7 +152,7 @@ class FEM3D:
     # ---- device system -----------------------------------------------------------------------
     def _system(self):
         rank, world, local_rank = sharding.dist_info()
-        dev = self._device if self._device is not None else (local_rank if world > 1 else 0)
+        dev = self._device if self._device is not None else (local_rank if world > 1 else 0)  # one process per GPU
         if self._sys is None:
             self._sys = System(dev, self._stream)
         return self._sys
@@ -220,7 +221,7 @@ class FEM3D:
             rcv_nodes = np.array([s[0] for s in st], dtype=np.int32)
             rcv_w = np.array([s[1] for s in st], dtype=np.float64)
 
-        rank, world, _ = sharding.dist_info()
+        rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
         owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch,
