@@ -19,7 +19,7 @@
 
 namespace fdb {
 
-constexpr int kMaxF = 16;
+constexpr int kMaxF = 64;   // widest batch: small meshes are launch-bound, wide batches amortise the fixed costs
 constexpr int kBlock = 256;
 
 struct __align__(16) Scalars {
@@ -54,7 +54,7 @@ struct SweepWork {
     int graph_F = 0;
     bool graph_overlay = false;
     int spmv_cfg = 0;             // FDB_SPMV_CFG: 0..3 bulk-copy pipeline shapes; 8..12 plain kernel launch shapes (tuning aid)
-    int tma_stage_entries[2] = {0, 0};
+    int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
     bool graph_real = false;
@@ -162,21 +162,24 @@ __device__ __forceinline__ void finalize_last_block(double* __restrict__ partial
 template <int F, int NV, int BLOCK, typename Fin>
 __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
                                                       unsigned int* __restrict__ ticket, Fin fin) {
-    __shared__ double s_red[BLOCK / 32][kMaxF][NV];
+    __shared__ double s_red[BLOCK / 32][32][NV];
+    constexpr int SW = F < 32 ? F : 32;   // distinct frequencies inside one warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double w[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) w[i] = warp_sum_by_f<F>(v[i]);
-    if (lane < F) {
+    if (lane < SW) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) s_red[warp][lane][i] = w[i];
     }
     __syncthreads();
     if (threadIdx.x < F) {
+        const int l = threadIdx.x & 31;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double s = 0;
-            for (int k = 0; k < BLOCK / 32; ++k) s += s_red[k][threadIdx.x][i];
+            for (int k = 0; k < BLOCK / 32; ++k)
+                if ((k * 32 + l) % F == (int)threadIdx.x) s += s_red[k][l][i];   // warps whose lane l carries this frequency
             partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
         }
     }
@@ -751,6 +754,9 @@ struct Launch {
     // ---- plain (LDG) SpMV: complex only; used for F = 1 and as the fallback when a tile does not fit shared memory
     template <int BLOCK, int MINB>
     static void spmv_cfg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+        if constexpr (F > 32) {
+            throw Error("femder_b200: the plain SpMV kernel supports batch <= 32 (rows of this mesh are too long for the bulk-copy pipeline)");
+        } else {
         const int64_t N = w->N;
         const int rpw = 32 / F;
         const int64_t groups = (N + rpw - 1) / rpw;
@@ -764,6 +770,7 @@ struct Launch {
             if (overlay) args(k_spmv<F, true, true, BLOCK, MINB>); else args(k_spmv<F, true, false, BLOCK, MINB>);
         } else {
             if (overlay) args(k_spmv<F, false, true, BLOCK, MINB>); else args(k_spmv<F, false, false, BLOCK, MINB>);
+        }
         }
     }
     static void spmv_ldg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
@@ -779,7 +786,7 @@ struct Launch {
     // ---- bulk-copy pipeline SpMV
     template <int TS>
     static int stage_entries(fdb_system* sys, SweepWork* w) {
-        int& cached = w->tma_stage_entries[TS == 8 ? 0 : 1];
+        int& cached = w->tma_stage_entries[TS == 4 ? 2 : (TS == 8 ? 0 : 1)];
         if (cached == 0) {
             const int64_t S = sys->n_slices, n_tiles = (S + TS - 1) / TS;
             int64_t mx = 0;
@@ -831,18 +838,23 @@ struct Launch {
             constexpr int RPW = 32 / LPR;                        // rows per warp and pass
             constexpr int W8 = (64 / RPW < 16) ? (64 / RPW < 1 ? 1 : 64 / RPW) : 16;      // consumer warps for an 8-slice tile
             constexpr int W16 = (128 / RPW < 16) ? (128 / RPW < 1 ? 1 : 128 / RPW) : 16;  // ... for a 16-slice tile
+            constexpr int W4 = (32 / RPW < 16) ? (32 / RPW < 1 ? 1 : 32 / RPW) : 16;      // ... for a 4-slice tile
             switch (w->spmv_cfg) {
                 case 1: return spmv_tma<CPX, W8, 8, 2, 4>(sys, w, x, y, dot, overlay);
                 case 2: return spmv_tma<CPX, W8, 8, 3, 8>(sys, w, x, y, dot, overlay);
                 case 3: return spmv_tma<CPX, W8, 8, 2, 8>(sys, w, x, y, dot, overlay);
-                default: return spmv_tma<CPX, W16, 16, 2, 8>(sys, w, x, y, dot, overlay);  // measured best at F = 4, 8
+                default:
+                    // 128-row tiles (measured best); smaller tiles when the rows are long (Tet10, unstructured meshes)
+                    if (spmv_tma<CPX, W16, 16, 2, 8>(sys, w, x, y, dot, overlay)) return true;
+                    if (spmv_tma<CPX, W8, 8, 2, 8>(sys, w, x, y, dot, overlay)) return true;
+                    return spmv_tma<CPX, W4, 4, 2, 8>(sys, w, x, y, dot, overlay);
             }
         }
     }
     // can a real-arithmetic sweep run at this batch width on this mesh?
     static bool real_supported(fdb_system* sys, SweepWork* w) {
         if (F < 4 || w->spmv_cfg >= 8) return false;
-        return (size_t)2 * stage_entries<16>(sys, w) * 20 <= 100 * 1024 && (size_t)3 * stage_entries<8>(sys, w) * 20 <= 100 * 1024;
+        return (size_t)2 * stage_entries<4>(sys, w) * 20 <= 100 * 1024;   // the smallest tile shape must fit
     }
     static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         if (w->real) {
@@ -942,13 +954,15 @@ struct Launch {
         case 4: Launch<4>::CALL; break;                           \
         case 8: Launch<8>::CALL; break;                           \
         case 16: Launch<16>::CALL; break;                         \
-        default: throw Error("femder_b200: batch must be 1, 2, 4, 8 or 16"); \
+        case 32: Launch<32>::CALL; break;                         \
+        case 64: Launch<64>::CALL; break;                         \
+        default: throw Error("femder_b200: batch must be 1, 2, 4, 8, 16, 32 or 64"); \
     }
 
 static SweepWork* new_work(fdb_system* sys, int F);
 
 static SweepWork* get_work(fdb_system* sys, int F) {
-    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16, "batch must be 1, 2, 4, 8 or 16");
+    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16 || F == 32 || F == 64, "batch must be 1, 2, 4, 8, 16, 32 or 64");
     FDB_REQUIRE(sys->have_pattern && sys->have_hq, "pattern and H/Q values must be set before the sweep");
     SweepWork* w = sys->work;
     if (w && (w->F != F || w->N != sys->n_nodes || w->n_groups != sys->n_groups)) {
@@ -1035,7 +1049,10 @@ static void k_jacobi_launch(fdb_system* sys, SweepWork* w, int F) {
         case 2: go(k_jacobi<2>); break;
         case 4: go(k_jacobi<4>); break;
         case 8: go(k_jacobi<8>); break;
-        default: go(k_jacobi<16>); break;
+        case 16: go(k_jacobi<16>); break;
+        case 32: go(k_jacobi<32>); break;
+        case 64: go(k_jacobi<64>); break;
+        default: throw Error("femder_b200: unsupported batch width");
     }
 }
 
@@ -1046,7 +1063,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     FDB_REQUIRE(prm->n_freq >= 0 && prm->n_src >= 0 && prm->n_rcv >= 0, "negative count");
     FDB_REQUIRE(prm->tol > 0 && prm->max_iter > 0, "tol and max_iter must be positive");
     int F = prm->batch;
-    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16, "batch must be 1, 2, 4, 8 or 16");
+    FDB_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8 || F == 16 || F == 32 || F == 64, "batch must be 1, 2, 4, 8, 16, 32 or 64");
     const int64_t N = sys->n_nodes;
     const int ng = sys->n_groups;
     FDB_REQUIRE(ng == 0 || prm->mu != nullptr, "mu is required when the system has boundary groups");
@@ -1239,7 +1256,8 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
 
         // Tail of the sweep: the queue is empty and slots fall idle, but the fused SpMV costs the same whatever the
         // number of live slots.  Move the live slots into a narrower batch as soon as they fit one.
-        if (next >= nf && n_busy > 0 && !any_reset) {
+        static const bool no_narrow = getenv("FDB_NO_NARROW") != nullptr;   // debugging aid
+        if (next >= nf && n_busy > 0 && !any_reset && !no_narrow) {
             int F2 = F;
             const int fmin = w->real ? 4 : 1;
             while (F2 / 2 >= fmin && F2 / 2 >= n_busy) F2 /= 2;

@@ -14,7 +14,8 @@ from scipy.sparse import csc_matrix
 from . import _lib
 from ._lib import SweepParams, SweepResult, check, ptr
 
-VALID_BATCH = (1, 2, 4, 8, 16)
+VALID_BATCH = (1, 2, 4, 8, 16, 32, 64)
+SMALL_MESH_NODES = 200_000  # below this the kernels are launch-bound: use wider batches
 
 
 def _i32(a):
@@ -255,6 +256,8 @@ class System:
             # frequencies fill the 128-byte gather line that 8 complex ones do
             real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex
             batch = 16 if real else 8
+            if self.n_nodes <= SMALL_MESH_NODES:
+                batch *= 4   # small meshes: the kernels are latency-bound, wide batches amortise the fixed cost per launch
         if batch not in VALID_BATCH:
             raise ValueError(f"batch must be one of {VALID_BATCH} or 'auto'")
         if len(src_q) != len(src_nodes):

@@ -90,7 +90,7 @@ typedef struct fdb_sweep_params {
     const double* src_q;      /* [n_src]  complex volume velocities q */
     double tol;               /* relative residual ||b - G x|| / ||b|| to reach */
     int32_t max_iter;
-    int32_t batch;            /* frequencies per fused SpMV: 1, 2, 4, 8 or 16 */
+    int32_t batch;            /* solver slots = frequencies per fused SpMV: 1, 2, 4, 8, 16, 32 or 64 */
     int32_t check_every;      /* iterations between host convergence checks (one CUDA graph launch) */
     int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
     int32_t precond;          /* 0: Jacobi */

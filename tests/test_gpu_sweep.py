@@ -20,7 +20,7 @@ def _solver_system(H, Q, A_list):
     return s
 
 
-@pytest.mark.parametrize("F", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("F", [1, 2, 4, 8, 16, 32, 64])
 def test_spmv_matches_scipy(gpu_lib, golden, F):
     g = golden
     s = _solver_system(g.H, g.Q, g.A)
@@ -52,7 +52,7 @@ def test_sweep_on_reference_matrices(gpu_lib, golden):
     assert np.abs(O.p2SPL(pR) - O.p2SPL(g.pR)).max() < 0.01
 
 
-@pytest.mark.parametrize("batch", [1, 2, 8, 16])
+@pytest.mark.parametrize("batch", [1, 2, 8, 16, 64])
 def test_sweep_batches_agree(gpu_lib, batch):
     from conftest import Golden
     g = Golden("tet4_shoebox_jitter")
