@@ -107,7 +107,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, shape=(26, 34, 22), cores=None):
     from oracle import cpu_baseline
-    return cpu_baseline.run(steps, warmup, shape=shape, cores=cores, f_lo=F_LO, f_hi=F_HI, src=SRC, rcv=RCV, c0=C0, rho0=RHO0)
+    workload_dof = (SHAPE[0] + 1) * (SHAPE[1] + 1) * (SHAPE[2] + 1)
+    return cpu_baseline.run(steps, warmup, shape=shape, cores=cores, f_lo=F_LO, f_hi=F_HI, src=SRC, rcv=RCV, c0=C0, rho0=RHO0,
+                            workload_dof=workload_dof)
 
 
 def run_reference(args):
@@ -125,7 +127,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reference_sample": r["sample"]},
-            "cpu_baseline": {"value": r["value"], "unit": "frequencies/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"],
+            "cpu_baseline": {"value": r["value"], "unit": "frequencies/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                             "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"]},
             "e2e": {"value": r["value"], "unit": "frequencies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

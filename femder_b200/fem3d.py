@@ -74,7 +74,7 @@ def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
 
 
 class FEM3D:
-    def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=50000, batch="auto",
+    def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=200000, batch="auto",
                  check_every=32, warm_start=False, compat_complex64=False, shard=True):
         self.BC = BC
         if BC is not None:

@@ -44,7 +44,7 @@ def _solve(freq):
 
 
 def run(steps, warmup, shape=(26, 34, 22), cores=None, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0, 1.2), rcv=(2.0, 3.0, 1.25),
-        c0=343.0, rho0=1.21):
+        c0=343.0, rho0=1.21, workload_dof=None):
     cores = cores or os.cpu_count() or 1
     total_steps = steps + warmup
     rng = np.random.default_rng(0)
@@ -60,8 +60,13 @@ def run(steps, warmup, shape=(26, 34, 22), cores=None, f_lo=20.0, f_hi=500.0, sr
             if s >= warmup:
                 times.append(dt)
     total = float(np.sum(times))
+    measured = steps * cores / total
+    scale = (n_dof / workload_dof) if workload_dof else 1.0
     sample = (f"oracle port of the reference algorithm (FP64 assembly, then per frequency: build G, scipy SuperLU factorise + solve, "
               f"PARDISO stand-in) on the config-1 shoebox {shape[0]}x{shape[1]}x{shape[2]} cells = {n_dof} DOF; {steps} steps x {cores} "
-              f"frequencies (one per core) drawn from {f_lo:g}-{f_hi:g} Hz; a 1M-DOF sparse LU does not fit this host's RAM, so the "
-              f"reference's direct solve cannot run the 1M-DOF workload at all")
-    return {"value": steps * cores / total, "seconds": total, "cores": cores, "N": n_dof, "sample": sample}
+              f"frequencies (one per core) drawn from {f_lo:g}-{f_hi:g} Hz: MEASURED {measured:.4g} frequencies/s at {n_dof} DOF. "
+              f"A 1M-DOF sparse LU does not fit this host's RAM, so the reference's direct solve cannot run the workload at all")
+    if workload_dof:
+        sample += (f"; `value` is that measurement scaled LINEARLY in DOF to the {workload_dof}-DOF workload (x {scale:.5f}), an "
+                   f"extrapolation that favours the reference (sparse LU cost grows faster than linearly, ~N^2 in 3-D)")
+    return {"value": measured * scale, "measured_at_sample": measured, "seconds": total, "cores": cores, "N": n_dof, "sample": sample}
