@@ -197,7 +197,7 @@ __device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], dou
 // ------------------------------------------------------------------------------------------------
 // launch shapes (threads per block, resident blocks per SM); FDB_SPMV_CFG picks one at run time (tuning aid)
 struct SpmvCfg { int block, per_sm; };
-constexpr SpmvCfg kSpmvCfgs[] = {{512, 2}, {512, 3}, {256, 4}, {1024, 1}, {256, 6}};
+constexpr SpmvCfg kSpmvCfgs[] = {{512, 2}};   // launch shape of the plain kernel (measured best of 5)
 
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 v;
@@ -205,12 +205,13 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
     return v;
 }
 
-template <int F, bool DOT, bool OVERLAY, int BLOCK, int MINB>
+template <typename T, int F, bool DOT, bool OVERLAY, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
        const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
-       const double2* __restrict__ coef, const double2* __restrict__ x, double2* __restrict__ y, int64_t n_rows,
+       const double2* __restrict__ coef, const T* __restrict__ x, T* __restrict__ y, int64_t n_rows,
        Scalars* __restrict__ sc, double* __restrict__ partial) {
+    static_assert(!(OVERLAY && std::is_same<T, double>::value), "a boundary term makes the system complex");
     constexpr int RPW = 32 / F;                 // rows per warp
     constexpr int NWARP = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -230,11 +231,12 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
             const int width = sell_off[slice + 1] - off;
             const int32_t* ip = sell_idx + ((int64_t)off * 8 + (row & 7));
             const double2* mp = sell_hq + ((int64_t)off * 8 + (row & 7));
-            double2 acc = make_double2(0.0, 0.0);
+            T acc = v_zero<T>();
             int k = 0;
             for (; k + 4 <= width; k += 4) {
                 int c[4];
-                double2 m[4], xv[4];
+                double2 m[4];
+                T xv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) c[u] = __ldg(ip + (k + u) * 8);
 #pragma unroll
@@ -242,36 +244,26 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
 #pragma unroll
                 for (int u = 0; u < 4; ++u) m[u] = ld_stream(mp + (k + u) * 8);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double gk = m[u].x - w2 * m[u].y;
-                    acc.x += gk * xv[u].x;
-                    acc.y += gk * xv[u].y;
-                }
+                for (int u = 0; u < 4; ++u) acc = v_add(acc, r_mul(m[u].x - w2 * m[u].y, xv[u]));
             }
             for (; k < width; ++k) {
                 const int c = __ldg(ip + k * 8);
                 const double2 m = ld_stream(mp + k * 8);
-                const double2 xv = __ldg(&x[(int64_t)c * F + f]);
-                const double gk = m.x - w2 * m.y;
-                acc.x += gk * xv.x;
-                acc.y += gk * xv.y;
+                acc = v_add(acc, r_mul(m.x - w2 * m.y, __ldg(&x[(int64_t)c * F + f])));
             }
-            if (OVERLAY) {
+            if constexpr (OVERLAY) {
                 const int ob = ov_ptr[row], oe = ov_ptr[row + 1];
                 for (int o = ob; o < oe; ++o) {
                     const int2 cg = ov_cg[o];
                     const double a = ov_val[o];
                     const double2 cf = coef[cg.y * F + f];
                     const double2 xv = __ldg(&x[(int64_t)cg.x * F + f]);
-                    const double2 t = cmul(make_double2(cf.x * a, cf.y * a), xv);
-                    acc.x += t.x;
-                    acc.y += t.y;
+                    acc = v_add(acc, cmul(make_double2(cf.x * a, cf.y * a), xv));
                 }
             }
             y[row * F + f] = acc;
             if (DOT) {
-                const double2 xv = __ldg(&x[row * F + f]);
-                const double2 d = cmul(xv, acc);
+                const double2 d = v_dot(__ldg(&x[row * F + f]), acc);
                 dot[0] += d.x;
                 dot[1] += d.y;
             }
@@ -284,14 +276,6 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K5 (bulk-copy pipeline): same arithmetic as k_spmv.  A block owns a contiguous range of tiles (TS slices =
-// 8*TS rows).  The only dependent chain in an SpMV is column index -> x gather, so the column indices are what
-// gets staged: a producer warp issues one 1-D bulk copy per tile (cp.async.bulk, the tile's indices are
-// contiguous in the SELL-8 array) into an NST-deep shared-memory ring, completion on an mbarrier, several
-// tiles ahead of the consumers.  NWARP consumer warps wait on the "full" barrier, read indices from shared
-// memory, gather x through L1 with 256-bit loads, stream (H,Q) straight from HBM with L1 bypassed (no
-// dependency, issued with the gathers) and release the stage on the "empty" barrier.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -751,36 +735,36 @@ __global__ void __launch_bounds__(kBlock) k_export(const T* __restrict__ x, int6
 // ------------------------------------------------------------------------------------------------
 template <int F>
 struct Launch {
-    // ---- plain (LDG) SpMV: complex only; used for F = 1 and as the fallback when a tile does not fit shared memory
-    template <int BLOCK, int MINB>
-    static void spmv_cfg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
+    // ---- plain (LDG) SpMV: narrow batches (F = 1, 2 and the tail of a sweep) and the fallback when a mesh's rows are too
+    //      long for the bulk-copy pipeline's shared-memory tiles
+    template <typename T, int BLOCK, int MINB>
+    static void spmv_cfg(fdb_system* sys, SweepWork* w, const T* x, T* y, bool dot, bool overlay) {
         if constexpr (F > 32) {
             throw Error("femder_b200: the plain SpMV kernel supports batch <= 32 (rows of this mesh are too long for the bulk-copy pipeline)");
         } else {
-        const int64_t N = w->N;
-        const int rpw = 32 / F;
-        const int64_t groups = (N + rpw - 1) / rpw;
-        const int64_t per_block = BLOCK / 32;
-        int grid = (int)std::min<int64_t>((groups + per_block - 1) / per_block, (int64_t)sys->num_sms * MINB);
-        auto args = [&](auto kern) {
-            kern<<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p, sys->ov_cg.p,
-                                                 sys->ov_val.p, w->coef.p, x, y, N, w->sc.p, (double*)w->partial.p);
-        };
-        if (dot) {
-            if (overlay) args(k_spmv<F, true, true, BLOCK, MINB>); else args(k_spmv<F, true, false, BLOCK, MINB>);
-        } else {
-            if (overlay) args(k_spmv<F, false, true, BLOCK, MINB>); else args(k_spmv<F, false, false, BLOCK, MINB>);
-        }
+            const int64_t N = w->N;
+            const int rpw = 32 / F;
+            const int64_t groups = (N + rpw - 1) / rpw;
+            const int64_t per_block = BLOCK / 32;
+            int grid = (int)std::min<int64_t>((groups + per_block - 1) / per_block, (int64_t)sys->num_sms * MINB);
+            auto args = [&](auto kern) {
+                kern<<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p, sys->ov_cg.p,
+                                                     sys->ov_val.p, w->coef.p, x, y, N, w->sc.p, (double*)w->partial.p);
+            };
+            if constexpr (std::is_same<T, double2>::value) {
+                if (dot) {
+                    if (overlay) args(k_spmv<T, F, true, true, BLOCK, MINB>); else args(k_spmv<T, F, true, false, BLOCK, MINB>);
+                } else {
+                    if (overlay) args(k_spmv<T, F, false, true, BLOCK, MINB>); else args(k_spmv<T, F, false, false, BLOCK, MINB>);
+                }
+            } else {
+                if (dot) args(k_spmv<T, F, true, false, BLOCK, MINB>); else args(k_spmv<T, F, false, false, BLOCK, MINB>);
+            }
         }
     }
-    static void spmv_ldg(fdb_system* sys, SweepWork* w, const double2* x, double2* y, bool dot, bool overlay) {
-        switch (w->spmv_cfg - 8) {
-            case 1: spmv_cfg<kSpmvCfgs[1].block, kSpmvCfgs[1].per_sm>(sys, w, x, y, dot, overlay); break;
-            case 2: spmv_cfg<kSpmvCfgs[2].block, kSpmvCfgs[2].per_sm>(sys, w, x, y, dot, overlay); break;
-            case 3: spmv_cfg<kSpmvCfgs[3].block, kSpmvCfgs[3].per_sm>(sys, w, x, y, dot, overlay); break;
-            case 4: spmv_cfg<kSpmvCfgs[4].block, kSpmvCfgs[4].per_sm>(sys, w, x, y, dot, overlay); break;
-            default: spmv_cfg<kSpmvCfgs[0].block, kSpmvCfgs[0].per_sm>(sys, w, x, y, dot, overlay); break;
-        }
+    template <typename T>
+    static void spmv_ldg(fdb_system* sys, SweepWork* w, const T* x, T* y, bool dot, bool overlay) {
+        spmv_cfg<T, kSpmvCfgs[0].block, kSpmvCfgs[0].per_sm>(sys, w, x, y, dot, overlay);
     }
 
     // ---- bulk-copy pipeline SpMV
@@ -832,8 +816,8 @@ struct Launch {
     template <bool CPX>
     static bool spmv_tma_cfg(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         constexpr int LPR = CPX ? F / 2 : F / 4;              // lanes per row
-        if constexpr (LPR < 1) {
-            return false;
+        if constexpr (LPR < 2) {
+            return false;   // one lane per row scatters every 256-bit gather over 32 lines: the plain kernel is faster
         } else {
             constexpr int RPW = 32 / LPR;                        // rows per warp and pass
             constexpr int W8 = (64 / RPW < 16) ? (64 / RPW < 1 ? 1 : 64 / RPW) : 16;      // consumer warps for an 8-slice tile
@@ -853,16 +837,17 @@ struct Launch {
     }
     // can a real-arithmetic sweep run at this batch width on this mesh?
     static bool real_supported(fdb_system* sys, SweepWork* w) {
-        if (F < 4 || w->spmv_cfg >= 8) return false;
-        return (size_t)2 * stage_entries<4>(sys, w) * 20 <= 100 * 1024;   // the smallest tile shape must fit
+        if (F <= 32) return true;                                          // the plain kernel covers it
+        return (size_t)2 * stage_entries<4>(sys, w) * 20 <= 100 * 1024;   // wider: the smallest tile shape must fit
     }
     static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         if (w->real) {
-            if (!spmv_tma_cfg<false>(sys, w, x, y, dot, false)) throw Error("femder_b200: real-arithmetic SpMV not available for this mesh");
+            if (w->spmv_cfg < 8 && spmv_tma_cfg<false>(sys, w, x, y, dot, false)) return;
+            spmv_ldg<double>(sys, w, (const double*)x, (double*)y, dot, false);
             return;
         }
         if (w->spmv_cfg < 8 && spmv_tma_cfg<true>(sys, w, x, y, dot, overlay)) return;
-        spmv_ldg(sys, w, (const double2*)x, (double2*)y, dot, overlay);
+        spmv_ldg<double2>(sys, w, (const double2*)x, (double2*)y, dot, overlay);
     }
 
     static int egrid(SweepWork* w) {
@@ -1103,10 +1088,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     const int n_src = (int)u_nodes.size();
     // Real arithmetic when the systems are real (no boundary term) and the right-hand sides purely imaginary
     // (real q): p = 1j*u with G u = -w q.  Same COCG recurrences on half the bytes.
-    bool real = !overlay && prm->arithmetic != 1 && F >= 4;
+    bool real = !overlay && prm->arithmetic != 1;
     for (auto& v : u_q) real = real && (v.y == 0.0);
     // no wider than the number of frequencies needs
-    while (F / 2 >= (real ? 4 : 1) && F / 2 >= nf) F /= 2;
+    while (F / 2 >= 1 && F / 2 >= nf) F /= 2;
     SweepWork* w = get_work(sys, F);
     w->real = false;
     if (real) {
@@ -1259,8 +1244,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         static const bool no_narrow = getenv("FDB_NO_NARROW") != nullptr;   // debugging aid
         if (next >= nf && n_busy > 0 && !any_reset && !no_narrow) {
             int F2 = F;
-            const int fmin = w->real ? 4 : 1;
-            while (F2 / 2 >= fmin && F2 / 2 >= n_busy) F2 /= 2;
+            while (F2 / 2 >= 1 && F2 / 2 >= n_busy) F2 /= 2;
             if (F2 < F) {
                 SweepWork* w2 = new_work(sys, F2);
                 w2->real = w->real;
@@ -1353,7 +1337,7 @@ static bool bench_real(fdb_system* sys, SweepWork* w, int F, int flags) {
     bool ok = false;
     w->real = false;
     FDB_DISPATCH_F(F, query_real(sys, w, &ok));
-    FDB_REQUIRE(ok, "real-arithmetic SpMV needs batch >= 4 and tiles that fit shared memory");
+    FDB_REQUIRE(ok, "real-arithmetic SpMV at this batch width needs tiles that fit shared memory");
     return true;
 }
 
