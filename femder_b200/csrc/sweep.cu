@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/femder_b200.h"
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <type_traits>
 
@@ -34,6 +35,7 @@ struct __align__(16) Scalars {
     int active[kMaxF];
     int iters[kMaxF];
     int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
+    int bb_from_r0;        // ||b||^2 is taken from the start residual (general right-hand sides, zero starting guess)
     double tol2;
     unsigned int ticket[4];
 };
@@ -45,6 +47,10 @@ struct SweepWork {
     int grid = 0;
     DevBuf<double2> x, r, p, q, dinv, tmp;  // [N][F]
     DevBuf<double2> coef;              // [n_groups][F]  1j*omega*mu
+    DevBuf<double2> rcoef;             // [n_rhs_vec][F] coefficients of the extra right-hand-side vectors
+    int n_rn = 0;                      // nodes touched by extra right-hand-side vectors (complex sweeps only)
+    DevBuf<int32_t> rn_nodes, rn_ptr, rn_vec;   // per listed node: its (vector, value) terms
+    DevBuf<double> rn_val;
     DevBuf<double2> partial;           // [grid][F][2]
     DevBuf<Scalars> sc;
     DevBuf<double2> stage;             // [F][N] pN export staging
@@ -632,6 +638,25 @@ __global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* 
     if (all || sc->reset[f]) store_rhs(&dst[(int64_t)src_nodes[s] * F + f], sc->rhs_scale[f], src_q[s]);
 }
 
+// dst[node][f] += sum over the node's terms of rcoef[vec][f] * val   (one thread per (listed node, f): race-free, fixed order)
+template <int F>
+__global__ void k_add_rhs(const int32_t* __restrict__ rn_nodes, const int32_t* __restrict__ rn_ptr, const int32_t* __restrict__ rn_vec,
+                          const double* __restrict__ rn_val, int n_nodes, const double2* __restrict__ rcoef, bool all,
+                          const Scalars* __restrict__ sc, double2* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * F) return;
+    const int s = i / F, f = i % F;
+    if (!(all || sc->reset[f])) return;
+    double2 acc = dst[(int64_t)rn_nodes[s] * F + f];
+    for (int k = rn_ptr[s]; k < rn_ptr[s + 1]; ++k) {
+        const double2 c = rcoef[rn_vec[k] * F + f];
+        const double v = rn_val[k];
+        acc.x += c.x * v;
+        acc.y += c.y * v;
+    }
+    dst[(int64_t)rn_nodes[s] * F + f] = acc;
+}
+
 // reset slots: r = r - q    (r holds b on entry; q = G x0)
 template <typename T, int F>
 __global__ void __launch_bounds__(kBlock) k_sub(T* __restrict__ r, const T* __restrict__ q, int64_t n,
@@ -668,6 +693,7 @@ __global__ void __launch_bounds__(kBlock) k_start(T* __restrict__ p, const T* __
         sc->beta[ff] = make_double2(0.0, 0.0);
         sc->pq[ff] = make_double2(0.0, 0.0);
         sc->iters[ff] = 0;
+        if (sc->bb_from_r0) sc->bb[ff] = tot[2];
         sc->active[ff] = (tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
         sc->reset[ff] = 0;
     });
@@ -888,6 +914,13 @@ struct Launch {
             k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, false, w->sc.p, r);
             ++nk;
         }
+        if constexpr (std::is_same<T, double2>::value) {
+            if (w->n_rn) {
+                k_add_rhs<F><<<grid_for((int64_t)w->n_rn * F, 128), 128, 0, sys->stream>>>(w->rn_nodes.p, w->rn_ptr.p, w->rn_vec.p, w->rn_val.p,
+                                                                                         w->n_rn, w->rcoef.p, false, w->sc.p, r);
+                ++nk;
+            }
+        }
         if (keep_x) {
             spmv(sys, w, x, qq, false, overlay);
             k_sub<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(r, qq, ne, w->sc.p);
@@ -913,6 +946,11 @@ struct Launch {
         spmv(sys, w, x, qq, false, overlay);
         FDB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ne * sizeof(T), sys->stream));
         if (n_src) k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, true, w->sc.p, tmp);
+        if constexpr (std::is_same<T, double2>::value) {
+            if (w->n_rn)
+                k_add_rhs<F><<<grid_for((int64_t)w->n_rn * F, 128), 128, 0, sys->stream>>>(w->rn_nodes.p, w->rn_ptr.p, w->rn_vec.p, w->rn_val.p,
+                                                                                         w->n_rn, w->rcoef.p, true, w->sc.p, tmp);
+        }
         k_resnorm<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(tmp, qq, ne, w->sc.p, (double*)w->partial.p);
     }
     static void true_residual(fdb_system* sys, SweepWork* w, bool overlay, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
@@ -998,9 +1036,14 @@ static void fill_slot(Scalars& h, std::vector<double2>& coef, int F, int n_group
     }
 }
 
-static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, const std::vector<double2>& coef) {
+static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, const std::vector<double2>& coef,
+                           const std::vector<double2>* rcoef = nullptr) {
     FDB_CUDA(cudaMemcpyAsync(w->sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, sys->stream));
     FDB_CUDA(cudaMemcpyAsync(w->coef.p, coef.data(), coef.size() * sizeof(double2), cudaMemcpyHostToDevice, sys->stream));
+    if (rcoef && !rcoef->empty()) {
+        w->rcoef.alloc(rcoef->size());
+        FDB_CUDA(cudaMemcpyAsync(w->rcoef.p, rcoef->data(), rcoef->size() * sizeof(double2), cudaMemcpyHostToDevice, sys->stream));
+    }
     FDB_CUDA(cudaStreamSynchronize(sys->stream));  // pageable host buffers: be done before they change
 }
 
@@ -1086,9 +1129,52 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     double src_norm2 = 0;
     for (auto& v : u_q) src_norm2 += v.x * v.x + v.y * v.y;
     const int n_src = (int)u_nodes.size();
+    // extra right-hand-side vectors (velocity boundary conditions): regrouped per node so one thread owns a node
+    const int64_t nrv = prm->n_rhs_vec;
+    FDB_REQUIRE(nrv >= 0, "negative count");
+    std::vector<int32_t> rn_nodes, rn_ptr, rn_vec;
+    std::vector<double> rn_val, rhs_coef((size_t)nrv * nf * 2);
+    if (nrv) {
+        FDB_REQUIRE(prm->rhs_ptr && prm->rhs_coef, "right-hand-side vector arrays missing");
+        std::vector<int32_t> rp(nrv + 1);
+        FDB_CUDA(cudaMemcpy(rp.data(), prm->rhs_ptr, rp.size() * sizeof(int32_t), cudaMemcpyDefault));
+        const int64_t ne = rp[nrv];
+        FDB_REQUIRE(rp[0] == 0 && ne >= 0 && (ne == 0 || (prm->rhs_nodes && prm->rhs_vals)), "bad right-hand-side vector arrays");
+        std::vector<int32_t> en(ne);
+        std::vector<double> evl(ne);
+        if (ne) {
+            FDB_CUDA(cudaMemcpy(en.data(), prm->rhs_nodes, ne * sizeof(int32_t), cudaMemcpyDefault));
+            FDB_CUDA(cudaMemcpy(evl.data(), prm->rhs_vals, ne * sizeof(double), cudaMemcpyDefault));
+        }
+        if (!rhs_coef.empty()) FDB_CUDA(cudaMemcpy(rhs_coef.data(), prm->rhs_coef, rhs_coef.size() * sizeof(double), cudaMemcpyDefault));
+        std::vector<std::array<int64_t, 2>> ent;   // (node, entry index)
+        for (int64_t k = 0; k < nrv; ++k) {
+            FDB_REQUIRE(rp[k] <= rp[k + 1], "rhs_ptr is not monotone");
+            for (int32_t e = rp[k]; e < rp[k + 1]; ++e) {
+                FDB_REQUIRE(en[e] >= 0 && en[e] < N, "right-hand-side node out of range");
+                ent.push_back({(int64_t)en[e], (int64_t)e});
+            }
+        }
+        std::vector<int32_t> vec_of(ne);
+        for (int64_t k = 0; k < nrv; ++k)
+            for (int32_t e = rp[k]; e < rp[k + 1]; ++e) vec_of[e] = (int32_t)k;
+        std::stable_sort(ent.begin(), ent.end(), [](const std::array<int64_t, 2>& a, const std::array<int64_t, 2>& b) { return a[0] < b[0]; });
+        rn_ptr.push_back(0);
+        for (size_t i = 0; i < ent.size(); ++i) {
+            if (i == 0 || ent[i][0] != ent[i - 1][0]) {
+                if (i) rn_ptr.push_back((int32_t)rn_vec.size());
+                rn_nodes.push_back((int32_t)ent[i][0]);
+            }
+            rn_vec.push_back(vec_of[ent[i][1]]);
+            rn_val.push_back(evl[ent[i][1]]);
+        }
+        if (!ent.empty()) rn_ptr.push_back((int32_t)rn_vec.size());
+    }
+    const bool general_rhs = !rn_nodes.empty();
+
     // Real arithmetic when the systems are real (no boundary term) and the right-hand sides purely imaginary
     // (real q): p = 1j*u with G u = -w q.  Same COCG recurrences on half the bytes.
-    bool real = !overlay && prm->arithmetic != 1;
+    bool real = !overlay && prm->arithmetic != 1 && !general_rhs;
     for (auto& v : u_q) real = real && (v.y == 0.0);
     // no wider than the number of frequencies needs
     while (F / 2 >= 1 && F / 2 >= nf) F /= 2;
@@ -1101,6 +1187,14 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     }
     w->real = real;
     res->real_arithmetic = real ? 1 : 0;
+    w->n_rn = (int)rn_nodes.size();
+    if (general_rhs) {
+        w->rn_nodes.alloc(rn_nodes.size()); w->rn_ptr.alloc(rn_ptr.size()); w->rn_vec.alloc(rn_vec.size()); w->rn_val.alloc(rn_val.size());
+        FDB_CUDA(cudaMemcpy(w->rn_nodes.p, rn_nodes.data(), rn_nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FDB_CUDA(cudaMemcpy(w->rn_ptr.p, rn_ptr.data(), rn_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FDB_CUDA(cudaMemcpy(w->rn_vec.p, rn_vec.data(), rn_vec.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FDB_CUDA(cudaMemcpy(w->rn_val.p, rn_val.data(), rn_val.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     DevBuf<int32_t> d_src_nodes; DevBuf<double2> d_src_q;
     d_src_nodes.alloc(std::max(1, n_src)); d_src_q.alloc(std::max(1, n_src));
     if (n_src) {
@@ -1132,6 +1226,8 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     Scalars h;
     memset(&h, 0, sizeof(h));
     h.tol2 = prm->tol * prm->tol;
+    h.bb_from_r0 = general_rhs ? 1 : 0;
+    std::vector<double2> rcoef((size_t)nrv * F, make_double2(0.0, 0.0));   // [n_rhs_vec][F]
     std::vector<double2> coef((size_t)std::max(1, ng) * F, make_double2(0.0, 0.0));
     std::vector<double> mu_f((size_t)std::max(1, ng) * 2);
     std::vector<int64_t> slot_freq(F, -1);
@@ -1159,6 +1255,8 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             mu_f[2 * g + 1] = mu[((size_t)g * nf + fi) * 2 + 1];
         }
         fill_slot(h, coef, F, ng, slot, omega[fi], ng ? mu_f.data() : nullptr, src_norm2);
+        for (int64_t k = 0; k < nrv; ++k)
+            rcoef[(size_t)k * F + slot] = make_double2(rhs_coef[((size_t)k * nf + fi) * 2], rhs_coef[((size_t)k * nf + fi) * 2 + 1]);
         slot_freq[slot] = fi;
         h.reset[slot] = 1;
         h.active[slot] = 0;
@@ -1176,10 +1274,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     while (n_busy > 0) {
         if (any_reset) {
             // slots that held a solution before can start from it (warm start from the slot's previous frequency)
-            bool keep_x = prm->warm_start != 0;
+            bool keep_x = prm->warm_start != 0 && !general_rhs;   // ||b|| of a general right-hand side comes from r0 = b
             for (int f = 0; f < F; ++f)
                 if (h.reset[f] && !slot_used[f]) keep_x = false;
-            upload_scalars(sys, w, h, coef);
+            upload_scalars(sys, w, h, coef, &rcoef);
             int nk = 0;
             FDB_DISPATCH_F(F, reload(sys, w, overlay, keep_x, d_src_nodes.p, d_src_q.p, n_src, &nk));
             n_kernels += nk;
@@ -1188,7 +1286,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 if (h.reset[f]) slot_used[f] = 1;
             any_reset = false;
         } else {
-            upload_scalars(sys, w, h, coef);
+            upload_scalars(sys, w, h, coef, &rcoef);
         }
         FDB_CUDA(cudaGraphLaunch(w->graph, s));
         n_spmv += check_every;
@@ -1253,6 +1351,13 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 memset(&h2, 0, sizeof(h2));
                 h2.tol2 = h.tol2;
                 std::vector<double2> coef2((size_t)std::max(1, ng) * F2, make_double2(0.0, 0.0));
+                std::vector<double2> rcoef2((size_t)nrv * F2, make_double2(0.0, 0.0));
+                h2.bb_from_r0 = h.bb_from_r0;
+                w2->n_rn = w->n_rn;
+                std::swap(w2->rn_nodes.p, w->rn_nodes.p); std::swap(w2->rn_nodes.n, w->rn_nodes.n);
+                std::swap(w2->rn_ptr.p, w->rn_ptr.p); std::swap(w2->rn_ptr.n, w->rn_ptr.n);
+                std::swap(w2->rn_vec.p, w->rn_vec.p); std::swap(w2->rn_vec.n, w->rn_vec.n);
+                std::swap(w2->rn_val.p, w->rn_val.p); std::swap(w2->rn_val.n, w->rn_val.n);
                 std::vector<int64_t> freq2(F2, -1);
                 std::vector<char> used2(F2, 0);
                 int j = 0;
@@ -1264,6 +1369,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                     h2.rho[j] = h.rho[f]; h2.pq[j] = h.pq[f]; h2.beta[j] = h.beta[f]; h2.rr[j] = h.rr[f]; h2.bb[j] = h.bb[f];
                     h2.w2[j] = h.w2[f]; h2.rhs_scale[j] = h.rhs_scale[f]; h2.active[j] = h.active[f]; h2.iters[j] = h.iters[f];
                     for (int g = 0; g < ng; ++g) coef2[(size_t)g * F2 + j] = coef[(size_t)g * F + f];
+                    for (int64_t k = 0; k < nrv; ++k) rcoef2[(size_t)k * F2 + j] = rcoef[(size_t)k * F + f];
                     freq2[j] = slot_freq[f];
                     used2[j] = 1;
                     ++j;
@@ -1282,7 +1388,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 if (overlay) {
                     // the precomputed 1/diag depends on the slot's frequency: rebuild it for the moved slots
                     for (int f = 0; f < j; ++f) h2.reset[f] = 1;
-                    upload_scalars(sys, w2, h2, coef2);
+                    upload_scalars(sys, w2, h2, coef2, &rcoef2);
                     k_jacobi_launch(sys, w2, F2);
                     n_kernels += 1;
                     for (int f = 0; f < j; ++f) h2.reset[f] = 0;
@@ -1294,6 +1400,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 F = F2;
                 h = h2;
                 coef.swap(coef2);
+                rcoef.swap(rcoef2);
                 slot_freq.swap(freq2);
                 slot_used.swap(used2);
                 if (n_rcv) { w->rcv_out.alloc((size_t)F * n_rcv); rcv_host.resize((size_t)F * n_rcv); }

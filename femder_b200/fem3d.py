@@ -10,7 +10,9 @@ Differences from the reference, all deliberate:
 * every frequency is solved by Jacobi-preconditioned COCG to ``tol`` instead of a PARDISO factorisation.
 * a surface group without a boundary condition raises ``KeyError`` as in the reference (``FEM_3D.py:1310``);
   ``mu`` keys are paired with their own group instead of by position.
-* the velocity-BC and equivalent-fluid branches (``FEM_3D.py:1320-1347, 1367-1421``) raise NotImplementedError.
+* the velocity-BC branch (``FEM_3D.py:1320-1347``) is supported: ``b = -1j*w*sum_i v_i V_i 1`` (the reference's
+  cumulative ``V[indx] = v`` assignment reduces to this because ``V_i`` only has columns on group i's nodes); as in
+  the reference, point sources are ignored in that branch.  Equivalent fluids (``1367-1421``) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -172,8 +174,6 @@ class FEM3D:
         ``keep_pN=False`` is an addition for meshes whose ``(n_freq, N)`` pressure array is not wanted on the
         host (1M DOF x 481 frequencies = 7.7 GB): only the receiver pressures ``pR`` are returned."""
         then = time.time()
-        if len(self.v) > 0:
-            raise NotImplementedError("velocity boundary conditions (FEM_3D.py:1320-1347) are outside the B200 hot path")
         sys = self._system()
         N = self.NumNosC
         new_mesh = self._ensure_volume(sys)
@@ -200,6 +200,22 @@ class FEM3D:
             sys.assemble_surface()
             self.A = sys.get_A(drop_zeros=(self.order == 2))
 
+        # velocity boundary conditions (FEM_3D.py:1286-1287, 1320-1347): V_i are the surface matrices of the groups in
+        # BC.v; the right-hand side of frequency n is -1j*w[n] * sum_i v_i[n] * (V_i @ 1)
+        rhs_vecs = rhs_coef = None
+        if self.BC is not None and len(self.v) > 0:
+            from . import fem_numerical as fn
+            vkeys = np.sort([*self.v])
+            dev = sys.device
+            if self.order == 1:
+                self.V = fn.assemble_surface_matrices(self.elem_surf, self.nos, self.areas, self.domain_index_surf, vkeys, 1, device=dev)
+            else:
+                self.V = fn.assemble_A10_3_FAST(self.domain_index_surf, vkeys, self.NumElemC, self.NumNosC, self.elem_surf, self.nos,
+                                                self.c0, self.rho0, device=dev)
+            rhs_vecs = [np.asarray(Vm.sum(axis=1)).ravel() for Vm in self.V]
+            wv = np.asarray(self.w, dtype=np.float64)
+            rhs_coef = np.array([-1j * wv * np.asarray(self.v[k]).ravel()[:len(wv)] for k in vkeys])
+
         src_nodes, src_q = [], []
         if self.S is not None:
             for ii in range(len(self.S.coord)):
@@ -208,6 +224,8 @@ class FEM3D:
                 src_nodes.append(n)
                 src_q.append(complex(np.asarray(self.S.q[ii]).ravel()[0]))
         self.q = csc_matrix(q)
+        if rhs_vecs is not None:
+            src_nodes, src_q = [], []   # FEM_3D.py:1341: b = -1j*w*Vn only
 
         nf = len(self.freq)
         w = np.asarray(self.w, dtype=np.float64)
@@ -225,7 +243,8 @@ class FEM3D:
         owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch,
-                                  check_every=self.check_every, warm_start=self.warm_start)
+                                  check_every=self.check_every, warm_start=self.warm_start, rhs_vecs=rhs_vecs,
+                                  rhs_coef=None if rhs_coef is None else rhs_coef[:, owned])
         self.stats = stats
         if world > 1:
             pN = sharding.gather_rows(pN, owned, nf) if keep_pN else None

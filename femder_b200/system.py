@@ -242,19 +242,23 @@ class System:
 
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
-              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False):
+              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,
+              rhs_coef=None):
         """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
 
-        mu: (n_groups, n_freq) complex.  Returns (pN or None, pR or None, SweepStats)."""
+        mu: (n_groups, n_freq) complex.  ``rhs_vecs`` (list of real length-N vectors, dense or scipy sparse) with
+        ``rhs_coef`` (n_vec, n_freq) complex add ``sum_k rhs_coef[k, n] * vec_k`` to the right-hand side of frequency n
+        (velocity boundary conditions).  Returns (pN or None, pR or None, SweepStats)."""
         omega = _f64(np.atleast_1d(omega))
         nf = len(omega)
         mu = _c128(np.asarray(mu).reshape(self.n_groups, nf)) if self.n_groups else None
         src_nodes = _i32(np.atleast_1d(src_nodes))
         src_q = _c128(np.atleast_1d(src_q).ravel())
+        n_vec = 0 if rhs_vecs is None else len(rhs_vecs)
         if batch in (0, None, "auto"):
             # a rigid-wall sweep with real sources runs in real arithmetic (half the bytes per frequency), where 16
             # frequencies fill the 128-byte gather line that 8 complex ones do
-            real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex
+            real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex and n_vec == 0
             batch = 16 if real else 8
             if self.n_nodes <= SMALL_MESH_NODES:
                 batch *= 4   # small meshes: the kernels are latency-bound, wide batches amortise the fixed cost per launch
@@ -276,6 +280,23 @@ class System:
         prm.warm_start = int(bool(warm_start))
         prm.precond = 0
         prm.arithmetic = 1 if force_complex else 0
+        prm.n_rhs_vec = n_vec
+        if n_vec:
+            from scipy.sparse import issparse
+            ptr_, nodes_, vals_ = [0], [], []
+            for v in rhs_vecs:
+                if issparse(v):
+                    v = np.asarray(v.todense())
+                v = np.asarray(v, dtype=np.float64).ravel()
+                if len(v) != self.n_nodes:
+                    raise ValueError("right-hand-side vectors must have one entry per node")
+                nz = np.flatnonzero(v)
+                nodes_.append(nz.astype(np.int32)); vals_.append(v[nz]); ptr_.append(ptr_[-1] + len(nz))
+            rhs_ptr = np.asarray(ptr_, dtype=np.int32)
+            rhs_nodes = _i32(np.concatenate(nodes_)) if ptr_[-1] else np.zeros(0, dtype=np.int32)
+            rhs_vals = _f64(np.concatenate(vals_)) if ptr_[-1] else np.zeros(0)
+            rhs_coef = _c128(np.asarray(rhs_coef).reshape(n_vec, nf))
+            prm.rhs_ptr, prm.rhs_nodes, prm.rhs_vals, prm.rhs_coef = ptr(rhs_ptr), ptr(rhs_nodes), ptr(rhs_vals), ptr(rhs_coef)
         n_rcv = 0
         if rcv_nodes is not None:
             rcv_nodes = _i32(np.asarray(rcv_nodes).reshape(-1, 4))

@@ -95,6 +95,12 @@ typedef struct fdb_sweep_params {
     int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
     int32_t precond;          /* 0: Jacobi */
     int32_t arithmetic;       /* 0: automatic (real arithmetic for rigid-wall sweeps with real sources), 1: always complex */
+    /* extra right-hand-side terms (velocity boundary conditions, FEM_3D.py:1320-1347): b_n += sum_k rhs_coef[k][n] * vec_k */
+    int64_t n_rhs_vec;
+    const int32_t* rhs_ptr;   /* [n_rhs_vec+1] vec_k = entries rhs_ptr[k] .. rhs_ptr[k+1] */
+    const int32_t* rhs_nodes; /* node of each entry */
+    const double* rhs_vals;   /* real value of each entry */
+    const double* rhs_coef;   /* [n_rhs_vec][n_freq] complex coefficients (the caller folds -1j*w in) */
     int64_t n_rcv;            /* receivers: pR[n][i] = sum_j rcv_w[i][j] * p[n][rcv_nodes[i][j]] */
     const int32_t* rcv_nodes; /* [n_rcv][4] (unused slots: weight 0, any valid node) */
     const double* rcv_w;      /* [n_rcv][4] */

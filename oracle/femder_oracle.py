@@ -227,7 +227,19 @@ def system_matrix(H, Q, A_list, mu_list, w):
     return (H + 1j * w * Ag - (w ** 2) * Q).tocsc().astype(np.complex128)
 
 
-def solve_sweep(H, Q, A_list, mu_by_group, group_ids, freq, q):
+def velocity_vector(V_list, v_by_group, n, N):
+    """``Vn`` of the velocity-BC branch (FEM_3D.py:1326-1339), restated literally: ``V`` is assigned group by group
+    (later groups overwrite shared nodes) and ``Vn += V_i @ V`` after each assignment."""
+    V = np.zeros(N, dtype=np.complex128)
+    Vn = np.zeros(N, dtype=np.complex128)
+    for Vm, bl in zip(V_list, np.sort([*v_by_group])):
+        idx = np.unique(Vm.tocoo().col)          # nodes of the group's triangles
+        V[idx] = np.asarray(v_by_group[bl]).ravel()[n]
+        Vn += Vm @ V
+    return Vn
+
+
+def solve_sweep(H, Q, A_list, mu_by_group, group_ids, freq, q, V_list=None, v_by_group=None):
     """Direct solve per frequency: returns pN (n_f, N) complex128."""
     freq = np.asarray(freq, dtype=np.float64)
     w = 2.0 * np.pi * freq
@@ -235,12 +247,16 @@ def solve_sweep(H, Q, A_list, mu_by_group, group_ids, freq, q):
     for n in range(len(freq)):
         mus = [np.asarray(mu_by_group[g]).ravel()[n] for g in group_ids]
         G = system_matrix(H, Q, A_list, mus, w[n])
-        pN[n] = splu(G).solve(-1j * w[n] * q)
+        if V_list is not None:
+            b = -1j * w[n] * velocity_vector(V_list, v_by_group, n, H.shape[0])   # FEM_3D.py:1341
+        else:
+            b = -1j * w[n] * q
+        pN[n] = splu(G).solve(b)
     return pN
 
 
-def compute(grid, freq, mu_by_group, src_coord, src_q, c0=343.0, rho0=1.21, compat_complex64=False):
-    """Branch A of ``FEM3D.compute()``; returns dict(H, Q, A, q, pN, group_ids)."""
+def compute(grid, freq, mu_by_group, src_coord, src_q, c0=343.0, rho0=1.21, compat_complex64=False, v_by_group=None):
+    """Branch A of ``FEM3D.compute()`` (and its velocity-BC variant); returns dict(H, Q, A, q, pN, group_ids)."""
     group_ids = np.sort([*mu_by_group])
     if grid.order == 1:
         H, Q = assemble_tet4(grid.elem_vol, grid.nos, c0, rho0, compat_complex64)
@@ -248,8 +264,11 @@ def compute(grid, freq, mu_by_group, src_coord, src_q, c0=343.0, rho0=1.21, comp
         H, Q = assemble_tet10(grid.elem_vol, grid.nos, c0, rho0)
     A = assemble_surface(grid.elem_surf, grid.nos, grid.domain_index_surf, group_ids, grid.order)
     q = source_vector(grid.nos, src_coord, src_q)
-    pN = solve_sweep(H, Q, A, mu_by_group, group_ids, freq, q)
-    return dict(H=H, Q=Q, A=A, q=q, pN=pN, group_ids=group_ids)
+    V = None
+    if v_by_group:
+        V = assemble_surface(grid.elem_surf, grid.nos, grid.domain_index_surf, np.sort([*v_by_group]), grid.order)
+    pN = solve_sweep(H, Q, A, mu_by_group, group_ids, freq, q, V, v_by_group)
+    return dict(H=H, Q=Q, A=A, q=q, pN=pN, group_ids=group_ids, V=V)
 
 
 def tet4_interpolate(nos, elem_vol, coord, pN):

@@ -153,7 +153,7 @@ class PlainReceiver:
         self.coord = np.atleast_2d(np.asarray(coord, dtype=np.float64))
 
 
-def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, c0=343.0, rho0=1.21):
+def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, c0=343.0, rho0=1.21, v_by_group=None):
     """Run the reference's own ``FEM3D.compute()`` + ``evaluate()`` on ``grid``.  Returns the FEM3D object."""
     ref = load_reference()
     AP = ref.controlsair.AirProperties(c0=c0, rho0=rho0)
@@ -161,6 +161,8 @@ def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, 
     BC = ref.BoundaryConditions.BC(AC, AP)
     for g, mu in mu_by_group.items():
         BC.mu[g] = np.asarray(mu)
+    for g, v in (v_by_group or {}).items():
+        BC.v[g] = np.asarray(v)
     S = PlainSource(src_coord, src_q)
     R = PlainReceiver(rcv_coord)
     obj = ref.FEM_3D.FEM3D(grid, S, R, AP, AC, BC)

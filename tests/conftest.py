@@ -50,6 +50,7 @@ class Golden:
         self.src = d["src"]
         self.src_q = d["src_q"]
         self.rcv = d["rcv"]
+        self.v = {int(k): d["v"][i] for i, k in enumerate(d["v_ids"])} if "v_ids" in d else None   # velocity BCs
         self.rcv_off = d["rcv_off"] if "rcv_off" in d else None
         self.pR_off = d["pR_off"] if "pR_off" in d else None
 

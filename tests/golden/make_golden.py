@@ -32,9 +32,9 @@ def csc_fields(prefix, M, out):
     out[prefix + "_indptr"] = M.indptr
 
 
-def run_case(name, grid, freq, mu, src, rcv, rcv_off=None):
+def run_case(name, grid, freq, mu, src, rcv, rcv_off=None, v=None):
     freq = np.asarray(freq, dtype=np.float64)
-    obj = run_reference_compute(grid, freq, mu, src, [1e-4] * len(np.atleast_2d(src)), rcv, C0, RHO0)
+    obj = run_reference_compute(grid, freq, mu, src, [1e-4] * len(np.atleast_2d(src)), rcv, C0, RHO0, v_by_group=v)
     extra = {}
     if rcv_off is not None:
         # the reference's evaluate() cannot mix on-node and off-node receivers in one call
@@ -55,6 +55,9 @@ def run_case(name, grid, freq, mu, src, rcv, rcv_off=None):
                mu=np.array([np.asarray(mu[g], dtype=np.complex128) for g in np.sort([*mu])]),
                areas=np.asarray(obj.areas), q=np.asarray(obj.q.todense()).ravel(),
                pN=obj.pN, pR=obj.pR, **extra)
+    if v is not None:
+        out["v_ids"] = np.sort([*v]).astype(np.int64)
+        out["v"] = np.array([np.asarray(v[g], dtype=np.complex128) for g in np.sort([*v])])
     csc_fields("H", obj.H, out)
     csc_fields("Q", obj.Q, out)
     for i, A in enumerate(obj.A):
@@ -97,6 +100,13 @@ def main():
     mu[7] = ones * 0.02 / (C0 * RHO0)
     run_case("tet10_shoebox", g, freq, mu, [g.nos[g.closest_node([1.0, 1.0, 1.2])]],
              [g.nos[g.closest_node([2.0, 3.0, 1.25])]])
+
+    # 4b. velocity boundary conditions (FEM_3D.py:1320-1347): two driven walls sharing an edge, one absorbing wall
+    g = shoebox_tet4(5, 6, 4, jitter=0.2)
+    mu = {t: np.zeros(nf) for t in range(2, 8)}
+    mu[7] = ones * 0.05 / (C0 * RHO0)
+    v = {2: np.array([1e-3, 2e-3 + 1e-3j, 5e-4, -1e-3j]), 4: np.array([5e-4, -1e-3, 2e-3j, 1e-3])}
+    run_case("tet4_velocity", g, freq, mu, [[1.0, 1.0, 1.2]], [g.nos[g.closest_node([2.0, 3.0, 1.25])]], v=v)
 
     # 5. real gmsh Tet10 mesh from the reference repository (Mshs/FEM_3D/bixa1_mesh.msh is not usable:
     #    its element 25 is a blank line)

@@ -14,6 +14,8 @@ def _run(g, **kw):
     BC = fd.BC(AC, AP)
     for k, v in g.mu.items():
         BC.mu[k] = v
+    for k, v in (g.v or {}).items():
+        BC.v[k] = v
     S = fd.Source(coord=g.src, q=g.src_q)
     R = fd.Receiver(coord=g.rcv)
     obj = fd.FEM3D(g.grid, S, R, AP, AC, BC, tol=1e-10, batch=4, **kw)
@@ -32,9 +34,11 @@ def test_compute_leaves_reference_state(gpu_lib, golden):
     assert obj.areas.dtype == np.complex128 and np.abs(obj.areas - g.areas).max() < 1e-15
     assert obj.pN.shape == g.pN.shape and obj.pN.dtype == np.complex128 and obj.t > 0
     # end to end against the oracle with FP64 assembly (north star: 1e-6 relative L2, 0.01 dB)
-    r = O.compute(g.grid, g.freq, g.mu, g.src, g.src_q, g.c0, g.rho0)
+    r = O.compute(g.grid, g.freq, g.mu, g.src, g.src_q, g.c0, g.rho0, v_by_group=g.v)
     rel = np.linalg.norm(obj.pN - r["pN"], axis=1) / np.linalg.norm(r["pN"], axis=1)
     assert rel.max() < 1e-6
+    if g.v:
+        assert len(obj.V) == len(g.v) and all(M.format == "csc" for M in obj.V)
     pR = obj.evaluate(R)
     assert pR.shape == (len(g.freq), len(g.rcv))
     assert np.abs(obj.spl - O.p2SPL(O.evaluate(g.grid.nos, g.grid.elem_vol, r["pN"], g.rcv))).max() < 0.01
@@ -79,9 +83,9 @@ def test_missing_bc_raises_keyerror(gpu_lib):
     obj = fd.FEM3D(g.grid, fd.Source(coord=g.src, q=g.src_q), None, AP, AC, BC)
     with pytest.raises(KeyError):
         obj.compute(timeit=False)
-    BC.v[3] = np.ones(len(g.freq))
+    BC.rhoc[1] = np.ones(len(g.freq))   # equivalent-fluid domains are outside the hot path
     with pytest.raises(NotImplementedError):
-        fd.FEM3D(g.grid, None, None, AP, AC, BC).compute(timeit=False)
+        fd.FEM3D(g.grid, None, None, AP, AC, BC)
 
 
 def test_h_is_cached_between_computes(gpu_lib):

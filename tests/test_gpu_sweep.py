@@ -45,7 +45,13 @@ def test_sweep_on_reference_matrices(gpu_lib, golden):
     w = 2 * np.pi * g.freq
     mu = np.array([g.mu[int(k)] for k in g.group_ids])
     src = [O.closest_node(g.grid.nos, c) for c in g.src]
-    pN, _, st = s.sweep(w, mu, src, g.src_q, tol=1e-10, batch=4, max_iter=20000)
+    if g.v:   # velocity-BC branch: b = -1j*w*sum_i v_i (V_i @ 1), point sources ignored (FEM_3D.py:1341)
+        V = O.assemble_surface(g.grid.elem_surf, g.grid.nos, g.grid.domain_index_surf, np.sort([*g.v]), g.order)
+        vecs = [np.asarray(Vm.sum(axis=1)).ravel() for Vm in V]
+        coef = np.array([-1j * w * g.v[k] for k in np.sort([*g.v])])
+        pN, _, st = s.sweep(w, mu, [], [], tol=1e-10, batch=4, max_iter=20000, rhs_vecs=vecs, rhs_coef=coef)
+    else:
+        pN, _, st = s.sweep(w, mu, src, g.src_q, tol=1e-10, batch=4, max_iter=20000)
     assert st.n_unconverged == 0, st
     assert _rel_rows(pN, g.pN).max() < 1e-6
     pR = O.evaluate(g.grid.nos, g.grid.elem_vol, pN, g.rcv)

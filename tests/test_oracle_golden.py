@@ -11,7 +11,8 @@ def _rel(a, b):
 def test_golden_fixtures_exist():
     from conftest import golden_names
     names = golden_names()
-    assert {"tet4_shoebox_jitter", "tet4_shoebox_rigid", "tet4_cplx_room", "tet10_shoebox", "tet10_testmesh"} <= set(names)
+    assert {"tet4_shoebox_jitter", "tet4_shoebox_rigid", "tet4_cplx_room", "tet10_shoebox", "tet10_testmesh",
+            "tet4_velocity"} <= set(names)
 
 
 def test_oracle_assembly_matches_reference(golden):
@@ -62,7 +63,10 @@ def test_oracle_solution_matches_reference(golden):
     # identical matrices in (the reference's own), same direct solver family out
     q = O.source_vector(g.grid.nos, g.src, g.src_q)
     assert np.array_equal(q, g.q)
-    pN = O.solve_sweep(g.H.astype(np.complex128), g.Q.astype(np.complex128), g.A, g.mu, g.group_ids, g.freq, q)
+    V = None
+    if g.v:   # velocity-BC branch (FEM_3D.py:1320-1347)
+        V = O.assemble_surface(g.grid.elem_surf, g.grid.nos, g.grid.domain_index_surf, np.sort([*g.v]), g.order)
+    pN = O.solve_sweep(g.H.astype(np.complex128), g.Q.astype(np.complex128), g.A, g.mu, g.group_ids, g.freq, q, V, g.v)
     rel = np.linalg.norm(pN - g.pN, axis=1) / np.linalg.norm(g.pN, axis=1)
     assert rel.max() < 1e-9
     pR = O.evaluate(g.grid.nos, g.grid.elem_vol, pN, g.rcv)
@@ -76,7 +80,7 @@ def test_oracle_fp64_end_to_end_close_to_reference(golden):
     """FP64 assembly vs the reference's complex64 Tet4 matrices: solutions differ at the 1e-5..1e-3 level
     (SURVEY F3); Tet10 (float64 in the reference) agrees to round-off."""
     g = golden
-    r = O.compute(g.grid, g.freq, g.mu, g.src, g.src_q, g.c0, g.rho0)
+    r = O.compute(g.grid, g.freq, g.mu, g.src, g.src_q, g.c0, g.rho0, v_by_group=g.v)
     rel = np.linalg.norm(r["pN"] - g.pN, axis=1) / np.linalg.norm(g.pN, axis=1)
     assert rel.max() < (1e-9 if g.order == 2 else 5e-3)
 
