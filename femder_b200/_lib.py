@@ -21,7 +21,8 @@ c_u8p = C.POINTER(C.c_uint8)
 
 class SweepParams(C.Structure):
     _fields_ = [("n_freq", C.c_int64), ("omega", C.c_void_p), ("mu", C.c_void_p), ("n_src", C.c_int64),
-                ("src_nodes", C.c_void_p), ("src_q", C.c_void_p), ("tol", C.c_double), ("max_iter", C.c_int32),
+                ("src_nodes", C.c_void_p), ("src_q", C.c_void_p), ("n_src_sets", C.c_int64), ("src_set_ptr", C.c_void_p),
+                ("tol", C.c_double), ("max_iter", C.c_int32),
                 ("batch", C.c_int32), ("check_every", C.c_int32), ("warm_start", C.c_int32), ("precond", C.c_int32),
                 ("arithmetic", C.c_int32), ("n_rhs_vec", C.c_int64), ("rhs_ptr", C.c_void_p), ("rhs_nodes", C.c_void_p),
                 ("rhs_vals", C.c_void_p), ("rhs_coef", C.c_void_p), ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p)]

@@ -35,6 +35,7 @@ struct __align__(16) Scalars {
     int active[kMaxF];
     int iters[kMaxF];
     int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
+    int src_set[kMaxF];    // which source set (right-hand side) the slot solves: multi-RHS sweeps share G(w)
     int bb_from_r0;        // ||b||^2 is taken from the start residual (general right-hand sides, zero starting guess)
     double tol2;
     unsigned int ticket[4];
@@ -48,6 +49,7 @@ struct SweepWork {
     DevBuf<double2> x, r, p, q, dinv, tmp;  // [N][F]
     DevBuf<double2> coef;              // [n_groups][F]  1j*omega*mu
     DevBuf<double2> rcoef;             // [n_rhs_vec][F] coefficients of the extra right-hand-side vectors
+    DevBuf<int32_t> src_set_ptr;       // [n_sets+1] partition of the (deduplicated) source arrays into right-hand sides
     int n_rn = 0;                      // nodes touched by extra right-hand-side vectors (complex sweeps only)
     DevBuf<int32_t> rn_nodes, rn_ptr, rn_vec;   // per listed node: its (vector, value) terms
     DevBuf<double> rn_val;
@@ -630,12 +632,15 @@ __global__ void __launch_bounds__(kBlock) k_slot_clear(T* __restrict__ x, T* __r
 __device__ __forceinline__ void store_rhs(double2* dst, double2 scale, double2 q) { *dst = cmul(scale, q); }
 __device__ __forceinline__ void store_rhs(double* dst, double2 scale, double2 q) { *dst = scale.y * q.x; }
 template <typename T, int F>
-__global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, int n_src, bool all,
-                          const Scalars* __restrict__ sc, T* __restrict__ dst) {
+__global__ void k_set_rhs(const int32_t* __restrict__ src_nodes, const double2* __restrict__ src_q, const int32_t* __restrict__ set_ptr,
+                          int max_set, bool all, const Scalars* __restrict__ sc, T* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_src * F) return;
-    const int s = i / F, f = i % F;
-    if (all || sc->reset[f]) store_rhs(&dst[(int64_t)src_nodes[s] * F + f], sc->rhs_scale[f], src_q[s]);
+    if (i >= max_set * F) return;
+    const int j = i / F, f = i % F;
+    if (!(all || sc->reset[f])) return;
+    const int set = sc->src_set[f];
+    const int e = set_ptr[set] + j;
+    if (e < set_ptr[set + 1]) store_rhs(&dst[(int64_t)src_nodes[e] * F + f], sc->rhs_scale[f], src_q[e]);
 }
 
 // dst[node][f] += sum over the node's terms of rcoef[vec][f] * val   (one thread per (listed node, f): race-free, fixed order)
@@ -911,7 +916,7 @@ struct Launch {
         k_slot_clear<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, keep_x, ne, w->sc.p);
         ++nk;
         if (n_src) {
-            k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, false, w->sc.p, r);
+            k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, w->src_set_ptr.p, n_src, false, w->sc.p, r);
             ++nk;
         }
         if constexpr (std::is_same<T, double2>::value) {
@@ -945,7 +950,7 @@ struct Launch {
         T *x = (T*)w->x.p, *qq = (T*)w->q.p, *tmp = (T*)w->tmp.p;
         spmv(sys, w, x, qq, false, overlay);
         FDB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ne * sizeof(T), sys->stream));
-        if (n_src) k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, n_src, true, w->sc.p, tmp);
+        if (n_src) k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, w->src_set_ptr.p, n_src, true, w->sc.p, tmp);
         if constexpr (std::is_same<T, double2>::value) {
             if (w->n_rn)
                 k_add_rhs<F><<<grid_for((int64_t)w->n_rn * F, 128), 128, 0, sys->stream>>>(w->rn_nodes.p, w->rn_ptr.p, w->rn_vec.p, w->rn_val.p,
@@ -1116,19 +1121,37 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         FDB_CUDA(cudaMemcpy(src_nodes.data(), prm->src_nodes, prm->n_src * sizeof(int32_t), cudaMemcpyDefault));
         FDB_CUDA(cudaMemcpy(src_q.data(), prm->src_q, prm->n_src * sizeof(double2), cudaMemcpyDefault));
     }
-    // q[node] = S.q (assignment: a later source on the same node overwrites, FEM_3D.py:1298-1300)
-    std::vector<int32_t> u_nodes;
-    std::vector<double2> u_q;
-    for (int64_t i = 0; i < prm->n_src; ++i) {
-        FDB_REQUIRE(src_nodes[i] >= 0 && src_nodes[i] < N, "source node out of range");
-        bool found = false;
-        for (size_t j = 0; j < u_nodes.size(); ++j)
-            if (u_nodes[j] == src_nodes[i]) { u_q[j] = src_q[i]; found = true; }
-        if (!found) { u_nodes.push_back(src_nodes[i]); u_q.push_back(src_q[i]); }
+    // Source sets = right-hand sides sharing G(w) (one set unless the caller batches source candidates).  Inside a
+    // set q[node] = S.q is an assignment: a later source on the same node overwrites (FEM_3D.py:1298-1300).
+    const int64_t n_sets = std::max<int64_t>(1, prm->n_src_sets);
+    std::vector<int32_t> set_in(n_sets + 1, 0);
+    if (prm->n_src_sets > 0) {
+        FDB_REQUIRE(prm->src_set_ptr != nullptr, "src_set_ptr missing");
+        FDB_CUDA(cudaMemcpy(set_in.data(), prm->src_set_ptr, (n_sets + 1) * sizeof(int32_t), cudaMemcpyDefault));
+        FDB_REQUIRE(set_in[0] == 0 && set_in[n_sets] == prm->n_src, "src_set_ptr does not span the sources");
+    } else {
+        set_in[1] = (int32_t)prm->n_src;
     }
-    double src_norm2 = 0;
-    for (auto& v : u_q) src_norm2 += v.x * v.x + v.y * v.y;
-    const int n_src = (int)u_nodes.size();
+    std::vector<int32_t> u_nodes, set_ptr(n_sets + 1, 0);
+    std::vector<double2> u_q;
+    std::vector<double> set_norm2(n_sets, 0.0);
+    int max_set = 0;
+    for (int64_t st = 0; st < n_sets; ++st) {
+        FDB_REQUIRE(set_in[st] <= set_in[st + 1], "src_set_ptr is not monotone");
+        const size_t base = u_nodes.size();
+        for (int32_t i = set_in[st]; i < set_in[st + 1]; ++i) {
+            FDB_REQUIRE(src_nodes[i] >= 0 && src_nodes[i] < N, "source node out of range");
+            bool found = false;
+            for (size_t j = base; j < u_nodes.size(); ++j)
+                if (u_nodes[j] == src_nodes[i]) { u_q[j] = src_q[i]; found = true; }
+            if (!found) { u_nodes.push_back(src_nodes[i]); u_q.push_back(src_q[i]); }
+        }
+        set_ptr[st + 1] = (int32_t)u_nodes.size();
+        max_set = std::max(max_set, (int)(u_nodes.size() - base));
+        for (size_t j = base; j < u_nodes.size(); ++j) set_norm2[st] += u_q[j].x * u_q[j].x + u_q[j].y * u_q[j].y;
+    }
+    const int n_src = max_set;            // launch width of the right-hand-side kernels
+    const int64_t n_sys = n_sets * nf;    // systems = (source set, frequency) pairs, index set*nf + frequency
     // extra right-hand-side vectors (velocity boundary conditions): regrouped per node so one thread owns a node
     const int64_t nrv = prm->n_rhs_vec;
     FDB_REQUIRE(nrv >= 0, "negative count");
@@ -1177,7 +1200,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     bool real = !overlay && prm->arithmetic != 1 && !general_rhs;
     for (auto& v : u_q) real = real && (v.y == 0.0);
     // no wider than the number of frequencies needs
-    while (F / 2 >= 1 && F / 2 >= nf) F /= 2;
+    while (F / 2 >= 1 && F / 2 >= n_sys) F /= 2;
     SweepWork* w = get_work(sys, F);
     w->real = false;
     if (real) {
@@ -1196,10 +1219,12 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         FDB_CUDA(cudaMemcpy(w->rn_val.p, rn_val.data(), rn_val.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     DevBuf<int32_t> d_src_nodes; DevBuf<double2> d_src_q;
-    d_src_nodes.alloc(std::max(1, n_src)); d_src_q.alloc(std::max(1, n_src));
-    if (n_src) {
-        FDB_CUDA(cudaMemcpyAsync(d_src_nodes.p, u_nodes.data(), n_src * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        FDB_CUDA(cudaMemcpyAsync(d_src_q.p, u_q.data(), n_src * sizeof(double2), cudaMemcpyHostToDevice, s));
+    d_src_nodes.alloc(std::max<size_t>(1, u_nodes.size())); d_src_q.alloc(std::max<size_t>(1, u_nodes.size()));
+    w->src_set_ptr.alloc(set_ptr.size());
+    FDB_CUDA(cudaMemcpyAsync(w->src_set_ptr.p, set_ptr.data(), set_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (!u_nodes.empty()) {
+        FDB_CUDA(cudaMemcpyAsync(d_src_nodes.p, u_nodes.data(), u_nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        FDB_CUDA(cudaMemcpyAsync(d_src_q.p, u_q.data(), u_q.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
     }
     const int n_rcv = (int)prm->n_rcv;
     DevBuf<int32_t> d_rcv_nodes; DevBuf<double> d_rcv_w;
@@ -1238,26 +1263,28 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
 
     // Frequencies are dispatched to the slots in descending order: the iteration count grows with frequency, and
     // starting the expensive systems first leaves the cheap ones for the tail where slots begin to idle.
-    std::vector<int64_t> order(nf);
-    for (int64_t i = 0; i < nf; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return omega[a] > omega[b]; });
+    std::vector<int64_t> order(n_sys);
+    for (int64_t i = 0; i < n_sys; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return omega[a % nf] > omega[b % nf]; });
 
     auto assign = [&](int slot) {
-        if (next >= nf) {
+        if (next >= n_sys) {
             slot_freq[slot] = -1;
             h.active[slot] = 0;
             h.reset[slot] = 0;
             return false;
         }
-        const int64_t fi = order[next++];
+        const int64_t si = order[next++];
+        const int64_t fi = si % nf, st = si / nf;
         for (int g = 0; g < ng; ++g) {
             mu_f[2 * g] = mu[((size_t)g * nf + fi) * 2];
             mu_f[2 * g + 1] = mu[((size_t)g * nf + fi) * 2 + 1];
         }
-        fill_slot(h, coef, F, ng, slot, omega[fi], ng ? mu_f.data() : nullptr, src_norm2);
+        fill_slot(h, coef, F, ng, slot, omega[fi], ng ? mu_f.data() : nullptr, set_norm2[st]);
+        h.src_set[slot] = (int)st;
         for (int64_t k = 0; k < nrv; ++k)
             rcoef[(size_t)k * F + slot] = make_double2(rhs_coef[((size_t)k * nf + fi) * 2], rhs_coef[((size_t)k * nf + fi) * 2 + 1]);
-        slot_freq[slot] = fi;
+        slot_freq[slot] = si;
         h.reset[slot] = 1;
         h.active[slot] = 0;
         h.iters[slot] = 0;
@@ -1269,7 +1296,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     for (int f = 0; f < F; ++f) fill_slot(h, coef, F, ng, f, 1.0, nullptr, 0.0);
     bool any_reset = false;
     for (int f = 0; f < F; ++f) any_reset = assign(f) || any_reset;
-    if (nf > 0) ensure_graph(sys, w, F, check_every, overlay);
+    if (n_sys > 0) ensure_graph(sys, w, F, check_every, overlay);
 
     while (n_busy > 0) {
         if (any_reset) {
@@ -1340,7 +1367,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         // Tail of the sweep: the queue is empty and slots fall idle, but the fused SpMV costs the same whatever the
         // number of live slots.  Move the live slots into a narrower batch as soon as they fit one.
         static const bool no_narrow = getenv("FDB_NO_NARROW") != nullptr;   // debugging aid
-        if (next >= nf && n_busy > 0 && !any_reset && !no_narrow) {
+        if (next >= n_sys && n_busy > 0 && !any_reset && !no_narrow) {
             int F2 = F;
             while (F2 / 2 >= 1 && F2 / 2 >= n_busy) F2 /= 2;
             if (F2 < F) {
@@ -1354,6 +1381,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 std::vector<double2> rcoef2((size_t)nrv * F2, make_double2(0.0, 0.0));
                 h2.bb_from_r0 = h.bb_from_r0;
                 w2->n_rn = w->n_rn;
+                std::swap(w2->src_set_ptr.p, w->src_set_ptr.p); std::swap(w2->src_set_ptr.n, w->src_set_ptr.n);
                 std::swap(w2->rn_nodes.p, w->rn_nodes.p); std::swap(w2->rn_nodes.n, w->rn_nodes.n);
                 std::swap(w2->rn_ptr.p, w->rn_ptr.p); std::swap(w2->rn_ptr.n, w->rn_ptr.n);
                 std::swap(w2->rn_vec.p, w->rn_vec.p); std::swap(w2->rn_vec.n, w->rn_vec.n);
@@ -1368,6 +1396,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                     map.src[j] = f;
                     h2.rho[j] = h.rho[f]; h2.pq[j] = h.pq[f]; h2.beta[j] = h.beta[f]; h2.rr[j] = h.rr[f]; h2.bb[j] = h.bb[f];
                     h2.w2[j] = h.w2[f]; h2.rhs_scale[j] = h.rhs_scale[f]; h2.active[j] = h.active[f]; h2.iters[j] = h.iters[f];
+                    h2.src_set[j] = h.src_set[f];
                     for (int g = 0; g < ng; ++g) coef2[(size_t)g * F2 + j] = coef[(size_t)g * F + f];
                     for (int64_t k = 0; k < nrv; ++k) rcoef2[(size_t)k * F2 + j] = rcoef[(size_t)k * F + f];
                     freq2[j] = slot_freq[f];

@@ -243,15 +243,25 @@ class System:
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
               max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,
-              rhs_coef=None):
+              rhs_coef=None, src_sets=None):
         """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
 
         mu: (n_groups, n_freq) complex.  ``rhs_vecs`` (list of real length-N vectors, dense or scipy sparse) with
         ``rhs_coef`` (n_vec, n_freq) complex add ``sum_k rhs_coef[k, n] * vec_k`` to the right-hand side of frequency n
-        (velocity boundary conditions).  Returns (pN or None, pR or None, SweepStats)."""
+        (velocity boundary conditions).  ``src_sets`` = list of ``(nodes, q)`` pairs solves several right-hand sides
+        per frequency in the same batches (source candidate loops); outputs then carry a leading set axis.
+        Returns (pN or None, pR or None, SweepStats)."""
         omega = _f64(np.atleast_1d(omega))
         nf = len(omega)
         mu = _c128(np.asarray(mu).reshape(self.n_groups, nf)) if self.n_groups else None
+        n_sets = 1
+        set_ptr = None
+        if src_sets is not None:
+            n_sets = len(src_sets)
+            set_ptr = np.zeros(n_sets + 1, dtype=np.int32)
+            set_ptr[1:] = np.cumsum([len(np.atleast_1d(n)) for n, _ in src_sets])
+            src_nodes = np.concatenate([np.atleast_1d(n) for n, _ in src_sets]) if n_sets else []
+            src_q = np.concatenate([np.atleast_1d(q).ravel() for _, q in src_sets]) if n_sets else []
         src_nodes = _i32(np.atleast_1d(src_nodes))
         src_q = _c128(np.atleast_1d(src_q).ravel())
         n_vec = 0 if rhs_vecs is None else len(rhs_vecs)
@@ -273,6 +283,8 @@ class System:
         prm.n_src = len(src_nodes)
         prm.src_nodes = ptr(src_nodes)
         prm.src_q = ptr(src_q)
+        prm.n_src_sets = n_sets if src_sets is not None else 0
+        prm.src_set_ptr = ptr(set_ptr) if src_sets is not None else None
         prm.tol = float(tol)
         prm.max_iter = int(max_iter)
         prm.batch = int(batch)
@@ -310,15 +322,21 @@ class System:
         if pN_out is not None:
             pN = pN_out
         elif want_pN:
-            pN = np.empty((nf, self.n_nodes), dtype=np.complex128)
-        pR = np.empty((nf, n_rcv), dtype=np.complex128) if n_rcv else None
-        iters = np.zeros(nf, dtype=np.int32)
-        relres = np.zeros(nf, dtype=np.float64)
+            pN = np.empty((n_sets * nf, self.n_nodes), dtype=np.complex128)
+        pR = np.empty((n_sets * nf, n_rcv), dtype=np.complex128) if n_rcv else None
+        iters = np.zeros(n_sets * nf, dtype=np.int32)
+        relres = np.zeros(n_sets * nf, dtype=np.float64)
         res.pN = ptr(pN)
         res.pR = ptr(pR)
         res.iters = ptr(iters)
         res.relres = ptr(relres)
         check(self._lib.fdb_sweep(self._h, C.byref(prm), C.byref(res)))
+        if src_sets is not None:
+            if pN is not None and pN_out is None:
+                pN = pN.reshape(n_sets, nf, self.n_nodes)
+            if pR is not None:
+                pR = pR.reshape(n_sets, nf, n_rcv)
+            iters, relres = iters.reshape(n_sets, nf), relres.reshape(n_sets, nf)
         st = SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged)
         st.real_arithmetic = bool(res.real_arithmetic)
         return pN, pR, st

@@ -88,6 +88,10 @@ typedef struct fdb_sweep_params {
     int64_t n_src;
     const int32_t* src_nodes; /* [n_src]  node of each source (later duplicates overwrite, as the reference) */
     const double* src_q;      /* [n_src]  complex volume velocities q */
+    /* multi-RHS: the sources are split into n_src_sets right-hand sides sharing G(w) (source/receiver candidate loops,
+     * FEM_3D.py:1633-1648).  0 = one set.  Outputs are then [n_src_sets][n_freq][...]. */
+    int64_t n_src_sets;
+    const int32_t* src_set_ptr; /* [n_src_sets+1] set k = sources src_set_ptr[k] .. src_set_ptr[k+1] */
     double tol;               /* relative residual ||b - G x|| / ||b|| to reach */
     int32_t max_iter;
     int32_t batch;            /* solver slots = frequencies per fused SpMV: 1, 2, 4, 8, 16, 32 or 64 */
@@ -109,10 +113,10 @@ typedef struct fdb_sweep_params {
  * GPU and passes only the frequencies it owns; there is no collective on this path. */
 
 typedef struct fdb_sweep_result {
-    double* pR;       /* [n_freq][n_rcv] complex; may be NULL */
-    double* pN;       /* [n_freq][n_nodes] complex; may be NULL */
-    int32_t* iters;   /* [n_freq] iterations used; may be NULL */
-    double* relres;   /* [n_freq] final recursive relative residual ; may be NULL */
+    double* pR;       /* [n_sets][n_freq][n_rcv] complex; may be NULL */
+    double* pN;       /* [n_sets][n_freq][n_nodes] complex; may be NULL */
+    int32_t* iters;   /* [n_sets][n_freq] iterations used; may be NULL */
+    double* relres;   /* [n_sets][n_freq] true relative residual ||b - G x|| / ||b|| of what is returned; may be NULL */
     double seconds;   /* device time of the sweep (CUDA events on the system's stream) */
     int64_t n_spmv;   /* fused SpMV launches */
     int64_t n_kernels;/* all kernel launches of the sweep */

@@ -245,3 +245,23 @@ def test_config2_tet10_admittance_wall(gpu_lib):
     assert np.abs(obj.A[-1].data - ref["A"][-1].data).max() / np.abs(ref["A"][-1].data).max() < 1e-12
     assert _rel_rows(obj.pN, ref["pN"]).max() < 1e-6
     assert np.abs(obj.spl - O.p2SPL(O.evaluate(grid.nos, grid.elem_vol, ref["pN"], R.coord))).max() < 0.01
+
+
+def test_multi_rhs_source_sets(gpu_lib):
+    """Several source candidates per frequency in the same batches (FEM_3D.py:1633-1648): each
+    (set, frequency) system equals the single-set solve."""
+    from conftest import Golden
+    g = Golden("tet4_cplx_room")
+    s = _solver_system(g.H, g.Q, g.A)
+    freq = np.linspace(30.0, 200.0, 7)
+    w = 2 * np.pi * freq
+    mu = np.array([np.resize(g.mu[int(k)], len(freq)) for k in g.group_ids])
+    sets = [([5], [1e-4]), ([40, 7], [2e-4j, 1e-4]), ([100, 100], [9.0, 3e-4])]   # the last one: overwrite semantics
+    rn = np.array([[3, 3, 3, 3], [50, 60, 70, 80]]); rw = np.array([[1.0, 0, 0, 0], [0.1, 0.2, 0.3, 0.4]])
+    pN, pR, st = s.sweep(w, mu, None, None, rn, rw, tol=1e-11, batch=8, src_sets=sets)
+    assert pN.shape == (3, len(freq), g.N) and pR.shape == (3, len(freq), 2) and st.iters.shape == (3, len(freq))
+    assert st.n_unconverged == 0
+    for k, (nodes, q) in enumerate(sets):
+        one, oneR, _ = s.sweep(w, mu, nodes, q, rn, rw, tol=1e-11, batch=8)
+        assert _rel_rows(pN[k], one).max() < 1e-8
+        assert np.abs(pR[k] - oneR).max() / np.abs(oneR).max() < 1e-8

@@ -85,7 +85,7 @@ assert full.shape == (nf, 2) and np.array_equal(full, ref), rank
 assert gather_rows(None, owned, nf) is None
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()
 '''
 
 
