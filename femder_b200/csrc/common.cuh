@@ -134,7 +134,6 @@ namespace fdb {
 // ---- pattern.cu ----
 void exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int64_t* total_host, cudaStream_t s);
 void build_pattern(Pattern& pat, int64_t n_rows, int64_t n_elem, int nper, const int32_t* conn_dev, cudaStream_t s);
-void build_contrib_map(Pattern& pat, cudaStream_t s);
 void check_external_pattern(const int32_t* indptr, const int32_t* indices, int64_t n_rows, int64_t nnz, cudaStream_t s);
 
 // ---- assemble.cu ----

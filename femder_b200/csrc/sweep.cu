@@ -15,6 +15,7 @@
 #include "../../include/femder_b200.h"
 #include <algorithm>
 #include <array>
+#include <map>
 #include <cstdlib>
 #include <type_traits>
 
@@ -61,7 +62,7 @@ struct SweepWork {
     int graph_iters = 0;
     int graph_F = 0;
     bool graph_overlay = false;
-    int spmv_cfg = 0;             // FDB_SPMV_CFG: 0..3 bulk-copy pipeline shapes; 8..12 plain kernel launch shapes (tuning aid)
+    int spmv_cfg = 0;             // FDB_SPMV_CFG (tuning aid): 0 default, 1..3 other bulk-copy pipeline shapes, >= 8 plain kernel only
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
@@ -825,7 +826,14 @@ struct Launch {
         if (w->spmv_bps > 0) per_sm = std::min(per_sm, w->spmv_bps);
         int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sys->num_sms * per_sm);
         auto launch = [&](auto kern) {
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // largest dynamic shared memory already opted into, per (device, kernel): all instantiations share one
+            // function-pointer TYPE, so the key must be the pointer VALUE
+            static thread_local std::map<std::pair<int, const void*>, size_t> granted;
+            size_t& have = granted[{sys->device, (const void*)kern}];
+            if (smem > have) {
+                FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                have = smem;
+            }
             kern<<<grid, (NWARP + 1) * 32, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->ov_ptr.p,
                                                                sys->ov_cg.p, sys->ov_val.p, w->coef.p, (const double*)x, (double*)y, N, S,
                                                                se, w->sc.p, (double*)w->partial.p);
@@ -1241,9 +1249,13 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     if (res->pN) w->stage.alloc((size_t)F * N);
     FDB_CUDA(cudaStreamSynchronize(s));
 
-    cudaEvent_t ev0, ev1;
-    FDB_CUDA(cudaEventCreate(&ev0));
-    FDB_CUDA(cudaEventCreate(&ev1));
+    struct Events {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } evs;
+    FDB_CUDA(cudaEventCreate(&evs.a));
+    FDB_CUDA(cudaEventCreate(&evs.b));
+    cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     FDB_CUDA(cudaEventRecord(ev0, s));
     int64_t n_spmv = 0, n_kernels = 0;
     int n_unconv = 0;
@@ -1442,8 +1454,6 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     FDB_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
     FDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     res->seconds = ms * 1e-3;
     res->n_spmv = n_spmv;
     res->n_kernels = n_kernels;

@@ -99,3 +99,37 @@ def test_h_is_cached_between_computes(gpu_lib):
     assert obj.H is H0  # "H is None" is the cache test (FEM_3D.py:1269)
     r = O.compute(g.grid, g.freq, g.mu, g.grid.nos[10:11], [2e-4], g.c0, g.rho0)
     assert (np.linalg.norm(obj.pN - r["pN"], axis=1) / np.linalg.norm(r["pN"], axis=1)).max() < 1e-6
+
+
+def test_no_boundary_conditions_branch(gpu_lib):
+    """BC is None: G = H - w^2 Q (FEM_3D.py:1348-1365)."""
+    import femder_b200 as fd
+    from conftest import Golden
+    g = Golden("tet4_shoebox_rigid")
+    AP = fd.AirProperties(c0=g.c0, rho0=g.rho0)
+    AC = fd.AlgControls(AP, freq_vec=g.freq)
+    S = fd.Source(coord=g.src, q=g.src_q)
+    obj = fd.FEM3D(g.grid, S, None, AP, AC, None, tol=1e-10)
+    obj.compute(timeit=False)
+    assert obj.A is None and obj.stats.real_arithmetic
+    r = O.compute(g.grid, g.freq, {}, g.src, g.src_q, g.c0, g.rho0)
+    assert (np.linalg.norm(obj.pN - r["pN"], axis=1) / np.linalg.norm(r["pN"], axis=1)).max() < 1e-6
+
+
+def test_empty_surface_mesh_and_bad_batch(gpu_lib):
+    import femder_b200 as fd
+    from femder_b200._lib import FemderB200Error
+    grid = fd.shoebox_tet4(3, 3, 3, jitter=0.1)
+    s = fd.System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.assemble_volume(1.21, 343.0)
+    s.set_surface_mesh(np.zeros((0, 3), dtype=np.int32), np.zeros(0, dtype=np.int64), [2, 3])   # groups without triangles
+    s.assemble_surface()
+    A = s.get_A()
+    assert len(A) == 2 and all(a.nnz == 0 for a in A) and len(s.heron_areas()) == 0
+    pN, _, st = s.sweep(2 * np.pi * np.array([50.0]), np.zeros((2, 1)), [7], [1e-4], tol=1e-9, batch=4)
+    assert st.n_unconverged == 0 and pN.shape == (1, grid.NumNosC)
+    with pytest.raises(ValueError):
+        s.sweep(2 * np.pi * np.array([50.0]), np.zeros((2, 1)), [7], [1e-4], batch=3)
+    with pytest.raises(FemderB200Error, match="source node out of range"):
+        s.sweep(2 * np.pi * np.array([50.0]), np.zeros((2, 1)), [grid.NumNosC], [1e-4], batch=4)
