@@ -58,6 +58,7 @@ SIGNATURES = {
     "fdb_surface_pattern_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_surface_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_set_surface": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_locate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_sweep": (C.c_int, [C.c_void_p, C.POINTER(SweepParams), C.POINTER(SweepResult)]),
     "fdb_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i64p]),

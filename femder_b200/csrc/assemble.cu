@@ -493,6 +493,95 @@ void assemble_surface(fdb_system* sys) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7 (set-up half): batched receiver location.  Replaces closest_node + prob_elem + which_tetra + coord_interpolation
+// (femder/FEM_3D.py:173-224) and the nearest-node rule of evaluate() (2077-2086) for many points at once.
+// ------------------------------------------------------------------------------------------------
+// one block per query point: argmin over the nodes of |x_n - p|^2, ties to the lowest index (np.argmin)
+__global__ void __launch_bounds__(256) k_nearest_node(const double* __restrict__ nos, int64_t n_nodes, const double* __restrict__ pts,
+                                                       int32_t* __restrict__ nearest, double* __restrict__ dist2) {
+    const int64_t q = blockIdx.x;
+    const double px = pts[q * 3 + 0], py = pts[q * 3 + 1], pz = pts[q * 3 + 2];
+    double best = 1.7976931348623157e308;
+    int64_t bi = 0x7fffffff;
+    for (int64_t n = threadIdx.x; n < n_nodes; n += blockDim.x) {
+        const double dx = nos[n * 3 + 0] - px, dy = nos[n * 3 + 1] - py, dz = nos[n * 3 + 2] - pz;
+        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (d < best) { best = d; bi = n; }   // ascending n per thread: the first minimum is kept
+    }
+    __shared__ double s_d[256];
+    __shared__ long long s_i[256];
+    s_d[threadIdx.x] = best;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double d2 = s_d[threadIdx.x + o];
+            const long long i2 = s_i[threadIdx.x + o];
+            if (d2 < s_d[threadIdx.x] || (d2 == s_d[threadIdx.x] && i2 < s_i[threadIdx.x])) { s_d[threadIdx.x] = d2; s_i[threadIdx.x] = i2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { nearest[q] = (int32_t)s_i[0]; dist2[q] = s_d[0]; }
+}
+
+// one thread per query point: node stencil within `tol`, else the LAST element around the nearest node whose
+// barycentric coordinates pass 0 <= l <= 1, sum <= 1 (which_tetra: later hits overwrite), else the last candidate
+// (the reference's -1 sentinel); linear shape functions of the element's 4 corner nodes
+__global__ void k_locate(const double* __restrict__ nos, const int32_t* __restrict__ conn, int nper, const int32_t* __restrict__ n2e_ptr,
+                         const int32_t* __restrict__ n2e, const double* __restrict__ pts, const int32_t* __restrict__ nearest,
+                         const double* __restrict__ dist2, double tol, int64_t n_pts, int32_t* __restrict__ nodes,
+                         double* __restrict__ weights) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pts) return;
+    const int32_t n = nearest[q];
+    if (sqrt(dist2[q]) < tol || n2e_ptr[n] == n2e_ptr[n + 1]) {
+        for (int j = 0; j < 4; ++j) { nodes[q * 4 + j] = n; weights[q * 4 + j] = (j == 0) ? 1.0 : 0.0; }
+        return;
+    }
+    const double p[3] = {pts[q * 3 + 0], pts[q * 3 + 1], pts[q * 3 + 2]};
+    int32_t hit = -1;
+    double lh[3] = {0.0, 0.0, 0.0};
+    const int32_t kb = n2e_ptr[n], ke = n2e_ptr[n + 1];
+    for (int32_t k = kb; k < ke; ++k) {
+        const int32_t e = n2e[k];
+        const int32_t* c = conn + (int64_t)e * nper;
+        double o[3], M[3][3];   // columns of M = edge vectors from corner 0
+        for (int d = 0; d < 3; ++d) o[d] = nos[(int64_t)c[0] * 3 + d];
+        for (int j = 0; j < 3; ++j)
+            for (int d = 0; d < 3; ++d) M[d][j] = nos[(int64_t)c[j + 1] * 3 + d] - o[d];
+        const double det = det3(M);
+        double Mi[3][3];
+        inv3(M, det, Mi);
+        double l[3];
+        for (int i = 0; i < 3; ++i) l[i] = Mi[i][0] * (p[0] - o[0]) + Mi[i][1] * (p[1] - o[1]) + Mi[i][2] * (p[2] - o[2]);
+        const bool inside = l[0] >= 0 && l[1] >= 0 && l[2] >= 0 && l[0] <= 1 && l[1] <= 1 && l[2] <= 1 && (l[0] + l[1] + l[2]) <= 1;
+        if (inside || (hit < 0 && k == ke - 1)) {
+            if (inside || hit < 0) { hit = e; lh[0] = l[0]; lh[1] = l[1]; lh[2] = l[2]; }
+        }
+    }
+    const int32_t* c = conn + (int64_t)hit * nper;
+    for (int j = 0; j < 4; ++j) nodes[q * 4 + j] = c[j];
+    weights[q * 4 + 0] = 1.0 - lh[0] - lh[1] - lh[2];
+    weights[q * 4 + 1] = lh[0];
+    weights[q * 4 + 2] = lh[1];
+    weights[q * 4 + 3] = lh[2];
+}
+
+void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double tol, int32_t* nodes_dev, double* weights_dev) {
+    FDB_REQUIRE(sys->have_pattern && sys->vol.conn.p && sys->vol.n2e_ptr.p && sys->nos.p, "fdb_set_volume_mesh must be called first");
+    if (n_pts == 0) return;
+    DevBuf<int32_t> nearest;
+    DevBuf<double> dist2;
+    nearest.alloc(n_pts);
+    dist2.alloc(n_pts);
+    k_nearest_node<<<(unsigned)n_pts, 256, 0, sys->stream>>>(sys->nos.p, sys->n_nodes, pts_dev, nearest.p, dist2.p);
+    k_locate<<<grid_for(n_pts, 128), 128, 0, sys->stream>>>(sys->nos.p, sys->vol.conn.p, sys->vol.nper, sys->vol.n2e_ptr.p, sys->vol.n2e.p,
+                                                           pts_dev, nearest.p, dist2.p, tol, n_pts, nodes_dev, weights_dev);
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
 // overlay for the SpMV: per row, (col, group, value) of every touched (group, entry), ordered by entry then group
 // ------------------------------------------------------------------------------------------------
 template <int PASS>

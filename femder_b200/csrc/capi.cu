@@ -328,6 +328,24 @@ int fdb_set_surface(fdb_system* sys, int n_groups, int64_t nnz_b, const int32_t*
     FDB_API_END
 }
 
+int fdb_locate_points(fdb_system* sys, int64_t n_pts, const double* pts, double tol, int32_t* nodes, double* weights) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    FDB_REQUIRE(n_pts >= 0 && (n_pts == 0 || (pts && nodes && weights)), "bad arguments");
+    if (n_pts) {
+        fdb::DevBuf<double> d_pts, d_w;
+        fdb::DevBuf<int32_t> d_nodes;
+        d_pts.alloc((size_t)n_pts * 3);
+        d_w.alloc((size_t)n_pts * 4);
+        d_nodes.alloc((size_t)n_pts * 4);
+        FDB_CUDA(cudaMemcpyAsync(d_pts.p, pts, (size_t)n_pts * 3 * sizeof(double), cudaMemcpyDefault, sys->stream));
+        fdb::locate_points(sys, n_pts, d_pts.p, tol, d_nodes.p, d_w.p);
+        FDB_CUDA(cudaMemcpy(nodes, d_nodes.p, (size_t)n_pts * 4 * sizeof(int32_t), cudaMemcpyDefault));
+        FDB_CUDA(cudaMemcpy(weights, d_w.p, (size_t)n_pts * 4 * sizeof(double), cudaMemcpyDefault));
+    }
+    FDB_API_END
+}
+
 int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res) {
     FDB_API_BEGIN
     FDB_SYS(sys);

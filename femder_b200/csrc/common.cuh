@@ -73,10 +73,13 @@ struct Pattern {
     DevBuf<int32_t> elem2nnz;  // [n_elem][nper][nper]
     DevBuf<int32_t> c_ptr;     // [nnz+1]  contributions of nnz z are c_src[c_ptr[z] .. c_ptr[z+1])
     DevBuf<int32_t> c_src;     // [n_elem*nper*nper]  key e*nper^2 + a*nper + b, ascending within each nnz
+    DevBuf<int32_t> n2e_ptr;   // [n_rows+1]  elements around node n are n2e[n2e_ptr[n] .. n2e_ptr[n+1]), ascending
+    DevBuf<int32_t> n2e;       // [n_elem*nper]
     void reset() {
         n_rows = nnz = n_elem = 0;
         nper = 0;
         conn.release(); indptr.release(); indices.release(); elem2nnz.release(); c_ptr.release(); c_src.release();
+        n2e_ptr.release(); n2e.release();
     }
 };
 
@@ -143,6 +146,7 @@ void assemble_surface(fdb_system* sys);
 void build_overlay(fdb_system* sys);
 void extract_diagonal(fdb_system* sys);
 void build_sell(fdb_system* sys);
+void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double tol, int32_t* nodes_dev, double* weights_dev);
 void interleave_hq(fdb_system* sys, const double* H, const double* Q);
 void deinterleave_hq(fdb_system* sys, double* H, double* Q);
 

@@ -248,7 +248,9 @@ void build_pattern(Pattern& pat, int64_t n_rows, int64_t n_elem, int nper, const
     FDB_CUDA(cudaStreamSynchronize(s));
     FDB_REQUIRE(!bad_h, "connectivity holds a node index outside [0, n_nodes)");
 
-    DevBuf<int32_t> deg, n2e_ptr, n2e, cursor, scratch, rowlen;
+    DevBuf<int32_t> deg, cursor, scratch, rowlen;
+    DevBuf<int32_t>& n2e_ptr = pat.n2e_ptr;   // kept: receiver location walks the elements around a node
+    DevBuf<int32_t>& n2e = pat.n2e;
     deg.alloc(n_rows);
     deg.zero(s);
     if (nc) k_count_deg<<<grid_for(nc, B), B, 0, s>>>(conn_dev, nc, deg.p);

@@ -235,9 +235,7 @@ class FEM3D:
 
         rcv_nodes = rcv_w = None
         if self.R is not None and not keep_pN:
-            st = [receiver_stencil(self.nos, self.elem_vol, c) for c in np.atleast_2d(self.R.coord)]
-            rcv_nodes = np.array([s[0] for s in st], dtype=np.int32)
-            rcv_w = np.array([s[1] for s in st], dtype=np.float64)
+            rcv_nodes, rcv_w = sys.locate_points(np.atleast_2d(self.R.coord), 1e-3)   # batched on the GPU
 
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
         owned = sharding.owned_frequencies(nf, 1, rank, world)
@@ -270,8 +268,14 @@ class FEM3D:
         if self.pN is None:
             raise RuntimeError("evaluate() needs pN: call compute() (with keep_pN=True) first")
         cols = []
-        for i in range(len(R.coord)):
-            nodes, wts = receiver_stencil(self.nos, self.elem_vol, R.coord[i, :], interpolation_tolerance)
+        coords = np.atleast_2d(R.coord)
+        if self._sys is not None and self._sys_key is not None:
+            all_nodes, all_w = self._sys.locate_points(coords, interpolation_tolerance)   # batched on the GPU
+        else:
+            st = [receiver_stencil(self.nos, self.elem_vol, c, interpolation_tolerance) for c in coords]
+            all_nodes, all_w = np.array([t[0] for t in st]), np.array([t[1] for t in st])
+        for i in range(len(coords)):
+            nodes, wts = all_nodes[i], all_w[i]
             if wts[0] == 1.0 and not wts[1:].any():
                 cols.append(self.pN[:, nodes[0]])
             else:

@@ -240,6 +240,15 @@ class System:
         check(self._lib.fdb_set_surface(self._h, ng, len(ix), ptr(ip), ptr(ix), ptr(vals)))
         self.n_groups = ng
 
+    # ---- receivers ----------------------------------------------------------------------------
+    def locate_points(self, coords, tol=1e-3):
+        """(nodes (P, 4) int32, weights (P, 4)) with p(coord) = sum_j w_j p[node_j] for every point, on the GPU."""
+        pts = _f64(np.atleast_2d(coords))
+        nodes = np.empty((len(pts), 4), dtype=np.int32)
+        w = np.empty((len(pts), 4), dtype=np.float64)
+        check(self._lib.fdb_locate_points(self._h, len(pts), ptr(pts), float(tol), ptr(nodes), ptr(w)))
+        return nodes, w
+
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
               max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,

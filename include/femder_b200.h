@@ -77,6 +77,15 @@ int fdb_surface_get(fdb_system* sys, double* A_vals /* [n_groups][nnz_b] */, uin
 int fdb_set_surface(fdb_system* sys, int n_groups, int64_t nnz_b, const int32_t* indptr, const int32_t* indices,
                     const double* A_vals /* [n_groups][nnz_b] */);
 
+/* ---- receivers (K7, set-up half) ------------------------------------------------------------------ *
+ * Batched receiver location: for every query point the 4 nodes and weights with p(point) = sum_j w_j p[node_j].
+ * Replaces, for many points at once, the nearest-node rule of evaluate() (femder/FEM_3D.py:2077-2086) and
+ * closest_node + prob_elem + which_tetra + coord_interpolation (FEM_3D.py:173-224): the closest node if it lies
+ * within `tol`, otherwise linear interpolation in the LAST element around that node that passes the barycentric
+ * test (the last candidate if none does).  The result feeds fdb_sweep_params.rcv_nodes / rcv_w. */
+int fdb_locate_points(fdb_system* sys, int64_t n_pts, const double* pts /* [n_pts][3] */, double tol,
+                      int32_t* nodes /* [n_pts][4] */, double* weights /* [n_pts][4] */);
+
 /* ---- frequency sweep (K5 fused multi-frequency SpMV, K6 COCG, K7 receiver gather) -------------- *
  * Replaces the hot loop FEM_3D.py:1304-1319: for every frequency n
  *     G = H + 1j*w[n]*sum_g mu[g][n]*A[g] - w[n]**2*Q ;  b = -1j*w[n]*q ;  pN[n] = solve(G, b)

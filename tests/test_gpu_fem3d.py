@@ -133,3 +133,37 @@ def test_empty_surface_mesh_and_bad_batch(gpu_lib):
         s.sweep(2 * np.pi * np.array([50.0]), np.zeros((2, 1)), [7], [1e-4], batch=3)
     with pytest.raises(FemderB200Error, match="source node out of range"):
         s.sweep(2 * np.pi * np.array([50.0]), np.zeros((2, 1)), [grid.NumNosC], [1e-4], batch=4)
+
+
+def test_gpu_point_location_matches_host_rule(gpu_lib):
+    """fdb_locate_points against the host restatement of closest_node / which_tetra / coord_interpolation
+    (FEM_3D.py:173-224) on random points, mesh nodes and points outside the mesh (sentinel rule)."""
+    import femder_b200 as fd
+    from femder_b200 import receiver_stencil
+    grid = fd.shoebox_tet4(7, 9, 6, jitter=0.2)
+    s = fd.System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    rng = np.random.default_rng(5)
+    pts = np.vstack([rng.uniform([0.05, 0.05, 0.05], [2.95, 3.95, 2.45], size=(300, 3)), grid.nos[[0, 17, 200]],
+                     grid.nos[5] + 4e-4, [[3.2, 4.1, 2.6], [-0.1, 2.0, 1.0]]])
+    nodes, w = s.locate_points(pts, 1e-3)
+    assert nodes.shape == (len(pts), 4) and w.shape == (len(pts), 4)
+    pN = rng.standard_normal((2, grid.NumNosC)) + 1j * rng.standard_normal((2, grid.NumNosC))
+    ref = O.evaluate(grid.nos, grid.elem_vol, pN, pts)
+    got = np.einsum("fpj,pj->fp", pN[:, nodes.astype(np.int64)], w)
+    assert np.abs(got - ref).max() < 1e-10
+    n_same = 0
+    for i, c in enumerate(pts):
+        hn, hw = receiver_stencil(grid.nos, grid.elem_vol, c)
+        n_same += int(np.array_equal(hn, nodes[i]))
+        assert abs(w[i].sum() - 1) < 1e-12
+    assert n_same >= len(pts) - 3          # a point exactly on a face may legitimately pick the neighbouring element
+    # Tet10: corner nodes of the quadratic element
+    g10 = fd.to_tet10(grid)
+    s10 = fd.System(0)
+    s10.set_volume_mesh(g10.nos, g10.elem_vol)
+    n10, w10 = s10.locate_points(pts[:50], 1e-3)
+    p10 = rng.standard_normal((1, g10.NumNosC))
+    for i in range(50):   # same rule on the Tet10 connectivity: the nearest node may be a mid-edge node
+        hn, hw = receiver_stencil(g10.nos, g10.elem_vol, pts[i])
+        assert abs(p10[0, n10[i].astype(np.int64)] @ w10[i] - p10[0, hn.astype(np.int64)] @ hw) < 1e-10
