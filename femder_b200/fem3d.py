@@ -112,9 +112,10 @@ class FEM3D:
         self.pN = None
         self.F_n = None
         self.Vc = None
-        self.H = None
-        self.Q = None
-        self.A = None
+        # H, Q, A live on the GPU after compute(); the scipy objects the reference leaves behind are built on first access
+        self._H = self._Q = self._A = None
+        self._assembled = False
+        self._A_ready = False
         self.rho = {}
         self.c = {}
         if BC is not None and (len(getattr(BC, "rhoc", {})) > 0 or len(getattr(BC, "cc", {})) > 0):
@@ -133,6 +134,47 @@ class FEM3D:
         self._stream = stream
         self._sys = None
         self._sys_key = None
+
+    # ---- H, Q, A: same attributes as the reference, fetched from the device on demand ------------------
+    def _fetch_HQ(self):
+        H, Q = self._sys.get_HQ()
+        if self.compat_complex64:
+            H, Q = H.astype(np.complex64), Q.astype(np.complex64)
+        self._H, self._Q = H, Q
+
+    @property
+    def H(self):
+        if self._H is None and self._assembled:
+            self._fetch_HQ()
+        return self._H
+
+    @H.setter
+    def H(self, value):
+        self._H = value
+        if value is None:
+            self._assembled = False   # "H is None" is the reference's cache test (FEM_3D.py:1269): forces re-assembly
+
+    @property
+    def Q(self):
+        if self._Q is None and self._assembled:
+            self._fetch_HQ()
+        return self._Q
+
+    @Q.setter
+    def Q(self, value):
+        self._Q = value
+
+    @property
+    def A(self):
+        if self._A is None and self._A_ready:
+            self._A = self._sys.get_A(drop_zeros=(self.order == 2))
+        return self._A
+
+    @A.setter
+    def A(self, value):
+        self._A = value
+        if value is None:
+            self._A_ready = False
 
     # ---- reference properties (FEM_3D.py:1220-1238) ------------------------------------------
     @property
@@ -187,18 +229,17 @@ class FEM3D:
         sys.set_surface_mesh(self.elem_surf, self.domain_index_surf, group_ids)
         self.areas = sys.heron_areas().astype(np.complex128)  # compute_areas returns complex128 (FEM_3D.py:743)
 
-        if self.H is None or new_mesh:
+        if not self._assembled or new_mesh:
             sys.assemble_volume(self.rho0, self.c0)
             if self.compat_complex64:
                 H, Q = sys.get_HQ_values()
                 sys.set_HQ_values(H.astype(np.float32).astype(np.float64), Q.astype(np.float32).astype(np.float64))
-            self.H, self.Q = sys.get_HQ()
-            if self.compat_complex64:
-                self.H = self.H.astype(np.complex64)
-                self.Q = self.Q.astype(np.complex64)
+            self._H = self._Q = None
+            self._assembled = True
         if self.BC is not None:
             sys.assemble_surface()
-            self.A = sys.get_A(drop_zeros=(self.order == 2))
+            self._A = None
+            self._A_ready = True
 
         # velocity boundary conditions (FEM_3D.py:1286-1287, 1320-1347): V_i are the surface matrices of the groups in
         # BC.v; the right-hand side of frequency n is -1j*w[n] * sum_i v_i[n] * (V_i @ 1)
