@@ -60,6 +60,8 @@ SIGNATURES = {
     "fdb_set_surface": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_locate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "fdb_sweep": (C.c_int, [C.c_void_p, C.POINTER(SweepParams), C.POINTER(SweepResult)]),
+    "fdb_sizeof_sweep_params": (C.c_int, []),
+    "fdb_sizeof_sweep_result": (C.c_int, []),
     "fdb_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i64p]),
     "fdb_spmv_enqueue": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i64p]),
@@ -85,6 +87,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.fdb_sizeof_sweep_params() != C.sizeof(SweepParams) or lib.fdb_sizeof_sweep_result() != C.sizeof(SweepResult):
+        raise FemderB200Error("libfemder_b200.so and femder_b200/_lib.py disagree on the sweep struct layout - rebuild the library")
     _lib = lib
     return lib
 

@@ -353,6 +353,9 @@ int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* re
     FDB_API_END
 }
 
+int fdb_sizeof_sweep_params(void) { return (int)sizeof(fdb_sweep_params); }
+int fdb_sizeof_sweep_result(void) { return (int)sizeof(fdb_sweep_result); }
+
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu, const double* x, double* y) {
     FDB_API_BEGIN
     FDB_SYS(sys);

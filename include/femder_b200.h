@@ -134,6 +134,9 @@ typedef struct fdb_sweep_result {
 } fdb_sweep_result;
 
 int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);
+/* sizeof(fdb_sweep_params) / sizeof(fdb_sweep_result) as compiled, so a binding can verify its struct layout. */
+int fdb_sizeof_sweep_params(void);
+int fdb_sizeof_sweep_result(void);
 
 /* y = G_f x for a batch of frequencies on caller data: x, y are [n_nodes][batch] complex. (K5 alone; parity) */
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu /* [n_groups][batch] complex */,
