@@ -202,3 +202,50 @@ def test_bad_inputs_raise(gpu_lib):
     s.set_volume_mesh(grid.nos, grid.elem_vol)
     with pytest.raises(FemderB200Error):
         s.assemble_volume(0.0, 343.0)
+
+
+def test_config4_full_size_properties(gpu_lib):
+    """BASELINE config 4 at full size (99x133x74 cells, 1 005 000 DOF): size-independent properties of the pattern, the
+    assembled matrices and two solves, checked on the host with numpy / scipy."""
+    from scipy.sparse import csr_matrix
+    from femder_b200 import System
+    from femder_b200.mesh import shoebox_tet4
+    grid = shoebox_tet4(99, 133, 74)
+    N = grid.NumNosC
+    assert N == 1005000 and grid.NumElemC == 5846148
+    s = System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    indptr, indices = s.pattern()
+    # canonical CSR: int32, sorted and duplicate-free inside every row
+    rows = np.repeat(np.arange(N, dtype=np.int64), np.diff(indptr))
+    key = rows * N + indices
+    assert indptr[0] == 0 and indptr[-1] == len(indices) and np.all(np.diff(key) > 0)
+    # exactly the couplings of the connectivity: nnz = N + 2 * (number of mesh edges), pattern symmetric
+    ev = np.asarray(grid.elem_vol, dtype=np.int64)
+    pairs = np.concatenate([np.minimum(ev[:, a], ev[:, b]) * N + np.maximum(ev[:, a], ev[:, b])
+                            for a, b in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))])
+    edges = np.unique(pairs)
+    assert len(indices) == N + 2 * len(edges)
+    upper = key[indices > rows]
+    assert np.array_equal(upper, edges)                                   # row-major upper triangle == sorted edge keys
+    lower = (indices[indices < rows].astype(np.int64) * N + rows[indices < rows])
+    assert np.array_equal(np.sort(lower), edges)                          # symmetric
+    # assembled values
+    c0, rho0 = 343.0, 1.21
+    s.assemble_volume(rho0, c0)
+    Hv, Qv = s.get_HQ_values()
+    H = csr_matrix((Hv, indices, indptr), shape=(N, N))
+    Q = csr_matrix((Qv, indices, indptr), shape=(N, N))
+    assert abs(Qv.sum() * rho0 * c0 ** 2 - 30.0) < 1e-8                   # sum(Q) rho c^2 = room volume
+    assert np.abs(H @ np.ones(N)).max() < 1e-9                            # H 1 = 0
+    assert np.abs((H - H.T).data).max() < 1e-12 if (H - H.T).nnz else True
+    # two solves verified with scipy: ||b - G x|| / ||b|| <= tol, purely imaginary pressure for a rigid room
+    freq = np.array([20.0, 45.0])
+    w = 2 * np.pi * freq
+    src = grid.closest_node([1.0, 1.0, 1.2])
+    pN, _, st = s.sweep(w, np.zeros((0, 2)), [src], [1e-4], tol=1e-8, batch=16)
+    assert st.n_unconverged == 0 and st.real_arithmetic and not pN.real.any()
+    for n in range(2):
+        b = np.zeros(N, dtype=complex); b[src] = -1j * w[n] * 1e-4
+        res = b - (H @ pN[n] - w[n] ** 2 * (Q @ pN[n]))
+        assert np.linalg.norm(res) / np.linalg.norm(b) < 1.05e-8

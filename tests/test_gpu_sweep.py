@@ -265,3 +265,35 @@ def test_multi_rhs_source_sets(gpu_lib):
         one, oneR, _ = s.sweep(w, mu, nodes, q, rn, rw, tol=1e-11, batch=8)
         assert _rel_rows(pN[k], one).max() < 1e-8
         assert np.abs(pR[k] - oneR).max() / np.abs(oneR).max() < 1e-8
+
+
+def test_config4_spmv_full_size(gpu_lib):
+    """The fused multi-frequency SpMV at BASELINE config-4 size (1M DOF) with an admittance wall: every slot against
+    scipy's G_f @ x built from the GPU-assembled H, Q, A, and symmetry x^T G y = y^T G x."""
+    import femder_b200 as fd
+    grid = fd.shoebox_tet4(99, 133, 74, jitter=0.2)
+    s = fd.System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.set_surface_mesh(grid.elem_surf, grid.domain_index_surf, np.arange(2, 8))
+    s.assemble_volume(1.21, 343.0)
+    s.assemble_surface()
+    H, Q = s.get_HQ()
+    A = s.get_A()
+    N, F = grid.NumNosC, 8
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((N, F)) + 1j * rng.standard_normal((N, F))
+    w = 2 * np.pi * np.linspace(40.0, 480.0, F)
+    mu = np.zeros((6, F), dtype=complex)
+    mu[5] = (0.05 + 0.01j) / (343 * 1.21)
+    mu[1] = 0.2 / (343 * 1.21)
+    y = s.spmv(w, mu, x)
+    Hr, Qr = H.tocsr(), Q.tocsr()
+    Ar = [a.tocsr() for a in A]
+    for f in (0, 3, 7):
+        ref = Hr @ x[:, f] - w[f] ** 2 * (Qr @ x[:, f]) + 1j * w[f] * sum(mu[g, f] * (Ar[g] @ x[:, f]) for g in range(6))
+        assert np.linalg.norm(y[:, f] - ref) / np.linalg.norm(ref) < 1e-13
+    z = rng.standard_normal((N, F)) + 1j * rng.standard_normal((N, F))
+    yz = s.spmv(w, mu, z)
+    lhs = np.einsum("nf,nf->f", z, y)      # z^T G x (unconjugated)
+    rhs = np.einsum("nf,nf->f", x, yz)     # x^T G z
+    assert np.abs(lhs - rhs).max() / np.abs(lhs).max() < 1e-11
