@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfemder_b200.so")
-SOURCES = ["pattern.cu", "assemble.cu", "sweep.cu", "capi.cu"]
+SOURCES = ["pattern.cu", "assemble.cu", "reorder.cu", "sweep.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "femder_b200.h")]
 
 

@@ -298,7 +298,7 @@ __global__ void k_deinterleave(const double2* __restrict__ hq, int64_t n, double
     }
 }
 __global__ void k_diag(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                       const double2* __restrict__ hq, int64_t n_rows, double2* __restrict__ diag) {
+                       const double2* __restrict__ hq, int64_t n_rows, const int32_t* __restrict__ perm, double2* __restrict__ diag) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     int lo = indptr[r], hi = indptr[r + 1];
@@ -309,7 +309,7 @@ __global__ void k_diag(const int32_t* __restrict__ indptr, const int32_t* __rest
         if (c == r) { d = hq[mid]; break; }
         if (c < r) lo = mid + 1; else hi = mid;
     }
-    diag[r] = d;
+    diag[perm[r]] = d;   // stored in the sweep's internal order
 }
 
 void interleave_hq(fdb_system* sys, const double* H, const double* Q) {
@@ -340,71 +340,12 @@ void deinterleave_hq(fdb_system* sys, double* H, double* Q) {
 }
 
 void extract_diagonal(fdb_system* sys) {
+    FDB_REQUIRE(sys->have_order, "internal order missing");
     sys->diag_hq.alloc(sys->n_nodes);
     k_diag<<<grid_for(sys->n_nodes, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p,
-                                                                  sys->n_nodes, sys->diag_hq.p);
+                                                                  sys->n_nodes, sys->perm.p, sys->diag_hq.p);
     FDB_CUDA(cudaGetLastError());
     build_sell(sys);
-}
-
-// SELL-8: the layout the SpMV streams.  A warp's rows read the same k of one slice together, so the column
-// index and (H, Q) loads of a warp are contiguous (one or two sectors) instead of one sector per row.
-__global__ void k_sell_width(const int32_t* __restrict__ indptr, int64_t n_rows, int64_t n_slices, int32_t* __restrict__ width) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slices) return;
-    int w = 0;
-    for (int i = 0; i < 8; ++i) {
-        int64_t r = s * 8 + i;
-        if (r < n_rows) w = max(w, indptr[r + 1] - indptr[r]);
-    }
-    width[s] = w;
-}
-
-__global__ void k_sell_fill(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                            const double2* __restrict__ hq, int64_t n_rows, int64_t n_slices,
-                            const int32_t* __restrict__ sell_off, int32_t* __restrict__ sell_idx,
-                            double2* __restrict__ sell_hq) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_slices * 8) return;
-    const int64_t s = t >> 3;
-    const int pos = (int)(t & 7);
-    const int64_t r = t;
-    const int off = sell_off[s], width = sell_off[s + 1] - off;
-    int b = 0, len = 0;
-    if (r < n_rows) { b = indptr[r]; len = indptr[r + 1] - b; }
-    const int32_t pad_col = (int32_t)min(r, n_rows - 1);
-    for (int k = 0; k < width; ++k) {
-        const int64_t o = ((int64_t)off + k) * 8 + pos;
-        if (k < len) {
-            sell_idx[o] = indices[b + k];
-            sell_hq[o] = hq[b + k];
-        } else {
-            sell_idx[o] = pad_col;
-            sell_hq[o] = make_double2(0.0, 0.0);
-        }
-    }
-}
-
-void build_sell(fdb_system* sys) {
-    const int64_t N = sys->n_nodes;
-    const int64_t S = (N + 7) / 8;
-    sys->n_slices = S;
-    DevBuf<int32_t> width;
-    width.alloc(S);
-    k_sell_width<<<grid_for(S, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, N, S, width.p);
-    sys->sell_off.alloc(S + 1);
-    int64_t tot = 0;
-    exclusive_scan_i32(width.p, sys->sell_off.p, S, &tot, sys->stream);
-    FDB_REQUIRE(tot * 8 < 2147483647LL, "SELL layout exceeds int32 indexing");
-    sys->sell_entries = tot * 8;
-    sys->sell_idx.alloc(tot ? tot * 8 : 1);
-    sys->sell_hq.alloc(tot ? tot * 8 : 1);
-    k_sell_fill<<<grid_for(S * 8, 256), 256, 0, sys->stream>>>(sys->vol.indptr.p, sys->vol.indices.p, sys->hq.p, N, S,
-                                                               sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p);
-    FDB_CUDA(cudaGetLastError());
-    sys->sell_off_host.resize(S + 1);
-    FDB_CUDA(cudaMemcpyAsync(sys->sell_off_host.data(), sys->sell_off.p, (S + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, sys->stream));
-    FDB_CUDA(cudaStreamSynchronize(sys->stream));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,38 +528,42 @@ void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double
 template <int PASS>
 __global__ void k_overlay(const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
                           const double* __restrict__ A_vals, const uint8_t* __restrict__ touched, int n_groups,
-                          int64_t nnz_b, int64_t n_rows, int32_t* __restrict__ cnt, const int32_t* __restrict__ ov_ptr,
+                          int64_t nnz_b, int64_t n_rows, const int32_t* __restrict__ perm, const int32_t* __restrict__ iperm,
+                          int32_t* __restrict__ cnt, const int32_t* __restrict__ ov_ptr,
                           int2* __restrict__ ov_cg, double* __restrict__ ov_val) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
+    // one thread per row of the sweep's internal order; r = that row in the caller's numbering
+    const int64_t rn = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rn >= n_rows) return;
+    const int64_t r = iperm[rn];
     int n = 0;
-    int32_t out = (PASS == 1) ? ov_ptr[r] : 0;
+    int32_t out = (PASS == 1) ? ov_ptr[rn] : 0;
     for (int32_t z = b_indptr[r]; z < b_indptr[r + 1]; ++z)
         for (int g = 0; g < n_groups; ++g)
             if (touched[(int64_t)g * nnz_b + z]) {
                 if (PASS == 1) {
-                    ov_cg[out + n] = make_int2(b_indices[z], g);
+                    ov_cg[out + n] = make_int2(perm[b_indices[z]], g);
                     ov_val[out + n] = A_vals[(int64_t)g * nnz_b + z];
                 }
                 ++n;
             }
-    if (PASS == 0) cnt[r] = n;
+    if (PASS == 0) cnt[rn] = n;
 }
 
 void build_overlay(fdb_system* sys) {
+    FDB_REQUIRE(sys->have_order, "set the volume pattern before the surface matrices");
     const int64_t N = sys->n_nodes, Zb = sys->surf.nnz;
     DevBuf<int32_t> cnt;
     cnt.alloc(N);
     sys->ov_ptr.alloc(N + 1);
     k_overlay<0><<<grid_for(N, 256), 256, 0, sys->stream>>>(sys->surf.indptr.p, sys->surf.indices.p, sys->A_vals.p,
-                                                           sys->A_touched.p, sys->n_groups, Zb, N, cnt.p, nullptr, nullptr, nullptr);
+                                                           sys->A_touched.p, sys->n_groups, Zb, N, sys->perm.p, sys->iperm.p, cnt.p, nullptr, nullptr, nullptr);
     int64_t n_ov = 0;
     exclusive_scan_i32(cnt.p, sys->ov_ptr.p, N, &n_ov, sys->stream);
     sys->n_ov = n_ov;
     sys->ov_cg.alloc(n_ov ? n_ov : 1);
     sys->ov_val.alloc(n_ov ? n_ov : 1);
     k_overlay<1><<<grid_for(N, 256), 256, 0, sys->stream>>>(sys->surf.indptr.p, sys->surf.indices.p, sys->A_vals.p,
-                                                           sys->A_touched.p, sys->n_groups, Zb, N, nullptr, sys->ov_ptr.p,
+                                                           sys->A_touched.p, sys->n_groups, Zb, N, sys->perm.p, sys->iperm.p, nullptr, sys->ov_ptr.p,
                                                            sys->ov_cg.p, sys->ov_val.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(sys->stream));

@@ -128,7 +128,10 @@ int fdb_set_volume_mesh(fdb_system* sys, int64_t n_nodes, const double* nos, int
     FDB_CUDA(cudaMemcpyAsync(sys->vol.conn.p, conn, (size_t)n_elem * nper * sizeof(int32_t), cudaMemcpyDefault, sys->stream));
     sys->have_pattern = false;
     sys->have_hq = false;
+    sys->have_order = false;
+    sys->have_overlay = false;   // stored in the internal order of the previous pattern
     fdb::build_pattern(sys->vol, n_nodes, n_elem, nper, sys->vol.conn.p, sys->stream);
+    fdb::build_order(sys);
     sys->have_pattern = true;
     FDB_API_END
 }
@@ -177,6 +180,9 @@ int fdb_set_pattern(fdb_system* sys, int64_t n_nodes, int64_t nnz, const int32_t
     sys->vol.indices.alloc(nnz ? nnz : 1);
     FDB_CUDA(cudaMemcpy(sys->vol.indptr.p, hp.data(), hp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (nnz) FDB_CUDA(cudaMemcpy(sys->vol.indices.p, hi.data(), hi.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    sys->have_order = false;
+    sys->have_overlay = false;   // stored in the internal order of the previous pattern
+    fdb::build_order(sys);
     sys->have_pattern = true;
     sys->have_hq = false;
     FDB_API_END

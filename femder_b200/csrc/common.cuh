@@ -102,14 +102,27 @@ struct fdb_system {
     fdb::DevBuf<double2> hq;         // [nnz] (H, Q) interleaved: the layout the SpMV streams
     bool have_hq = false;
     fdb::DevBuf<double2> diag_hq;    // [n_nodes] diagonal of H and Q
-    // SELL-8 copy of (indices, hq) the SpMV streams: slice s = rows 8s..8s+7, entry k of row r at
-    // (sell_off[s] + k)*8 + r%8; rows shorter than the slice width are padded with (col = row, 0, 0)
+    // SELL-8 copy of (indices, hq) the SpMV streams, in the internal order: slice s = rows 8s..8s+7, entry k of row r
+    // at (sell_off[s] + k)*8 + r%8; rows shorter than the slice width are padded with (col = row, 0, 0)
     int64_t n_slices = 0;
     int64_t sell_entries = 0;
     fdb::DevBuf<int32_t> sell_off;   // [n_slices+1] in units of 8 entries
     fdb::DevBuf<int32_t> sell_idx;   // [sell_entries]
     fdb::DevBuf<double2> sell_hq;    // [sell_entries]
     std::vector<int32_t> sell_off_host;
+    // Internal node order of the sweep (reorder.cu): new = perm[old], old = iperm[new].  The SELL stream, diag_hq and
+    // the overlay are stored in the NEW order; the C ABI speaks the caller's numbering.
+    bool have_order = false;
+    fdb::DevBuf<int32_t> perm, iperm;
+    std::vector<int32_t> perm_host;
+    fdb::DevBuf<int32_t> sell_src;     // [sell_entries] CSR position behind each SELL entry, -1 = padding
+    // 128-row tiles of k_spmv_blob: sorted distinct columns per tile, 16-bit position of every entry's column in it
+    int64_t n_tiles = 0;
+    int max_tile_cols = 0, max_tile_entries = 0;
+    fdb::DevBuf<int32_t> tile_cptr;    // [n_tiles+1]
+    fdb::DevBuf<int32_t> tile_cols;    // [tile_cptr[n_tiles]] new-order column ids
+    fdb::DevBuf<int32_t> tile_self;    // [n_tiles] position of the tile's first own row in its column list
+    fdb::DevBuf<uint16_t> sell_lidx;   // [sell_entries]
 
     // surface
     int64_t n_tri = 0;
@@ -145,7 +158,8 @@ void heron_areas(fdb_system* sys);
 void assemble_surface(fdb_system* sys);
 void build_overlay(fdb_system* sys);
 void extract_diagonal(fdb_system* sys);
-void build_sell(fdb_system* sys);
+void build_sell(fdb_system* sys);    // reorder.cu: SELL values from the CSR values
+void build_order(fdb_system* sys);   // reorder.cu: internal order + SELL structure + tile tables, once per pattern
 void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double tol, int32_t* nodes_dev, double* weights_dev);
 void interleave_hq(fdb_system* sys, const double* H, const double* Q);
 void deinterleave_hq(fdb_system* sys, double* H, double* Q);

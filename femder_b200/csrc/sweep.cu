@@ -509,6 +509,178 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5 for vectors whose rows are 128 bytes (8 complex or 16 real frequencies): the x rows a 128-row tile touches are
+// staged in SHARED MEMORY once and the ~15 gathers per row are served from there.
+//
+// The L1 global-load path returns one 128-byte line every ~2 cycles per SM; with 15 gathers of a full line per
+// row that pipe, not HBM, bounded k_spmv_tma.  Shared memory returns 128 bytes per cycle, and
+// in the sweep's blob order (reorder.cu) a tile's distinct columns are only ~2.5 x its 128 rows, so staging costs a
+// fraction of the gathers it replaces.
+//   fill     thread 0 streams the tile's (H, Q) values and 16-bit local column positions with two bulk copies
+//            (cp.async.bulk -> mbarrier); all threads copy the tile's x rows with 16-byte cp.async (L2 -> smem, no
+//            registers, no L1 allocation)
+//   compute  2 lanes per row, 16 rows per warp.  A row of x is 8 chunks of 16 bytes; lane h of row r reads chunks
+//            h + 2*((r + j) % 4), j = 0..3, so the 8 lanes of every quarter-warp phase hit 8 different bank groups:
+//            conflict-free 128-bit loads whatever the column positions are.
+// Blocks take tiles round-robin, so the tiles in flight are neighbours in the blob order and share their halo rows
+// in L2.  Two blocks per SM overlap one block's fill with the other's compute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kBlobBlock = 256;
+constexpr int kBlobTile = 128;   // rows per tile (= kTileRows of reorder.cu)
+
+template <bool CPX, bool DOT, bool OVERLAY>
+__global__ void __launch_bounds__(kBlobBlock, 2)
+k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
+            const int32_t* __restrict__ tile_cptr, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_self,
+            const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
+            const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
+            int64_t n_slices, int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int F = CPX ? 8 : 16;
+    static_assert(!(OVERLAY && !CPX), "a boundary term makes the system complex");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);                                                              // [x_cap][16]
+    double2* s_hq = reinterpret_cast<double2*>(smem_raw + (size_t)x_cap * 128);                                    // [stage_entries]
+    uint16_t* s_lx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 16);    // [stage_entries]
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = lane & 1, rl = lane >> 1;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int choff[4];        // offset (in doubles) of the chunk this lane reads at step j
+    double w2v[4][2];    // omega^2 of the frequencies in that chunk
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = h + 2 * ((rl + j) & 3);
+        choff[j] = 2 * ch;
+        w2v[j][0] = sc->w2[CPX ? ch : 2 * ch];
+        w2v[j][1] = sc->w2[CPX ? ch : 2 * ch + 1];
+    }
+    double dot[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int c0 = tile_cptr[t], C = tile_cptr[t + 1] - c0;
+        const int64_t sl0 = t * (kBlobTile / 8), sl1 = min(sl0 + kBlobTile / 8, n_slices);
+        const int tile_off = sell_off[sl0];
+        if (tid == 0) {
+            const int64_t e0 = (int64_t)tile_off * 8;
+            const uint32_t n = (uint32_t)(sell_off[sl1] - tile_off) * 8u;
+            mbar_expect_tx(&bar, n * 18u);
+            if (n) {
+                bulk_g2s(s_hq, sell_hq + e0, n * 16u, &bar);
+                bulk_g2s(s_lx, sell_lidx + e0, n * 2u, &bar);
+            }
+        }
+        for (int i = tid; i < C * 8; i += kBlobBlock) {
+            const int c = i >> 3, ch = i & 7;
+            const int col = __ldg(&tile_cols[c0 + c]);
+            cp_async16(xs + c * 16 + ch * 2, x + (int64_t)col * 16 + ch * 2);
+        }
+        cp_async_commit();
+        const int rin = warp * 16 + rl;
+        const int64_t row = t * kBlobTile + rin;
+        const bool valid = row < n_rows;
+        int width = 0, base = 0, ob = 0, oe = 0;
+        if (valid) {
+            const int64_t slice = row >> 3;
+            const int o = sell_off[slice];
+            width = sell_off[slice + 1] - o;
+            base = (o - tile_off) * 8 + (int)(row & 7);
+            if (OVERLAY) { ob = ov_ptr[row]; oe = ov_ptr[row + 1]; }
+        }
+        const int self = tile_self[t] + rin;
+        cp_async_wait_all();
+        mbar_wait(&bar, it & 1u);
+        __syncthreads();
+        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+        for (int k = 0; k < width; ++k) {
+            const double2 m = s_hq[base + k * 8];
+            const int li = s_lx[base + k * 8];
+            const double* xr = xs + li * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
+                if constexpr (CPX) {
+                    const double g = m.x - w2v[j][0] * m.y;
+                    acc[j][0] += g * v.x;
+                    acc[j][1] += g * v.y;
+                } else {
+                    acc[j][0] += (m.x - w2v[j][0] * m.y) * v.x;
+                    acc[j][1] += (m.x - w2v[j][1] * m.y) * v.y;
+                }
+            }
+        }
+        if constexpr (OVERLAY) {
+            for (int o = ob; o < oe; ++o) {
+                const int2 cg = ov_cg[o];
+                const double a = ov_val[o];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 cf = coef[cg.y * F + (choff[j] >> 1)];
+                    const double2 xv = *reinterpret_cast<const double2*>(x + (int64_t)cg.x * 16 + choff[j]);
+                    const double2 tt = cmul(make_double2(cf.x * a, cf.y * a), xv);
+                    acc[j][0] += tt.x;
+                    acc[j][1] += tt.y;
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = make_double2(acc[j][0], acc[j][1]);
+            if (DOT) {
+                const double* xo = xs + self * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(xo + choff[j]);
+                    if constexpr (CPX) {
+                        dot[j][0] += v.x * acc[j][0] - v.y * acc[j][1];
+                        dot[j][1] += v.x * acc[j][1] + v.y * acc[j][0];
+                    } else {
+                        dot[j][0] += v.x * acc[j][0];
+                        dot[j][1] += v.y * acc[j][1];
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with the staged tile before the next fill overwrites it
+    }
+    if (DOT) {
+        // per-thread sums -> per-frequency block sums in a fixed order (deterministic)
+        double* s_dot = xs;   // [kBlobBlock][8]; x_cap >= 128 rows = 16 KB
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_dot[tid * 8 + 2 * j] = dot[j][0]; s_dot[tid * 8 + 2 * j + 1] = dot[j][1]; }
+        __syncthreads();
+        if (tid < F) {
+            const int ch = CPX ? tid : (tid >> 1);
+            double s0 = 0.0, s1 = 0.0;
+            for (int th = (ch & 1); th < kBlobBlock; th += 2) {        // the lanes with h = ch % 2 hold this chunk ...
+                const int jj = ((ch >> 1) - ((th >> 1) & 3)) & 3;       // ... at step jj
+                if constexpr (CPX) {
+                    s0 += s_dot[th * 8 + 2 * jj];
+                    s1 += s_dot[th * 8 + 2 * jj + 1];
+                } else {
+                    s0 += s_dot[th * 8 + 2 * jj + (tid & 1)];
+                }
+            }
+            partial[((int64_t)blockIdx.x * F + tid) * 2 + 0] = s0;
+            partial[((int64_t)blockIdx.x * F + tid) * 2 + 1] = s1;
+        }
+        finalize_last_block<F, 2, kBlobBlock>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
+            sc->pq[ff] = make_double2(tot[0], tot[1]);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
 // finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
 // ------------------------------------------------------------------------------------------------
@@ -749,17 +921,30 @@ __global__ void k_gather_rcv(const T* __restrict__ x, const int32_t* __restrict_
     out[(int64_t)f * n_rcv + rc] = v_out(acc);
 }
 
-// pN export: stage[f][row] = x[row][f]
+// pN export: stage[f][node] = x[perm[node]][f]  (back to the caller's node numbering)
 template <typename T, int F>
-__global__ void __launch_bounds__(kBlock) k_export(const T* __restrict__ x, int64_t n_rows, double2* __restrict__ stage) {
+__global__ void __launch_bounds__(kBlock) k_export(const T* __restrict__ x, const int32_t* __restrict__ perm, int64_t n_rows,
+                                                    double2* __restrict__ stage) {
     __shared__ T tile[kBlock];
     constexpr int RPB = kBlock / F;
     const int64_t row0 = (int64_t)blockIdx.x * RPB;
-    const int64_t i = row0 * F + threadIdx.x;
-    if (i < n_rows * F) tile[threadIdx.x] = x[i];
+    const int rr = threadIdx.x / F, ff = threadIdx.x % F;
+    if (row0 + rr < n_rows) tile[threadIdx.x] = x[(int64_t)perm[row0 + rr] * F + ff];
     __syncthreads();
     const int f = threadIdx.x / RPB, rl = threadIdx.x % RPB;
     if (row0 + rl < n_rows) stage[(int64_t)f * n_rows + row0 + rl] = v_out(tile[rl * F + f]);
+}
+
+// stand-alone SpMV entry: caller's numbering <-> internal order, rows of F values
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_permute_rows(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ perm,
+                                                          int F, int64_t n_rows, bool forward) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_rows * F; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t row = i / F;
+        const int f = (int)(i % F);
+        const int64_t prow = perm[row];
+        if (forward) dst[prow * F + f] = src[i]; else dst[i] = src[prow * F + f];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -864,6 +1049,7 @@ struct Launch {
             constexpr int W4 = (32 / RPW < 16) ? (32 / RPW < 1 ? 1 : 32 / RPW) : 16;      // ... for a 4-slice tile
             switch (w->spmv_cfg) {
                 case 1: return spmv_tma<CPX, W8, 8, 2, 4>(sys, w, x, y, dot, overlay);
+                case 7: return spmv_tma<CPX, W16, 16, 2, 8>(sys, w, x, y, dot, overlay);   // the L1-gather pipeline where k_spmv_blob would run
                 case 2: return spmv_tma<CPX, W8, 8, 3, 8>(sys, w, x, y, dot, overlay);
                 case 3: return spmv_tma<CPX, W8, 8, 2, 8>(sys, w, x, y, dot, overlay);
                 default:
@@ -874,6 +1060,43 @@ struct Launch {
             }
         }
     }
+    // ---- shared-memory x tiles (k_spmv_blob): 128-byte vector rows only
+    template <bool CPX>
+    static bool spmv_blob(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
+        if constexpr ((CPX && F != 8) || (!CPX && F != 16)) {
+            return false;
+        } else {
+            if (sys->n_tiles == 0) return false;
+            const int x_cap = std::max(sys->max_tile_cols, 128);
+            const int se = sys->max_tile_entries;
+            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18;
+            if (smem > 112 * 1024) return false;   // two blocks per SM must fit: long rows (Tet10) use the L1 kernels
+            const int per_sm = (int)std::min<size_t>(3, (227 * 1024) / (smem + 1024));
+            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * per_sm);
+            auto launch = [&](auto kern) {
+                static thread_local std::map<std::pair<int, const void*>, size_t> granted;
+                size_t& have = granted[{sys->device, (const void*)kern}];
+                if (smem > have) {
+                    FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    have = smem;
+                }
+                kern<<<grid, kBlobBlock, smem, sys->stream>>>(sys->sell_off.p, sys->sell_lidx.p, sys->sell_hq.p, sys->tile_cptr.p,
+                                                             sys->tile_cols.p, sys->tile_self.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                                                             w->coef.p, (const double*)x, (double*)y, w->N, sys->n_slices, sys->n_tiles,
+                                                             x_cap, se, w->sc.p, (double*)w->partial.p);
+            };
+            if constexpr (CPX) {
+                if (dot) {
+                    if (overlay) launch(k_spmv_blob<true, true, true>); else launch(k_spmv_blob<true, true, false>);
+                } else {
+                    if (overlay) launch(k_spmv_blob<true, false, true>); else launch(k_spmv_blob<true, false, false>);
+                }
+            } else {
+                if (dot) launch(k_spmv_blob<false, true, false>); else launch(k_spmv_blob<false, false, false>);
+            }
+            return true;
+        }
+    }
     // can a real-arithmetic sweep run at this batch width on this mesh?
     static bool real_supported(fdb_system* sys, SweepWork* w) {
         if (F <= 32) return true;                                          // the plain kernel covers it
@@ -881,10 +1104,12 @@ struct Launch {
     }
     static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         if (w->real) {
+            if (w->spmv_cfg == 0 && spmv_blob<false>(sys, w, x, y, dot, false)) return;
             if (w->spmv_cfg < 8 && spmv_tma_cfg<false>(sys, w, x, y, dot, false)) return;
             spmv_ldg<double>(sys, w, (const double*)x, (double*)y, dot, false);
             return;
         }
+        if (w->spmv_cfg == 0 && spmv_blob<true>(sys, w, x, y, dot, overlay)) return;
         if (w->spmv_cfg < 8 && spmv_tma_cfg<true>(sys, w, x, y, dot, overlay)) return;
         spmv_ldg<double2>(sys, w, (const double2*)x, (double2*)y, dot, overlay);
     }
@@ -977,8 +1202,8 @@ struct Launch {
     }
     static void export_pn(fdb_system* sys, SweepWork* w) {
         const int rpb = kBlock / F;
-        if (w->real) k_export<double, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>((const double*)w->x.p, w->N, w->stage.p);
-        else k_export<double2, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>(w->x.p, w->N, w->stage.p);
+        if (w->real) k_export<double, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>((const double*)w->x.p, sys->perm.p, w->N, w->stage.p);
+        else k_export<double2, F><<<grid_for(w->N, rpb), kBlock, 0, sys->stream>>>(w->x.p, sys->perm.p, w->N, w->stage.p);
     }
     static void query_real(fdb_system* sys, SweepWork* w, bool* ok) { *ok = real_supported(sys, w); }
 };
@@ -1158,6 +1383,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         max_set = std::max(max_set, (int)(u_nodes.size() - base));
         for (size_t j = base; j < u_nodes.size(); ++j) set_norm2[st] += u_q[j].x * u_q[j].x + u_q[j].y * u_q[j].y;
     }
+    // the sweep's vectors live in the internal (blob) order: node lists are mapped once, here
+    const std::vector<int32_t>& perm = sys->perm_host;
+    FDB_REQUIRE(sys->have_order && (int64_t)perm.size() == N, "internal order missing");
+    for (auto& v : u_nodes) v = perm[v];
     const int n_src = max_set;            // launch width of the right-hand-side kernels
     const int64_t n_sys = n_sets * nf;    // systems = (source set, frequency) pairs, index set*nf + frequency
     // extra right-hand-side vectors (velocity boundary conditions): regrouped per node so one thread owns a node
@@ -1200,6 +1429,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             rn_val.push_back(evl[ent[i][1]]);
         }
         if (!ent.empty()) rn_ptr.push_back((int32_t)rn_vec.size());
+        for (auto& v : rn_nodes) v = perm[v];
     }
     const bool general_rhs = !rn_nodes.empty();
 
@@ -1240,7 +1470,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         FDB_REQUIRE(prm->rcv_nodes && prm->rcv_w, "receiver arrays missing");
         std::vector<int32_t> rn((size_t)n_rcv * 4);
         FDB_CUDA(cudaMemcpy(rn.data(), prm->rcv_nodes, rn.size() * sizeof(int32_t), cudaMemcpyDefault));
-        for (auto v : rn) FDB_REQUIRE(v >= 0 && v < N, "receiver node out of range");
+        for (auto& v : rn) {
+            FDB_REQUIRE(v >= 0 && v < N, "receiver node out of range");
+            v = perm[v];
+        }
         d_rcv_nodes.alloc(rn.size()); d_rcv_w.alloc(rn.size());
         FDB_CUDA(cudaMemcpyAsync(d_rcv_nodes.p, rn.data(), rn.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         FDB_CUDA(cudaMemcpyAsync(d_rcv_w.p, prm->rcv_w, rn.size() * sizeof(double), cudaMemcpyDefault, s));
@@ -1508,10 +1741,13 @@ void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, con
     w->real = false;
     load_batch_scalars(sys, w, F, om.data(), m.data());
     const size_t n = (size_t)w->N * F;
-    FDB_CUDA(cudaMemcpyAsync(w->p.p, x, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
+    const int pg = (int)std::min<int64_t>(grid_for((int64_t)n, kBlock), w->grid);
+    FDB_CUDA(cudaMemcpyAsync(w->tmp.p, x, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
+    k_permute_rows<double2><<<pg, kBlock, 0, sys->stream>>>(w->tmp.p, w->p.p, sys->perm.p, F, w->N, true);
     FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, false, has_overlay));
+    k_permute_rows<double2><<<pg, kBlock, 0, sys->stream>>>(w->q.p, w->tmp.p, sys->perm.p, F, w->N, false);
     FDB_CUDA(cudaGetLastError());
-    FDB_CUDA(cudaMemcpyAsync(y, w->q.p, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
+    FDB_CUDA(cudaMemcpyAsync(y, w->tmp.p, n * sizeof(double2), cudaMemcpyDefault, sys->stream));
     FDB_CUDA(cudaStreamSynchronize(sys->stream));
 }
 
