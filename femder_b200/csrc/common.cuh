@@ -119,9 +119,8 @@ struct fdb_system {
     // 128-row tiles of k_spmv_blob: sorted distinct columns per tile, 16-bit position of every entry's column in it
     int64_t n_tiles = 0;
     int max_tile_cols = 0, max_tile_entries = 0;
-    fdb::DevBuf<int32_t> tile_cptr;    // [n_tiles+1]
-    fdb::DevBuf<int32_t> tile_cols;    // [tile_cptr[n_tiles]] new-order column ids
-    fdb::DevBuf<int32_t> tile_self;    // [n_tiles] position of the tile's first own row in its column list
+    fdb::DevBuf<int4> tile_meta;       // [n_tiles] (list start, count | first own row's position << 16, SELL offset, SELL entries)
+    fdb::DevBuf<int32_t> tile_cols;    // column lists (new-order ids, ascending), each padded to a multiple of 4
     fdb::DevBuf<uint16_t> sell_lidx;   // [sell_entries]
 
     // surface

@@ -164,15 +164,25 @@ void build_order(fdb_system* sys) {
             tcols[t] = cols;
         }
     });
+    // column lists back to back, each padded to a multiple of 4 entries (16 bytes: the kernel fetches a list with one
+    // bulk copy); tile_meta[t] = (start of the list, count | position of the first own row << 16, first SELL slice
+    // offset, SELL entries of the tile)
     int max_cols = 0, max_ent = 8;
+    std::vector<int4> meta(n_tiles);
     for (int64_t t = 0; t < n_tiles; ++t) {
-        cptr[t + 1] = cptr[t] + (int32_t)tcols[t].size();
-        max_cols = std::max<int>(max_cols, (int)tcols[t].size());
+        const int c = (int)tcols[t].size();
+        FDB_REQUIRE(c < 65536 && t_entries[t] < (1 << 30), "tile too wide for the 16-bit column positions");
+        cptr[t + 1] = cptr[t] + ((c + 3) & ~3);
+        max_cols = std::max<int>(max_cols, c);
         max_ent = std::max(max_ent, t_entries[t]);
+        meta[t] = make_int4(cptr[t], c | (tself[t] << 16), off[t * (kTileRows / 8)], t_entries[t]);
     }
-    std::vector<int32_t> allcols(std::max<int64_t>(cptr[n_tiles], 1));
+    std::vector<int32_t> allcols(std::max<int64_t>(cptr[n_tiles], 4));
     parallel_for(n_tiles, [&](int64_t a, int64_t b, int) {
-        for (int64_t t = a; t < b; ++t) std::copy(tcols[t].begin(), tcols[t].end(), allcols.begin() + cptr[t]);
+        for (int64_t t = a; t < b; ++t) {
+            std::copy(tcols[t].begin(), tcols[t].end(), allcols.begin() + cptr[t]);
+            for (int32_t i = cptr[t] + (int32_t)tcols[t].size(); i < cptr[t + 1]; ++i) allcols[i] = tcols[t].back();
+        }
     });
 
     sys->n_slices = S;
@@ -186,17 +196,15 @@ void build_order(fdb_system* sys) {
     sys->sell_idx.alloc(sidx.size());
     sys->sell_src.alloc(ssrc.size());
     sys->sell_lidx.alloc(lidx.size());
-    sys->tile_cptr.alloc(n_tiles + 1);
+    sys->tile_meta.alloc(n_tiles);
     sys->tile_cols.alloc(allcols.size());
-    sys->tile_self.alloc(n_tiles);
-    FDB_CUDA(cudaMemcpyAsync(sys->tile_self.p, tself.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->perm.p, perm.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->iperm.p, order.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->sell_off.p, off.data(), (S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->sell_idx.p, sidx.data(), sidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->sell_src.p, ssrc.data(), ssrc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->sell_lidx.p, lidx.data(), lidx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-    FDB_CUDA(cudaMemcpyAsync(sys->tile_cptr.p, cptr.data(), (n_tiles + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    FDB_CUDA(cudaMemcpyAsync(sys->tile_meta.p, meta.data(), n_tiles * sizeof(int4), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->tile_cols.p, allcols.data(), allcols.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaStreamSynchronize(s));   // the host vectors die here
     sys->have_order = true;

@@ -537,21 +537,25 @@ constexpr int kBlobTile = 128;   // rows per tile (= kTileRows of reorder.cu)
 template <bool CPX, bool DOT, bool OVERLAY>
 __global__ void __launch_bounds__(kBlobBlock, 2)
 k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
-            const int32_t* __restrict__ tile_cptr, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_self,
+            const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols,
             const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
             const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
-            int64_t n_slices, int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
+            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
     constexpr int F = CPX ? 8 : 16;
     static_assert(!(OVERLAY && !CPX), "a boundary term makes the system complex");
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cols_cap = (x_cap + 3) & ~3;
     double* xs = reinterpret_cast<double*>(smem_raw);                                                              // [x_cap][16]
     double2* s_hq = reinterpret_cast<double2*>(smem_raw + (size_t)x_cap * 128);                                    // [stage_entries]
     uint16_t* s_lx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 16);    // [stage_entries]
-    __shared__ uint64_t bar;
+    int32_t* s_cols = reinterpret_cast<int32_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 18);    // [2][cols_cap]
+    __shared__ uint64_t bar, cbar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = lane & 1, rl = lane >> 1;
     if (tid == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -565,24 +569,41 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
         w2v[j][1] = sc->w2[CPX ? ch : 2 * ch + 1];
     }
     double dot[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    // Tile descriptors run two tiles ahead in registers and the column list one tile ahead in shared memory, so no
+    // fill starts with a chain of dependent global loads.
+    const int64_t G = gridDim.x;
+    int64_t t = blockIdx.x;
+    int4 m_cur = make_int4(0, 0, 0, 0), m_nxt = m_cur, m_nx2 = m_cur;
+    if (t < n_tiles) m_cur = tile_meta[t];
+    if (t + G < n_tiles) m_nxt = tile_meta[t + G];
+    if (tid == 0 && t < n_tiles) {
+        const uint32_t bytes = (uint32_t)(((m_cur.y & 0xffff) + 3) & ~3) * 4u;
+        mbar_expect_tx(&cbar[0], bytes);
+        bulk_g2s(s_cols, tile_cols + m_cur.x, bytes, &cbar[0]);
+    }
     uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int c0 = tile_cptr[t], C = tile_cptr[t + 1] - c0;
-        const int64_t sl0 = t * (kBlobTile / 8), sl1 = min(sl0 + kBlobTile / 8, n_slices);
-        const int tile_off = sell_off[sl0];
+    for (; t < n_tiles; t += G, ++it) {
+        const int C = m_cur.y & 0xffff, self0 = m_cur.y >> 16, tile_off = m_cur.z;
+        if (t + 2 * G < n_tiles) m_nx2 = tile_meta[t + 2 * G];
         if (tid == 0) {
             const int64_t e0 = (int64_t)tile_off * 8;
-            const uint32_t n = (uint32_t)(sell_off[sl1] - tile_off) * 8u;
+            const uint32_t n = (uint32_t)m_cur.w;
             mbar_expect_tx(&bar, n * 18u);
             if (n) {
                 bulk_g2s(s_hq, sell_hq + e0, n * 16u, &bar);
                 bulk_g2s(s_lx, sell_lidx + e0, n * 2u, &bar);
             }
+            if (t + G < n_tiles) {
+                const uint32_t bytes = (uint32_t)(((m_nxt.y & 0xffff) + 3) & ~3) * 4u;
+                mbar_expect_tx(&cbar[(it + 1) & 1], bytes);
+                bulk_g2s(s_cols + ((it + 1) & 1) * cols_cap, tile_cols + m_nxt.x, bytes, &cbar[(it + 1) & 1]);
+            }
         }
+        mbar_wait(&cbar[it & 1], (it >> 1) & 1u);
+        const int32_t* tc = s_cols + (it & 1) * cols_cap;
         for (int i = tid; i < C * 8; i += kBlobBlock) {
             const int c = i >> 3, ch = i & 7;
-            const int col = __ldg(&tile_cols[c0 + c]);
-            cp_async16(xs + c * 16 + ch * 2, x + (int64_t)col * 16 + ch * 2);
+            cp_async16(xs + c * 16 + ch * 2, x + (int64_t)tc[c] * 16 + ch * 2);
         }
         cp_async_commit();
         const int rin = warp * 16 + rl;
@@ -596,7 +617,7 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
             base = (o - tile_off) * 8 + (int)(row & 7);
             if (OVERLAY) { ob = ov_ptr[row]; oe = ov_ptr[row + 1]; }
         }
-        const int self = tile_self[t] + rin;
+        const int self = self0 + rin;
         cp_async_wait_all();
         mbar_wait(&bar, it & 1u);
         __syncthreads();
@@ -652,6 +673,8 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
             }
         }
         __syncthreads();   // everyone is done with the staged tile before the next fill overwrites it
+        m_cur = m_nxt;
+        m_nxt = m_nx2;
     }
     if (DOT) {
         // per-thread sums -> per-frequency block sums in a fixed order (deterministic)
@@ -1069,7 +1092,7 @@ struct Launch {
             if (sys->n_tiles == 0) return false;
             const int x_cap = std::max(sys->max_tile_cols, 128);
             const int se = sys->max_tile_entries;
-            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18;
+            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18 + (size_t)2 * ((x_cap + 3) & ~3) * 4;
             if (smem > 112 * 1024) return false;   // two blocks per SM must fit: long rows (Tet10) use the L1 kernels
             const int per_sm = (int)std::min<size_t>(3, (227 * 1024) / (smem + 1024));
             const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * per_sm);
@@ -1080,9 +1103,9 @@ struct Launch {
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     have = smem;
                 }
-                kern<<<grid, kBlobBlock, smem, sys->stream>>>(sys->sell_off.p, sys->sell_lidx.p, sys->sell_hq.p, sys->tile_cptr.p,
-                                                             sys->tile_cols.p, sys->tile_self.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
-                                                             w->coef.p, (const double*)x, (double*)y, w->N, sys->n_slices, sys->n_tiles,
+                kern<<<grid, kBlobBlock, smem, sys->stream>>>(sys->sell_off.p, sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
+                                                             sys->tile_cols.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                                                             w->coef.p, (const double*)x, (double*)y, w->N, sys->n_tiles,
                                                              x_cap, se, w->sc.p, (double*)w->partial.p);
             };
             if constexpr (CPX) {
