@@ -533,6 +533,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kBlobBlock = 256;
 constexpr int kBlobTile = 128;   // rows per tile (= kTileRows of reorder.cu)
+constexpr int kBlobTail = 20;    // ints behind a tile's column list (= kTileTail of reorder.cu): relative slice offsets
 
 template <bool CPX, bool DOT, bool OVERLAY>
 __global__ void __launch_bounds__(kBlobBlock, 2)
@@ -544,7 +545,7 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
     constexpr int F = CPX ? 8 : 16;
     static_assert(!(OVERLAY && !CPX), "a boundary term makes the system complex");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int cols_cap = (x_cap + 3) & ~3;
+    const int cols_cap = ((x_cap + 3) & ~3) + kBlobTail;
     double* xs = reinterpret_cast<double*>(smem_raw);                                                              // [x_cap][16]
     double2* s_hq = reinterpret_cast<double2*>(smem_raw + (size_t)x_cap * 128);                                    // [stage_entries]
     uint16_t* s_lx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 16);    // [stage_entries]
@@ -573,18 +574,19 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
     // fill starts with a chain of dependent global loads.
     const int64_t G = gridDim.x;
     int64_t t = blockIdx.x;
-    int4 m_cur = make_int4(0, 0, 0, 0), m_nxt = m_cur, m_nx2 = m_cur;
+    int4 m_cur = make_int4(0, 0, 0, 0), m_nxt = m_cur;
     if (t < n_tiles) m_cur = tile_meta[t];
     if (t + G < n_tiles) m_nxt = tile_meta[t + G];
     if (tid == 0 && t < n_tiles) {
-        const uint32_t bytes = (uint32_t)(((m_cur.y & 0xffff) + 3) & ~3) * 4u;
+        const uint32_t bytes = (uint32_t)((((m_cur.y & 0xffff) + 3) & ~3) + kBlobTail) * 4u;
         mbar_expect_tx(&cbar[0], bytes);
         bulk_g2s(s_cols, tile_cols + m_cur.x, bytes, &cbar[0]);
     }
     uint32_t it = 0;
     for (; t < n_tiles; t += G, ++it) {
         const int C = m_cur.y & 0xffff, self0 = m_cur.y >> 16, tile_off = m_cur.z;
-        if (t + 2 * G < n_tiles) m_nx2 = tile_meta[t + 2 * G];
+        int4 m_ld = make_int4(0, 0, 0, 0);
+        if (t + 2 * G < n_tiles) m_ld = tile_meta[t + 2 * G];   // consumed at the bottom of the loop, after the compute
         if (tid == 0) {
             const int64_t e0 = (int64_t)tile_off * 8;
             const uint32_t n = (uint32_t)m_cur.w;
@@ -594,7 +596,7 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
                 bulk_g2s(s_lx, sell_lidx + e0, n * 2u, &bar);
             }
             if (t + G < n_tiles) {
-                const uint32_t bytes = (uint32_t)(((m_nxt.y & 0xffff) + 3) & ~3) * 4u;
+                const uint32_t bytes = (uint32_t)((((m_nxt.y & 0xffff) + 3) & ~3) + kBlobTail) * 4u;
                 mbar_expect_tx(&cbar[(it + 1) & 1], bytes);
                 bulk_g2s(s_cols + ((it + 1) & 1) * cols_cap, tile_cols + m_nxt.x, bytes, &cbar[(it + 1) & 1]);
             }
@@ -611,10 +613,10 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
         const bool valid = row < n_rows;
         int width = 0, base = 0, ob = 0, oe = 0;
         if (valid) {
-            const int64_t slice = row >> 3;
-            const int o = sell_off[slice];
-            width = sell_off[slice + 1] - o;
-            base = (o - tile_off) * 8 + (int)(row & 7);
+            const int32_t* so = tc + ((C + 3) & ~3) + (rin >> 3);   // relative slice offsets came with the column list
+            const int o = so[0];
+            width = so[1] - o;
+            base = o * 8 + (rin & 7);
             if (OVERLAY) { ob = ov_ptr[row]; oe = ov_ptr[row + 1]; }
         }
         const int self = self0 + rin;
@@ -674,7 +676,9 @@ k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ s
         }
         __syncthreads();   // everyone is done with the staged tile before the next fill overwrites it
         m_cur = m_nxt;
-        m_nxt = m_nx2;
+        // keep the compiler from consuming (converting to uniform registers) the descriptor load before this point
+        asm volatile("" : "+r"(m_ld.x), "+r"(m_ld.y), "+r"(m_ld.z), "+r"(m_ld.w));
+        m_nxt = m_ld;
     }
     if (DOT) {
         // per-thread sums -> per-frequency block sums in a fixed order (deterministic)
@@ -1092,7 +1096,7 @@ struct Launch {
             if (sys->n_tiles == 0) return false;
             const int x_cap = std::max(sys->max_tile_cols, 128);
             const int se = sys->max_tile_entries;
-            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18 + (size_t)2 * ((x_cap + 3) & ~3) * 4;
+            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18 + (size_t)2 * (((x_cap + 3) & ~3) + kBlobTail) * 4;
             if (smem > 112 * 1024) return false;   // two blocks per SM must fit: long rows (Tet10) use the L1 kernels
             const int per_sm = (int)std::min<size_t>(3, (227 * 1024) / (smem + 1024));
             const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * per_sm);
