@@ -121,6 +121,7 @@ struct fdb_system {
     int max_tile_cols = 0, max_tile_entries = 0;
     fdb::DevBuf<int4> tile_meta;       // [n_tiles] (list start, count | first own row's position << 16, SELL offset, SELL entries)
     fdb::DevBuf<int32_t> tile_cols;    // column lists (new-order ids, ascending), each padded to a multiple of 4
+    fdb::DevBuf<int32_t> tile_hdr;     // [n_tiles][20] relative SELL slice offsets (17), first own row's position, column count
     fdb::DevBuf<uint16_t> sell_lidx;   // [sell_entries]
 
     // surface

@@ -16,7 +16,7 @@
 namespace fdb {
 
 constexpr int kTileRows = 128;
-constexpr int kTileTail = 20;   // ints appended to a tile's column list: 17 relative slice offsets, padded to 16 bytes
+constexpr int kTileHdr = 20;    // ints of a tile's header: 17 relative slice offsets, position of the first own row, column count
 
 // Breadth-first blobs: a blob starts at the oldest still-free node on the boundary of what is already ordered and
 // grows until the current tile is full; what its queue still holds becomes boundary for later blobs.
@@ -165,28 +165,32 @@ void build_order(fdb_system* sys) {
             tcols[t] = cols;
         }
     });
-    // column lists back to back, each padded to a multiple of 4 entries (16 bytes: the kernel fetches a list and the
-    // slice offsets behind it with one bulk copy); tile_meta[t] = (start of the list, count | position of the first own row << 16, first SELL slice
+    // column lists back to back, each padded to a multiple of 4 entries (16 bytes: the kernel fetches a list with one
+    // bulk copy); tile_meta[t] = (start of the list, count | position of the first own row << 16, first SELL slice
     // offset, SELL entries of the tile)
     int max_cols = 0, max_ent = 8;
     std::vector<int4> meta(n_tiles);
     for (int64_t t = 0; t < n_tiles; ++t) {
         const int c = (int)tcols[t].size();
         FDB_REQUIRE(c < 65536 && t_entries[t] < (1 << 30), "tile too wide for the 16-bit column positions");
-        cptr[t + 1] = cptr[t] + ((c + 3) & ~3) + kTileTail;
+        cptr[t + 1] = cptr[t] + ((c + 3) & ~3);
         max_cols = std::max<int>(max_cols, c);
         max_ent = std::max(max_ent, t_entries[t]);
         meta[t] = make_int4(cptr[t], c | (tself[t] << 16), off[t * (kTileRows / 8)], t_entries[t]);
     }
     std::vector<int32_t> allcols(std::max<int64_t>(cptr[n_tiles], 4));
+    std::vector<int32_t> hdr((size_t)n_tiles * kTileHdr);
     parallel_for(n_tiles, [&](int64_t a, int64_t b, int) {
         for (int64_t t = a; t < b; ++t) {
             std::copy(tcols[t].begin(), tcols[t].end(), allcols.begin() + cptr[t]);
-            const int32_t tail = cptr[t + 1] - kTileTail;
-            for (int32_t i = cptr[t] + (int32_t)tcols[t].size(); i < tail; ++i) allcols[i] = tcols[t].back();
-            // ... followed by the tile's 17 SELL slice offsets relative to its first slice
+            for (int32_t i = cptr[t] + (int32_t)tcols[t].size(); i < cptr[t + 1]; ++i) allcols[i] = tcols[t].back();
+            // header the consumer warps read: the tile's 17 SELL slice offsets relative to its first slice, ...
             const int64_t s0 = t * (kTileRows / 8);
-            for (int i = 0; i < kTileTail; ++i) allcols[tail + i] = off[std::min<int64_t>(S, s0 + i)] - off[s0];
+            int32_t* hd = hdr.data() + t * kTileHdr;
+            for (int i = 0; i <= kTileRows / 8; ++i) hd[i] = off[std::min<int64_t>(S, s0 + i)] - off[s0];
+            hd[17] = tself[t];
+            hd[18] = (int32_t)tcols[t].size();
+            hd[19] = 0;
         }
     });
 
@@ -202,6 +206,8 @@ void build_order(fdb_system* sys) {
     sys->sell_src.alloc(ssrc.size());
     sys->sell_lidx.alloc(lidx.size());
     sys->tile_meta.alloc(n_tiles);
+    sys->tile_hdr.alloc(hdr.size());
+    FDB_CUDA(cudaMemcpyAsync(sys->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     sys->tile_cols.alloc(allcols.size());
     FDB_CUDA(cudaMemcpyAsync(sys->perm.p, perm.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     FDB_CUDA(cudaMemcpyAsync(sys->iperm.p, order.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, s));

@@ -65,6 +65,7 @@ struct SweepWork {
     int spmv_cfg = 0;             // FDB_SPMV_CFG (tuning aid): 0 default, 1..3 other bulk-copy pipeline shapes, >= 8 plain kernel only
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
+    int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
     bool graph_real = false;
 };
@@ -516,192 +517,231 @@ k_spmv_tma(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sel
 // row that pipe, not HBM, bounded k_spmv_tma.  Shared memory returns 128 bytes per cycle, and
 // in the sweep's blob order (reorder.cu) a tile's distinct columns are only ~2.5 x its 128 rows, so staging costs a
 // fraction of the gathers it replaces.
-//   fill     thread 0 streams the tile's (H, Q) values and 16-bit local column positions with two bulk copies
-//            (cp.async.bulk -> mbarrier); all threads copy the tile's x rows with 16-byte cp.async (L2 -> smem, no
-//            registers, no L1 allocation)
-//   compute  2 lanes per row, 16 rows per warp.  A row of x is 8 chunks of 16 bytes; lane h of row r reads chunks
-//            h + 2*((r + j) % 4), j = 0..3, so the 8 lanes of every quarter-warp phase hit 8 different bank groups:
-//            conflict-free 128-bit loads whatever the column positions are.
-// Blocks take tiles round-robin, so the tiles in flight are neighbours in the blob order and share their halo rows
-// in L2.  Two blocks per SM overlap one block's fill with the other's compute.
+//   One persistent block per SM, tiles dealt round-robin (the tiles in flight are neighbours in the blob order and
+//   share their halo rows in L2).  Two stage buffers; producer warps fill one while consumer warps work on the other.
+//   producers  thread 0 streams the tile's (H, Q) values, 16-bit local column positions and 80-byte header with bulk
+//              copies (cp.async.bulk, complete_tx on the stage's `full` mbarrier); all producer threads copy the tile's
+//              x rows with 16-byte cp.async (L2 -> smem, no registers, no L1 allocation) and hand their completion to
+//              the same mbarrier (cp.async.mbarrier.arrive.noinc).  The column list arrives two tiles ahead by its
+//              own bulk copy, the 16-byte tile descriptor two tiles ahead in registers: no fill starts with a chain
+//              of dependent global loads.
+//   consumers  LPR lanes per row.  A row of x is 8 chunks of 16 bytes; lane q of row r reads chunks
+//              q + LPR*((r + j) % (8/LPR)), so the 8 lanes of every quarter-warp phase hit 8 different bank groups:
+//              conflict-free 128-bit loads whatever the column positions are.  Warps never synchronise with each
+//              other: a warp waits for `full`, does its rows, arrives on `empty`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int4 ld_meta(const int4* p) {
+    // through inline asm so the compiler treats the descriptor as per-thread data: a plain uniform load is converted to
+    // uniform registers right behind the load, which stalls every tile for a global-memory round trip
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
-constexpr int kBlobBlock = 256;
-constexpr int kBlobTile = 128;   // rows per tile (= kTileRows of reorder.cu)
-constexpr int kBlobTail = 20;    // ints behind a tile's column list (= kTileTail of reorder.cu): relative slice offsets
+constexpr int kBlobTile = 128;      // rows per tile (= kTileRows of reorder.cu)
+constexpr int kBlobHdr = 20;        // ints of a tile header (= kTileHdr of reorder.cu)
+constexpr int kBlobProducers = 4;   // producer warps
 
-template <bool CPX, bool DOT, bool OVERLAY>
-__global__ void __launch_bounds__(kBlobBlock, 2)
-k_spmv_blob(const int32_t* __restrict__ sell_off, const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
-            const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols,
+template <bool CPX, bool DOT, bool OVERLAY, int LPR>
+__global__ void __launch_bounds__(kBlobTile * LPR + kBlobProducers * 32, 1)
+k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
+            const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_hdr,
             const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
             const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
             int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
     constexpr int F = CPX ? 8 : 16;
+    constexpr int NCONS = kBlobTile * LPR;            // consumer threads
+    constexpr int NPROD = kBlobProducers * 32;        // producer threads
+    constexpr int BLOCK = NCONS + NPROD;
+    constexpr int NCH = 8 / LPR;      // 16-byte chunks of a row per lane
+    constexpr int RPW = 32 / LPR;     // rows per warp
     static_assert(!(OVERLAY && !CPX), "a boundary term makes the system complex");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int cols_cap = ((x_cap + 3) & ~3) + kBlobTail;
-    double* xs = reinterpret_cast<double*>(smem_raw);                                                              // [x_cap][16]
-    double2* s_hq = reinterpret_cast<double2*>(smem_raw + (size_t)x_cap * 128);                                    // [stage_entries]
-    uint16_t* s_lx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 16);    // [stage_entries]
-    int32_t* s_cols = reinterpret_cast<int32_t*>(smem_raw + (size_t)x_cap * 128 + (size_t)stage_entries * 18);    // [2][cols_cap]
-    __shared__ uint64_t bar, cbar[2];
+    const int cols_cap = (x_cap + 3) & ~3;
+    const size_t x_bytes = (size_t)x_cap * 128, hq_bytes = (size_t)stage_entries * 16, lx_bytes = (size_t)stage_entries * 2;
+    double* xs = reinterpret_cast<double*>(smem_raw);                                               // [2][x_cap][16]
+    double2* s_hq = reinterpret_cast<double2*>(smem_raw + 2 * x_bytes);                             // [2][stage_entries]
+    uint16_t* s_lx = reinterpret_cast<uint16_t*>(smem_raw + 2 * x_bytes + 2 * hq_bytes);            // [2][stage_entries]
+    int32_t* s_hdr = reinterpret_cast<int32_t*>(smem_raw + 2 * x_bytes + 2 * hq_bytes + 2 * lx_bytes);   // [2][kBlobHdr]
+    int32_t* s_cols = s_hdr + 2 * kBlobHdr;                                                          // [2][cols_cap]
+    __shared__ uint64_t full[2], empty[2], cbar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h = lane & 1, rl = lane >> 1;
     if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_init(&cbar[0], 1);
-        mbar_init(&cbar[1], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], NPROD + 1);       // every producer thread's cp.async completion + thread 0's expect_tx
+            mbar_init(&empty[i], NCONS / 32);     // one arrival per consumer warp
+            mbar_init(&cbar[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    int choff[4];        // offset (in doubles) of the chunk this lane reads at step j
-    double w2v[4][2];    // omega^2 of the frequencies in that chunk
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = h + 2 * ((rl + j) & 3);
-        choff[j] = 2 * ch;
-        w2v[j][0] = sc->w2[CPX ? ch : 2 * ch];
-        w2v[j][1] = sc->w2[CPX ? ch : 2 * ch + 1];
-    }
-    double dot[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-    // Tile descriptors run two tiles ahead in registers and the column list one tile ahead in shared memory, so no
-    // fill starts with a chain of dependent global loads.
     const int64_t G = gridDim.x;
-    int64_t t = blockIdx.x;
-    int4 m_cur = make_int4(0, 0, 0, 0), m_nxt = m_cur;
-    if (t < n_tiles) m_cur = tile_meta[t];
-    if (t + G < n_tiles) m_nxt = tile_meta[t + G];
-    if (tid == 0 && t < n_tiles) {
-        const uint32_t bytes = (uint32_t)((((m_cur.y & 0xffff) + 3) & ~3) + kBlobTail) * 4u;
-        mbar_expect_tx(&cbar[0], bytes);
-        bulk_g2s(s_cols, tile_cols + m_cur.x, bytes, &cbar[0]);
-    }
-    uint32_t it = 0;
-    for (; t < n_tiles; t += G, ++it) {
-        const int C = m_cur.y & 0xffff, self0 = m_cur.y >> 16, tile_off = m_cur.z;
-        int4 m_ld = make_int4(0, 0, 0, 0);
-        if (t + 2 * G < n_tiles) m_ld = tile_meta[t + 2 * G];   // consumed at the bottom of the loop, after the compute
-        if (tid == 0) {
-            const int64_t e0 = (int64_t)tile_off * 8;
-            const uint32_t n = (uint32_t)m_cur.w;
-            mbar_expect_tx(&bar, n * 18u);
-            if (n) {
-                bulk_g2s(s_hq, sell_hq + e0, n * 16u, &bar);
-                bulk_g2s(s_lx, sell_lidx + e0, n * 2u, &bar);
+    double dot[NCH][2];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) dot[j][0] = dot[j][1] = 0.0;
+
+    if (tid >= NCONS) {
+        // ===================== producers =====================
+        const int ptid = tid - NCONS;
+        auto list_bytes = [](const int4& m) { return (uint32_t)(((m.y & 0xffff) + 3) & ~3) * 4u; };
+        auto copy_cols = [&](const int4& m, int slot) {      // producer thread 0
+            mbar_expect_tx(&cbar[slot], list_bytes(m));
+            bulk_g2s(s_cols + slot * cols_cap, tile_cols + m.x, list_bytes(m), &cbar[slot]);
+        };
+        const int4 zero4 = make_int4(0, 0, 0, 0);
+        int64_t t = blockIdx.x;
+        int4 m_cur = zero4, m_nxt = zero4, m_nx2 = zero4;
+        if (t < n_tiles) m_cur = ld_meta(tile_meta + t);
+        if (t + G < n_tiles) m_nxt = ld_meta(tile_meta + t + G);
+        if (ptid == 0) {
+            if (t < n_tiles) copy_cols(m_cur, 0);
+            if (t + G < n_tiles) copy_cols(m_nxt, 1);
+        }
+        for (uint32_t it = 0; t < n_tiles; t += G, ++it) {
+            const int buf = it & 1;
+            if (t + 2 * G < n_tiles) m_nx2 = ld_meta(tile_meta + t + 2 * G);
+            mbar_wait(&empty[buf], ((it >> 1) & 1u) ^ 1u);    // the consumers released this stage (passes at once for it < 2)
+            if (ptid == 0) {
+                const int64_t e0 = (int64_t)m_cur.z * 8;
+                const uint32_t n = (uint32_t)m_cur.w;
+                mbar_expect_tx(&full[buf], n * 18u + kBlobHdr * 4u);
+                bulk_g2s(s_hdr + buf * kBlobHdr, tile_hdr + t * kBlobHdr, kBlobHdr * 4u, &full[buf]);
+                if (n) {
+                    bulk_g2s(s_hq + (size_t)buf * stage_entries, sell_hq + e0, n * 16u, &full[buf]);
+                    bulk_g2s(s_lx + (size_t)buf * stage_entries, sell_lidx + e0, n * 2u, &full[buf]);
+                }
             }
-            if (t + G < n_tiles) {
-                const uint32_t bytes = (uint32_t)((((m_nxt.y & 0xffff) + 3) & ~3) + kBlobTail) * 4u;
-                mbar_expect_tx(&cbar[(it + 1) & 1], bytes);
-                bulk_g2s(s_cols + ((it + 1) & 1) * cols_cap, tile_cols + m_nxt.x, bytes, &cbar[(it + 1) & 1]);
+            mbar_wait(&cbar[buf], (it >> 1) & 1u);            // this tile's column list
+            const int C = m_cur.y & 0xffff;
+            const int32_t* tc = s_cols + buf * cols_cap;
+            double* dst = xs + (size_t)buf * x_cap * 16;
+            for (int i = ptid; i < C * 8; i += NPROD) {
+                const int c = i >> 3, ch = i & 7;
+                cp_async16(dst + c * 16 + ch * 2, x + (int64_t)tc[c] * 16 + ch * 2);
             }
+            cp_async_arrive_noinc(&full[buf]);
+            // all producers are done reading the column list: its slot takes the list of the tile after next
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+            if (ptid == 0 && t + 2 * G < n_tiles) copy_cols(m_nx2, buf);
+            m_cur = m_nxt;
+            m_nxt = m_nx2;
         }
-        mbar_wait(&cbar[it & 1], (it >> 1) & 1u);
-        const int32_t* tc = s_cols + (it & 1) * cols_cap;
-        for (int i = tid; i < C * 8; i += kBlobBlock) {
-            const int c = i >> 3, ch = i & 7;
-            cp_async16(xs + c * 16 + ch * 2, x + (int64_t)tc[c] * 16 + ch * 2);
+    } else {
+        // ===================== consumers =====================
+        const int q = lane % LPR, rl = lane / LPR;
+        int choff[NCH];        // offset (in doubles) of the chunk this lane reads at step j
+        double w2v[NCH][2];    // omega^2 of the frequencies in that chunk
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int ch = q + LPR * ((rl + j) % NCH);
+            choff[j] = 2 * ch;
+            w2v[j][0] = sc->w2[CPX ? ch : 2 * ch];
+            w2v[j][1] = sc->w2[CPX ? ch : 2 * ch + 1];
         }
-        cp_async_commit();
-        const int rin = warp * 16 + rl;
-        const int64_t row = t * kBlobTile + rin;
-        const bool valid = row < n_rows;
-        int width = 0, base = 0, ob = 0, oe = 0;
-        if (valid) {
-            const int32_t* so = tc + ((C + 3) & ~3) + (rin >> 3);   // relative slice offsets came with the column list
-            const int o = so[0];
-            width = so[1] - o;
-            base = o * 8 + (rin & 7);
-            if (OVERLAY) { ob = ov_ptr[row]; oe = ov_ptr[row + 1]; }
-        }
-        const int self = self0 + rin;
-        cp_async_wait_all();
-        mbar_wait(&bar, it & 1u);
-        __syncthreads();
-        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        const int rin = warp * RPW + rl;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++it) {
+            const int buf = it & 1;
+            const int64_t row = t * kBlobTile + rin;
+            const bool valid = row < n_rows;
+            int ob = 0, oe = 0;
+            if (OVERLAY && valid) { ob = ov_ptr[row]; oe = ov_ptr[row + 1]; }
+            mbar_wait(&full[buf], (it >> 1) & 1u);
+            const int32_t* hd = s_hdr + buf * kBlobHdr;
+            const int o = hd[rin >> 3];
+            const int width = valid ? hd[(rin >> 3) + 1] - o : 0;
+            const int self0 = hd[17];
+            const double2* thq = s_hq + (size_t)buf * stage_entries + o * 8 + (rin & 7);
+            const uint16_t* tlx = s_lx + (size_t)buf * stage_entries + o * 8 + (rin & 7);
+            const double* xb = xs + (size_t)buf * x_cap * 16;
+            double acc[NCH][2];
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) acc[j][0] = acc[j][1] = 0.0;
 #pragma unroll 4
-        for (int k = 0; k < width; ++k) {
-            const double2 m = s_hq[base + k * 8];
-            const int li = s_lx[base + k * 8];
-            const double* xr = xs + li * 16;
+            for (int k = 0; k < width; ++k) {
+                const double2 m = thq[k * 8];
+                const int li = tlx[k * 8];
+                const double* xr = xb + li * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
-                if constexpr (CPX) {
-                    const double g = m.x - w2v[j][0] * m.y;
-                    acc[j][0] += g * v.x;
-                    acc[j][1] += g * v.y;
-                } else {
-                    acc[j][0] += (m.x - w2v[j][0] * m.y) * v.x;
-                    acc[j][1] += (m.x - w2v[j][1] * m.y) * v.y;
-                }
-            }
-        }
-        if constexpr (OVERLAY) {
-            for (int o = ob; o < oe; ++o) {
-                const int2 cg = ov_cg[o];
-                const double a = ov_val[o];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 cf = coef[cg.y * F + (choff[j] >> 1)];
-                    const double2 xv = *reinterpret_cast<const double2*>(x + (int64_t)cg.x * 16 + choff[j]);
-                    const double2 tt = cmul(make_double2(cf.x * a, cf.y * a), xv);
-                    acc[j][0] += tt.x;
-                    acc[j][1] += tt.y;
-                }
-            }
-        }
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = make_double2(acc[j][0], acc[j][1]);
-            if (DOT) {
-                const double* xo = xs + self * 16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 v = *reinterpret_cast<const double2*>(xo + choff[j]);
+                for (int j = 0; j < NCH; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
                     if constexpr (CPX) {
-                        dot[j][0] += v.x * acc[j][0] - v.y * acc[j][1];
-                        dot[j][1] += v.x * acc[j][1] + v.y * acc[j][0];
+                        const double g = m.x - w2v[j][0] * m.y;
+                        acc[j][0] += g * v.x;
+                        acc[j][1] += g * v.y;
                     } else {
-                        dot[j][0] += v.x * acc[j][0];
-                        dot[j][1] += v.y * acc[j][1];
+                        acc[j][0] += (m.x - w2v[j][0] * m.y) * v.x;
+                        acc[j][1] += (m.x - w2v[j][1] * m.y) * v.y;
                     }
                 }
             }
+            if constexpr (OVERLAY) {
+                for (int oo = ob; oo < oe; ++oo) {
+                    const int2 cg = ov_cg[oo];
+                    const double a = ov_val[oo];
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const double2 cf = coef[cg.y * F + (choff[j] >> 1)];
+                        const double2 xv = *reinterpret_cast<const double2*>(x + (int64_t)cg.x * 16 + choff[j]);
+                        const double2 tt = cmul(make_double2(cf.x * a, cf.y * a), xv);
+                        acc[j][0] += tt.x;
+                        acc[j][1] += tt.y;
+                    }
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = make_double2(acc[j][0], acc[j][1]);
+                if (DOT) {
+                    const double* xo = xb + (self0 + rin) * 16;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(xo + choff[j]);
+                        if constexpr (CPX) {
+                            dot[j][0] += v.x * acc[j][0] - v.y * acc[j][1];
+                            dot[j][1] += v.x * acc[j][1] + v.y * acc[j][0];
+                        } else {
+                            dot[j][0] += v.x * acc[j][0];
+                            dot[j][1] += v.y * acc[j][1];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[buf]);   // this warp is done with the stage
         }
-        __syncthreads();   // everyone is done with the staged tile before the next fill overwrites it
-        m_cur = m_nxt;
-        // keep the compiler from consuming (converting to uniform registers) the descriptor load before this point
-        asm volatile("" : "+r"(m_ld.x), "+r"(m_ld.y), "+r"(m_ld.z), "+r"(m_ld.w));
-        m_nxt = m_ld;
     }
     if (DOT) {
         // per-thread sums -> per-frequency block sums in a fixed order (deterministic)
-        double* s_dot = xs;   // [kBlobBlock][8]; x_cap >= 128 rows = 16 KB
+        __syncthreads();
+        double* s_dot = xs;   // [NCONS][2 * NCH] = 16 KB <= one x buffer (x_cap >= 128 rows)
+        if (tid < NCONS) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s_dot[tid * 8 + 2 * j] = dot[j][0]; s_dot[tid * 8 + 2 * j + 1] = dot[j][1]; }
+            for (int j = 0; j < NCH; ++j) { s_dot[tid * 2 * NCH + 2 * j] = dot[j][0]; s_dot[tid * 2 * NCH + 2 * j + 1] = dot[j][1]; }
+        }
         __syncthreads();
         if (tid < F) {
             const int ch = CPX ? tid : (tid >> 1);
             double s0 = 0.0, s1 = 0.0;
-            for (int th = (ch & 1); th < kBlobBlock; th += 2) {        // the lanes with h = ch % 2 hold this chunk ...
-                const int jj = ((ch >> 1) - ((th >> 1) & 3)) & 3;       // ... at step jj
+            for (int th = ch % LPR; th < NCONS; th += LPR) {                      // the lanes with q = ch % LPR hold this chunk ...
+                const int jj = ((ch / LPR) - (th / LPR) % NCH + NCH) % NCH;       // ... at step jj
                 if constexpr (CPX) {
-                    s0 += s_dot[th * 8 + 2 * jj];
-                    s1 += s_dot[th * 8 + 2 * jj + 1];
+                    s0 += s_dot[th * 2 * NCH + 2 * jj];
+                    s1 += s_dot[th * 2 * NCH + 2 * jj + 1];
                 } else {
-                    s0 += s_dot[th * 8 + 2 * jj + (tid & 1)];
+                    s0 += s_dot[th * 2 * NCH + 2 * jj + (tid & 1)];
                 }
             }
             partial[((int64_t)blockIdx.x * F + tid) * 2 + 0] = s0;
             partial[((int64_t)blockIdx.x * F + tid) * 2 + 1] = s1;
         }
-        finalize_last_block<F, 2, kBlobBlock>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
+        finalize_last_block<F, 2, BLOCK>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
             sc->pq[ff] = make_double2(tot[0], tot[1]);
         });
     }
@@ -1096,31 +1136,34 @@ struct Launch {
             if (sys->n_tiles == 0) return false;
             const int x_cap = std::max(sys->max_tile_cols, 128);
             const int se = sys->max_tile_entries;
-            const size_t smem = (size_t)x_cap * 128 + (size_t)se * 18 + (size_t)2 * (((x_cap + 3) & ~3) + kBlobTail) * 4;
-            if (smem > 112 * 1024) return false;   // two blocks per SM must fit: long rows (Tet10) use the L1 kernels
-            const int per_sm = (int)std::min<size_t>(3, (227 * 1024) / (smem + 1024));
-            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * per_sm);
-            auto launch = [&](auto kern) {
+            const size_t smem = (size_t)2 * x_cap * 128 + (size_t)2 * se * 18 + (size_t)2 * (((x_cap + 3) & ~3) + kBlobHdr) * 4;
+            if (smem > 220 * 1024) return false;   // long rows (Tet10) or a mesh without locality: the L1 kernels
+            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms);
+            auto launch = [&](auto kern, int lpr) {
                 static thread_local std::map<std::pair<int, const void*>, size_t> granted;
                 size_t& have = granted[{sys->device, (const void*)kern}];
                 if (smem > have) {
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     have = smem;
                 }
-                kern<<<grid, kBlobBlock, smem, sys->stream>>>(sys->sell_off.p, sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
-                                                             sys->tile_cols.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                kern<<<grid, kBlobTile * lpr + kBlobProducers * 32, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
+                                                             sys->tile_cols.p, sys->tile_hdr.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
                                                              w->coef.p, (const double*)x, (double*)y, w->N, sys->n_tiles,
                                                              x_cap, se, w->sc.p, (double*)w->partial.p);
             };
-            if constexpr (CPX) {
-                if (dot) {
-                    if (overlay) launch(k_spmv_blob<true, true, true>); else launch(k_spmv_blob<true, true, false>);
+            auto pick = [&](auto lpr) {
+                constexpr int L = decltype(lpr)::value;
+                if constexpr (CPX) {
+                    if (dot) {
+                        if (overlay) launch(k_spmv_blob<true, true, true, L>, L); else launch(k_spmv_blob<true, true, false, L>, L);
+                    } else {
+                        if (overlay) launch(k_spmv_blob<true, false, true, L>, L); else launch(k_spmv_blob<true, false, false, L>, L);
+                    }
                 } else {
-                    if (overlay) launch(k_spmv_blob<true, false, true>); else launch(k_spmv_blob<true, false, false>);
+                    if (dot) launch(k_spmv_blob<false, true, false, L>, L); else launch(k_spmv_blob<false, false, false, L>, L);
                 }
-            } else {
-                if (dot) launch(k_spmv_blob<false, true, false>); else launch(k_spmv_blob<false, false, false>);
-            }
+            };
+            if (w->blob_lpr == 4) pick(std::integral_constant<int, 4>{}); else pick(std::integral_constant<int, 2>{});
             return true;
         }
     }
@@ -1271,6 +1314,7 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         w->grid = sys->num_sms * 8;
         if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
+        if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
