@@ -283,7 +283,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_spmv_tma (fused multi-frequency SpMV, batch %d, %s arithmetic)" % (F, "real" if real else "complex"), "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "k_spmv_blob (fused multi-frequency SpMV, shared-memory x tiles, batch %d, %s arithmetic)" % (F, "real" if real else "complex"), "bound": "hbm", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                 "algorithmic_bytes_per_launch": int(nbytes), "us_per_launch": spmv_ms * 1e3, "peak_source": peak_src,
                 "how": f"{reps} back-to-back launches on resident vectors (matrix+vectors 0.56 GB > L2), torch CUDA events on the launching stream"}

@@ -28,6 +28,7 @@ struct __align__(16) Scalars {
     double2 rho[kMaxF];    // r^T z (unconjugated)
     double2 pq[kMaxF];     // p^T G p
     double2 beta[kMaxF];
+    double2 alpha[kMaxF];  // step length of the iteration whose x update is still pending (applied by k_pupdate)
     double rr[kMaxF];      // ||r||^2
     double bb[kMaxF];      // ||b||^2
     double w2[kMaxF];      // omega^2
@@ -36,6 +37,7 @@ struct __align__(16) Scalars {
     int active[kMaxF];
     int iters[kMaxF];
     int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
+    int xpend[kMaxF];      // the slot took a step in the last k_update: k_pupdate owes it x += alpha p
     int src_set[kMaxF];    // which source set (right-hand side) the slot solves: multi-RHS sweeps share G(w)
     int bb_from_r0;        // ||b||^2 is taken from the start residual (general right-hand sides, zero starting guess)
     double tol2;
@@ -748,8 +750,10 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
-// finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
+// K6a: alpha = rho / pq ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
+// finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count, alpha kept for K6b
+// The x update of the step is DEFERRED to K6b, which streams p anyway: x += alpha p there costs a read and a write
+// of x, here it would cost those plus a read of p (one vector pass less per iteration, same arithmetic).
 // ------------------------------------------------------------------------------------------------
 // Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the sweep): the diagonal is rebuilt from
 // (H_rr, Q_rr) - 16 bytes per ROW instead of 16 bytes per (row, frequency); otherwise the precomputed 1/diag is read.
@@ -767,7 +771,7 @@ __device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, cons
 }
 
 template <typename T, int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
+__global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
                                                     const T* __restrict__ q, const double2* __restrict__ dinv,
                                                     const double2* __restrict__ diag_hq, int64_t n_elems,
                                                     Scalars* __restrict__ sc, double* __restrict__ partial) {
@@ -783,7 +787,6 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restr
     if (act) {
         for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
             const T rv = v_sub(r[i], s_mul(alpha, q[i]));
-            x[i] = v_add(x[i], s_mul(alpha, p[i]));
             r[i] = rv;
             const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, rv);
             const double2 rz = v_dot(rv, z);
@@ -796,6 +799,9 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restr
         if (sc->active[ff]) {
             const double2 rho_old = sc->rho[ff];
             const double2 rho_new = make_double2(tot[0], tot[1]);
+            const double2 pq = sc->pq[ff];
+            sc->alpha[ff] = (pq.x != 0.0 || pq.y != 0.0) ? cdiv(rho_old, pq) : make_double2(0.0, 0.0);   // what every block used above
+            sc->xpend[ff] = 1;
             double2 beta = make_double2(0.0, 0.0);
             if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
             sc->rho[ff] = rho_new;
@@ -806,22 +812,28 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restr
             sc->beta[ff] = beta;
         } else {
             sc->beta[ff] = make_double2(0.0, 0.0);
+            sc->xpend[ff] = 0;
         }
     });
 }
 
-// K6b: p = z + beta p
+// K6b: x += alpha p (the step K6a took) ; p = z + beta p
 template <typename T, int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ p, const T* __restrict__ r,
+__global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r,
                                                      const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
                                                      int64_t n_elems, const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
-    const double2 beta = sc->beta[f];
+    if (!sc->xpend[f]) return;   // frozen frequency: nothing pending, p is not used while alpha = 0
+    const bool act = sc->active[f] != 0;   // false: the slot converged in this iteration, only its last step is owed
+    const double2 alpha = sc->alpha[f], beta = sc->beta[f];
     const double w2 = sc->w2[f];
-    if (!sc->active[f]) return;  // frozen frequency: p is not used while alpha = 0
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
-        p[i] = v_add(z, s_mul(beta, p[i]));
+        const T pv = p[i];
+        x[i] = v_add(x[i], s_mul(alpha, pv));
+        if (act) {
+            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
+            p[i] = v_add(z, s_mul(beta, pv));
+        }
     }
 }
 
@@ -1194,12 +1206,12 @@ struct Launch {
         spmv(sys, w, p, q, true, overlay);
         if (overlay) {
             if constexpr (std::is_same<T, double2>::value) {
-                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
             }
         } else {
-            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
         }
     }
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {

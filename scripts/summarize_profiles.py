@@ -87,6 +87,6 @@ v = capture("spmv_real16", "fused multi-frequency SpMV, batch 16, real arithmeti
 capture("spmv_cpx8", "fused multi-frequency SpMV, batch 8, complex arithmetic (admittance sweeps)")
 if v:
     tr = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
-    json.dump({"kernel": "k_spmv_tma<16, real>", "dram_bytes_per_launch": tr, "source": f"profiles/{R}_spmv_real16.md"},
+    json.dump({"kernel": "k_spmv_blob<real, F=16>", "dram_bytes_per_launch": tr, "source": f"profiles/{R}_spmv_real16.md"},
               open(os.path.join(OUT, "spmv_traffic.json"), "w"))
 print(os.listdir(OUT))
