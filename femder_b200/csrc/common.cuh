@@ -118,6 +118,7 @@ struct fdb_system {
     fdb::DevBuf<int32_t> sell_src;     // [sell_entries] CSR position behind each SELL entry, -1 = padding
     // 128-row tiles of k_spmv_blob: sorted distinct columns per tile, 16-bit position of every entry's column in it
     int64_t n_tiles = 0;
+    int tile_rows = 128;               // rows per tile (128, or 64 with two resident blocks per SM)
     int max_tile_cols = 0, max_tile_entries = 0;
     fdb::DevBuf<int4> tile_meta;       // [n_tiles] (list start, count | first own row's position << 16, SELL offset, SELL entries)
     fdb::DevBuf<int32_t> tile_cols;    // column lists (new-order ids, ascending), each padded to a multiple of 4

@@ -15,12 +15,12 @@
 
 namespace fdb {
 
-constexpr int kTileRows = 128;
+constexpr int kMaxTileRows = 128;   // rows per tile: 128, or 64 (two resident blocks per SM); fdb_system::tile_rows
 constexpr int kTileHdr = 20;    // ints of a tile's header: 17 relative slice offsets, position of the first own row, column count
 
 // Breadth-first blobs: a blob starts at the oldest still-free node on the boundary of what is already ordered and
 // grows until the current tile is full; what its queue still holds becomes boundary for later blobs.
-static void blob_order(int64_t n, const int32_t* indptr, const int32_t* indices, std::vector<int32_t>& order /* new -> old */) {
+static void blob_order(int64_t n, const int32_t* indptr, const int32_t* indices, int kTileRows, std::vector<int32_t>& order /* new -> old */) {
     order.resize(n);
     std::vector<int32_t> mark(n, -1);
     std::vector<uint8_t> done(n, 0);
@@ -30,7 +30,7 @@ static void blob_order(int64_t n, const int32_t* indptr, const int32_t* indices,
     int64_t next_seed = 0, cnt = 0;
     int32_t blob = 0;
     std::vector<int32_t> q;
-    q.reserve(8 * kTileRows);
+    q.reserve(8 * kMaxTileRows);
     while (cnt < n) {
         int32_t seed = -1;
         while (fpos < frontier.size()) {
@@ -83,8 +83,11 @@ void build_order(fdb_system* sys) {
     if (Z) FDB_CUDA(cudaMemcpyAsync(indices.data(), sys->vol.indices.p, Z * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     FDB_CUDA(cudaStreamSynchronize(s));
 
+    int kTileRows = kMaxTileRows;
+    if (const char* e = getenv("FDB_TILE_ROWS")) kTileRows = (atoi(e) == 64) ? 64 : 128;   // tuning aid
+    sys->tile_rows = kTileRows;
     std::vector<int32_t> order;
-    blob_order(N, indptr.data(), indices.data(), order);
+    blob_order(N, indptr.data(), indices.data(), kTileRows, order);
     const int64_t n_tiles = (N + kTileRows - 1) / kTileRows;
     // rows of a tile by descending length (stable: ties keep the breadth-first order)
     parallel_for(n_tiles, [&](int64_t a, int64_t b, int) {

@@ -68,6 +68,7 @@ struct SweepWork {
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
+    int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
     bool graph_real = false;
 };
@@ -148,9 +149,22 @@ __device__ __forceinline__ void finalize_last_block(double* __restrict__ partial
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0;
     if (j < TPF) {
-        for (int b = j; b < (int)gridDim.x; b += TPF) {
+        // U independent loads in flight per round, added in block order: the chain of gridDim.x / TPF dependent L2 round
+        // trips was the tail of every reducing kernel (30 us of k_update's 48 us on a 21 735-DOF mesh at 64 slots)
+        constexpr int U = 8;
+        for (int b = j; b < (int)gridDim.x; b += TPF * U) {
+            double t[U][NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
+            for (int u = 0; u < U; ++u) {
+                const int bb = b + u * TPF;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) t[u][i] = (bb < (int)gridDim.x) ? __ldcg(&partial[((int64_t)bb * F + f) * NV + i]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] += t[u][i];
+            }
         }
     }
     __shared__ double s_fin[BLOCK][NV];
@@ -546,20 +560,23 @@ __device__ __forceinline__ int4 ld_meta(const int4* p) {
     return v;
 }
 
-constexpr int kBlobTile = 128;      // rows per tile (= kTileRows of reorder.cu)
 constexpr int kBlobHdr = 20;        // ints of a tile header (= kTileHdr of reorder.cu)
-constexpr int kBlobProducers = 4;   // producer warps
+// TILE = rows per tile (fdb_system::tile_rows): 128 rows with one resident block per SM, or 64 rows with two - the two
+// blocks of an SM drift apart, so one's fill overlaps the other's compute without a third stage buffer
+constexpr int blob_producers(int tile) { return tile / 32; }   // producer warps
+constexpr int blob_threads(int tile, int lpr) { return tile * lpr + blob_producers(tile) * 32; }
 
-template <bool CPX, bool DOT, bool OVERLAY, int LPR>
-__global__ void __launch_bounds__(kBlobTile * LPR + kBlobProducers * 32, 1)
+template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE>
+__global__ void __launch_bounds__(blob_threads(TILE, LPR), TILE == 64 ? 2 : 1)
 k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
             const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_hdr,
             const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
             const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
-            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
+            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial, int dbg) {
     constexpr int F = CPX ? 8 : 16;
+    constexpr int kBlobTile = TILE;
     constexpr int NCONS = kBlobTile * LPR;            // consumer threads
-    constexpr int NPROD = kBlobProducers * 32;        // producer threads
+    constexpr int NPROD = TILE;                        // producer threads (TILE / 32 warps)
     constexpr int BLOCK = NCONS + NPROD;
     constexpr int NCH = 8 / LPR;      // 16-byte chunks of a row per lane
     constexpr int RPW = 32 / LPR;     // rows per warp
@@ -611,7 +628,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             mbar_wait(&empty[buf], ((it >> 1) & 1u) ^ 1u);    // the consumers released this stage (passes at once for it < 2)
             if (ptid == 0) {
                 const int64_t e0 = (int64_t)m_cur.z * 8;
-                const uint32_t n = (uint32_t)m_cur.w;
+                const uint32_t n = (dbg & 4) ? 0u : (uint32_t)m_cur.w;   // dbg: timing experiments only (FDB_BLOB_DBG)
                 mbar_expect_tx(&full[buf], n * 18u + kBlobHdr * 4u);
                 bulk_g2s(s_hdr + buf * kBlobHdr, tile_hdr + t * kBlobHdr, kBlobHdr * 4u, &full[buf]);
                 if (n) {
@@ -620,7 +637,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                 }
             }
             mbar_wait(&cbar[buf], (it >> 1) & 1u);            // this tile's column list
-            const int C = m_cur.y & 0xffff;
+            const int C = (dbg & 2) ? 0 : (m_cur.y & 0xffff);
             const int32_t* tc = s_cols + buf * cols_cap;
             double* dst = xs + (size_t)buf * x_cap * 16;
             for (int i = ptid; i < C * 8; i += NPROD) {
@@ -657,7 +674,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             mbar_wait(&full[buf], (it >> 1) & 1u);
             const int32_t* hd = s_hdr + buf * kBlobHdr;
             const int o = hd[rin >> 3];
-            const int width = valid ? hd[(rin >> 3) + 1] - o : 0;
+            const int width = (valid && !(dbg & 1)) ? hd[(rin >> 3) + 1] - o : 0;
             const int self0 = hd[17];
             const double2* thq = s_hq + (size_t)buf * stage_entries + o * 8 + (rin & 7);
             const uint16_t* tlx = s_lx + (size_t)buf * stage_entries + o * 8 + (rin & 7);
@@ -1146,36 +1163,42 @@ struct Launch {
             return false;
         } else {
             if (sys->n_tiles == 0) return false;
-            const int x_cap = std::max(sys->max_tile_cols, 128);
+            const int tile = sys->tile_rows;
+            const int x_cap = std::max(sys->max_tile_cols, tile);
             const int se = sys->max_tile_entries;
             const size_t smem = (size_t)2 * x_cap * 128 + (size_t)2 * se * 18 + (size_t)2 * (((x_cap + 3) & ~3) + kBlobHdr) * 4;
-            if (smem > 220 * 1024) return false;   // long rows (Tet10) or a mesh without locality: the L1 kernels
-            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms);
-            auto launch = [&](auto kern, int lpr) {
+            // long rows (Tet10) or a mesh without locality: the L1 kernels
+            if (tile == 64 ? smem > 110 * 1024 : smem > 220 * 1024) return false;
+            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * (tile == 64 ? 2 : 1));
+            auto launch = [&](auto kern, int threads) {
                 static thread_local std::map<std::pair<int, const void*>, size_t> granted;
                 size_t& have = granted[{sys->device, (const void*)kern}];
                 if (smem > have) {
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     have = smem;
                 }
-                kern<<<grid, kBlobTile * lpr + kBlobProducers * 32, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
+                kern<<<grid, threads, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
                                                              sys->tile_cols.p, sys->tile_hdr.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
                                                              w->coef.p, (const double*)x, (double*)y, w->N, sys->n_tiles,
-                                                             x_cap, se, w->sc.p, (double*)w->partial.p);
+                                                             x_cap, se, w->sc.p, (double*)w->partial.p, w->blob_dbg);
             };
-            auto pick = [&](auto lpr) {
-                constexpr int L = decltype(lpr)::value;
+            auto pick = [&](auto lpr, auto tl) {
+                constexpr int L = decltype(lpr)::value, T = decltype(tl)::value;
+                constexpr int TH = blob_threads(T, L);
                 if constexpr (CPX) {
                     if (dot) {
-                        if (overlay) launch(k_spmv_blob<true, true, true, L>, L); else launch(k_spmv_blob<true, true, false, L>, L);
+                        if (overlay) launch(k_spmv_blob<true, true, true, L, T>, TH); else launch(k_spmv_blob<true, true, false, L, T>, TH);
                     } else {
-                        if (overlay) launch(k_spmv_blob<true, false, true, L>, L); else launch(k_spmv_blob<true, false, false, L>, L);
+                        if (overlay) launch(k_spmv_blob<true, false, true, L, T>, TH); else launch(k_spmv_blob<true, false, false, L, T>, TH);
                     }
                 } else {
-                    if (dot) launch(k_spmv_blob<false, true, false, L>, L); else launch(k_spmv_blob<false, false, false, L>, L);
+                    if (dot) launch(k_spmv_blob<false, true, false, L, T>, TH); else launch(k_spmv_blob<false, false, false, L, T>, TH);
                 }
             };
-            if (w->blob_lpr == 4) pick(std::integral_constant<int, 4>{}); else pick(std::integral_constant<int, 2>{});
+            using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
+            using T64 = std::integral_constant<int, 64>; using T128 = std::integral_constant<int, 128>;
+            if (tile == 64) { if (w->blob_lpr == 4) pick(I4{}, T64{}); else pick(I2{}, T64{}); }
+            else            { if (w->blob_lpr == 4) pick(I4{}, T128{}); else pick(I2{}, T128{}); }
             return true;
         }
     }
@@ -1196,8 +1219,11 @@ struct Launch {
         spmv_ldg<double2>(sys, w, (const double2*)x, (double2*)y, dot, overlay);
     }
 
+    // vector kernels: up to 8 blocks per SM, but at least 16 elements per thread - on a small mesh a thin grid leaves
+    // the reducing kernels fewer block partials to sum in their last block
     static int egrid(SweepWork* w) {
-        return (int)std::min<int64_t>((w->N * F + kBlock - 1) / kBlock, (int64_t)w->grid);
+        const int64_t want = (w->N * F + (int64_t)kBlock * 16 - 1) / ((int64_t)kBlock * 16);
+        return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)w->grid));
     }
     template <typename T>
     static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
@@ -1327,6 +1353,7 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
+        if (const char* e = getenv("FDB_BLOB_DBG")) w->blob_dbg = atoi(e);
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);

@@ -37,6 +37,33 @@ def test_spmv_matches_scipy(gpu_lib, golden, F):
         assert np.linalg.norm(y[:, f] - ref) / np.linalg.norm(ref) < 1e-13
 
 
+@pytest.mark.parametrize("tile", [64, 128])
+def test_spmv_blob_tile_rows(gpu_lib, golden, monkeypatch, tile):
+    """k_spmv_blob with 64-row tiles (two resident blocks per SM) and 128-row tiles (one): both against scipy, complex
+    batch of 8 with the boundary overlay; then a rigid sweep in real arithmetic (batch 16) against the complex one."""
+    monkeypatch.setenv("FDB_TILE_ROWS", str(tile))
+    g = golden
+    s = _solver_system(g.H, g.Q, g.A)
+    F = 8
+    rng = np.random.default_rng(tile)
+    x = rng.standard_normal((g.N, F)) + 1j * rng.standard_normal((g.N, F))
+    w = 2 * np.pi * np.linspace(30.0, 400.0, F)
+    mu = np.array([np.resize(g.mu[int(k)], F) * (1 + 0.1 * np.arange(F)) for k in g.group_ids])
+    y = s.spmv(w, mu, x)
+    Hd, Qd = g.H.astype(np.complex128), g.Q.astype(np.complex128)
+    for f in range(F):
+        ref = O.system_matrix(Hd, Qd, g.A, mu[:, f], w[f]) @ x[:, f]
+        assert np.linalg.norm(y[:, f] - ref) / np.linalg.norm(ref) < 1e-13
+    w16 = 2 * np.pi * np.linspace(30.0, 200.0, 16)
+    mu0 = np.zeros((len(g.group_ids), 16), dtype=complex)
+    nodes, q = np.array([5], dtype=np.int32), np.array([1e-4 + 0j])
+    pr, _, st_r = s.sweep(w16, mu0, nodes, q, tol=1e-11, batch=16)
+    assert st_r.real_arithmetic and st_r.n_unconverged == 0
+    pc, _, st_c = s.sweep(w16, mu0, nodes, q, tol=1e-11, batch=8, force_complex=True)
+    assert not st_c.real_arithmetic
+    assert _rel_rows(pr, pc).max() < 1e-7
+
+
 def test_sweep_on_reference_matrices(gpu_lib, golden):
     """Solver parity on identical inputs: the reference's own H, Q, A arrays in, its pN out (north star: relative
     L2 error <= 1e-6, receiver SPL within 0.01 dB)."""
