@@ -68,6 +68,7 @@ struct SweepWork {
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
+    bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
     int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
     bool graph_real = false;
@@ -303,6 +304,132 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5 for NARROW real batches (F = 2, 4, 8: the tail of a sweep, when the last systems run in a narrowing batch):
+// one lane per ROW, the row's F values in registers.  The plain kernel above gives every (row, f) its own lane, so F
+// lanes fetch the same matrix entry and a warp's matrix loads cover 32/F rows only - at F = 2..4 it is bound by load
+// instructions, not by HBM (197 us per iteration at F = 2 against 88 us at F = 1).  Here the matrix stream is read
+// exactly as at F = 1 (fully coalesced, each lane its own row of a SELL-8 slice) and one 16/32-byte load gathers
+// x[col][0..F).
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) d4x { double v[4]; };
+template <int FPL> struct RowVec { double v[FPL]; };
+template <int FPL>
+__device__ __forceinline__ RowVec<FPL> ld_row(const double* p) {
+    RowVec<FPL> r;
+    if constexpr (FPL == 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int h = 0; h < FPL / 4; ++h)
+            asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                         : "=d"(r.v[4 * h]), "=d"(r.v[4 * h + 1]), "=d"(r.v[4 * h + 2]), "=d"(r.v[4 * h + 3]) : "l"(p + 4 * h));
+    }
+    return r;
+}
+template <int FPL>
+__device__ __forceinline__ void st_row(double* p, const RowVec<FPL>& r) {
+    if constexpr (FPL == 2) {
+        *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
+    } else {
+#pragma unroll
+        for (int h = 0; h < FPL / 4; ++h) {
+            d4x t;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t.v[j] = r.v[4 * h + j];
+            *reinterpret_cast<d4x*>(p + 4 * h) = t;
+        }
+    }
+}
+
+template <int FPL, bool DOT, int BLOCK, int MINB, int UNR>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_spmv_rows(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
+            const double* __restrict__ x, double* __restrict__ y, int64_t n_rows, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int NWARP = BLOCK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double w2[FPL];
+#pragma unroll
+    for (int j = 0; j < FPL; ++j) w2[j] = sc->w2[j];
+    const int64_t n_groups = (n_rows + 31) / 32;
+    const int64_t gpb = (n_groups + gridDim.x - 1) / gridDim.x;   // contiguous groups of 32 rows per block
+    const int64_t g0 = (int64_t)blockIdx.x * gpb;
+    const int64_t g1 = min(g0 + gpb, n_groups);
+    double dot[FPL];
+#pragma unroll
+    for (int j = 0; j < FPL; ++j) dot[j] = 0.0;
+    for (int64_t g = g0 + warp; g < g1; g += NWARP) {
+        const int64_t row = g * 32 + lane;
+        if (row < n_rows) {
+            const int64_t slice = row >> 3;
+            const int off = sell_off[slice];
+            const int width = sell_off[slice + 1] - off;
+            const int32_t* ip = sell_idx + ((int64_t)off * 8 + (row & 7));
+            const double2* mp = sell_hq + ((int64_t)off * 8 + (row & 7));
+            double acc[FPL];
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) acc[j] = 0.0;
+            int k = 0;
+            for (; k + UNR <= width; k += UNR) {
+                int c[UNR];
+                double2 m[UNR];
+                RowVec<FPL> xv[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) c[u] = __ldg(ip + (k + u) * 8);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) xv[u] = ld_row<FPL>(x + (int64_t)c[u] * FPL);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) m[u] = ld_stream(mp + (k + u) * 8);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+                    for (int j = 0; j < FPL; ++j) acc[j] += (m[u].x - w2[j] * m[u].y) * xv[u].v[j];
+                }
+            }
+            for (; k < width; ++k) {
+                const int c = __ldg(ip + k * 8);
+                const double2 m = ld_stream(mp + k * 8);
+                const RowVec<FPL> xv = ld_row<FPL>(x + (int64_t)c * FPL);
+#pragma unroll
+                for (int j = 0; j < FPL; ++j) acc[j] += (m.x - w2[j] * m.y) * xv.v[j];
+            }
+            RowVec<FPL> out;
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) out.v[j] = acc[j];
+            st_row<FPL>(y + row * FPL, out);
+            if (DOT) {
+                const RowVec<FPL> xo = ld_row<FPL>(x + row * FPL);
+#pragma unroll
+                for (int j = 0; j < FPL; ++j) dot[j] += xo.v[j] * acc[j];
+            }
+        }
+    }
+    if (DOT) {
+        // every lane holds all FPL frequencies: lanes -> warp (shuffles, fixed order) -> block (fixed order) -> last block
+        __shared__ double s_w[NWARP][FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) s_w[warp][j] = dot[j];
+        }
+        __syncthreads();
+        if (threadIdx.x < FPL) {
+            double sum = 0.0;
+            for (int k = 0; k < NWARP; ++k) sum += s_w[k][threadIdx.x];
+            partial[((int64_t)blockIdx.x * FPL + threadIdx.x) * 2 + 0] = sum;
+            partial[((int64_t)blockIdx.x * FPL + threadIdx.x) * 2 + 1] = 0.0;
+        }
+        finalize_last_block<FPL, 2, BLOCK>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
+            sc->pq[ff] = make_double2(tot[0], tot[1]);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -330,6 +457,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// DRAM -> L2 only: takes the HBM latency of a later bulk copy early without holding shared memory for it
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 struct __align__(32) d4 { double v[4]; };   // one 256-bit access (LDG/STG.E.256 on sm_100): 2 complex or 4 real values
@@ -647,7 +779,23 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             cp_async_arrive_noinc(&full[buf]);
             // all producers are done reading the column list: its slot takes the list of the tile after next
             asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-            if (ptid == 0 && t + 2 * G < n_tiles) copy_cols(m_nx2, buf);
+            if (ptid == 0 && t + 2 * G < n_tiles) {
+                copy_cols(m_nx2, buf);
+                // Two stage buffers leave one fill in flight per SM, too few bytes to cover the HBM latency (fill alone 90 us,
+                // compute alone 94 us, together 127 us).  There is no room for a third stage, but L2 has it: the contiguous
+                // parts of the tile after next - matrix values, column positions, own x rows - start their way from HBM now.
+                if (!(dbg & 8)) {
+                    const int64_t t2 = t + 2 * G;
+                    const int64_t e2 = (int64_t)m_nx2.z * 8;
+                    const uint32_t n2 = (uint32_t)m_nx2.w;
+                    if (n2) {
+                        bulk_prefetch_l2(sell_hq + e2, n2 * 16u);
+                        bulk_prefetch_l2(sell_lidx + e2, n2 * 2u);
+                    }
+                    const int64_t rows2 = min((int64_t)kBlobTile, n_rows - t2 * kBlobTile);
+                    bulk_prefetch_l2(x + t2 * kBlobTile * 16, (uint32_t)rows2 * 128u);
+                }
+            }
             m_cur = m_nxt;
             m_nxt = m_nx2;
         }
@@ -775,17 +923,30 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
 // Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the sweep): the diagonal is rebuilt from
 // (H_rr, Q_rr) - 16 bytes per ROW instead of 16 bytes per (row, frequency); otherwise the precomputed 1/diag is read.
 template <typename T, int F, bool ONFLY>
-__device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
-                                          int64_t i, double w2, T rv) {
+__device__ __forceinline__ double2 jacobi_load(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq, int64_t i) {
+    if constexpr (ONFLY) return __ldg(&diag_hq[i / F]);
+    else return dinv[i];
+}
+template <typename T, bool ONFLY>
+__device__ __forceinline__ T jacobi_mul(double2 d, double w2, T rv) {
     if constexpr (ONFLY) {
-        const double2 d = __ldg(&diag_hq[i / F]);
         const double g = d.x - w2 * d.y;
         const double inv = (g == 0.0) ? 1.0 : 1.0 / g;
         return r_mul(inv, rv);
     } else {
-        return s_mul(dinv[i], rv);   // complex sweeps only
+        return s_mul(d, rv);   // complex sweeps only
     }
 }
+template <typename T, int F, bool ONFLY>
+__device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                          int64_t i, double w2, T rv) {
+    return jacobi_mul<T, ONFLY>(jacobi_load<T, F, ONFLY>(dinv, diag_hq, i), w2, rv);
+}
+
+// The streaming loops below handle kVecU elements per thread and round, ALL loads of a round issued before the first
+// store: a thread of a real sweep moves 8 bytes per access, and with one element per round (the store to r ahead of
+// the next round's loads, which the compiler must keep in order) a full SM has only ~32 KB in flight - 3 TB/s.
+constexpr int kVecU = 4;
 
 template <typename T, int F, bool ONFLY>
 __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
@@ -802,14 +963,32 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
     }
     double v[3] = {0.0, 0.0, 0.0};
     if (act) {
-        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-            const T rv = v_sub(r[i], s_mul(alpha, q[i]));
-            r[i] = rv;
-            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, rv);
-            const double2 rz = v_dot(rv, z);
-            v[0] += rz.x;
-            v[1] += rz.y;
-            v[2] += v_n2(rv);
+        const int64_t stride = (int64_t)gridDim.x * kBlock;   // a multiple of F: every element of a thread belongs to frequency f
+        for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
+            T rv[kVecU], qv[kVecU];
+            double2 d[kVecU];
+#pragma unroll
+            for (int u = 0; u < kVecU; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < n_elems) {
+                    rv[u] = r[i];
+                    qv[u] = q[i];
+                    d[u] = jacobi_load<T, F, ONFLY>(dinv, diag_hq, i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kVecU; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < n_elems) {
+                    const T rn = v_sub(rv[u], s_mul(alpha, qv[u]));
+                    r[i] = rn;
+                    const T z = jacobi_mul<T, ONFLY>(d[u], w2, rn);
+                    const double2 rz = v_dot(rn, z);
+                    v[0] += rz.x;
+                    v[1] += rz.y;
+                    v[2] += v_n2(rn);
+                }
+            }
         }
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
@@ -844,12 +1023,29 @@ __global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ x, T* __rest
     const bool act = sc->active[f] != 0;   // false: the slot converged in this iteration, only its last step is owed
     const double2 alpha = sc->alpha[f], beta = sc->beta[f];
     const double w2 = sc->w2[f];
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
-        const T pv = p[i];
-        x[i] = v_add(x[i], s_mul(alpha, pv));
-        if (act) {
-            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
-            p[i] = v_add(z, s_mul(beta, pv));
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
+        T xv[kVecU], pv[kVecU], rv[kVecU];
+        double2 d[kVecU];
+#pragma unroll
+        for (int u = 0; u < kVecU; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n_elems) {
+                xv[u] = x[i];
+                pv[u] = p[i];
+                if (act) {
+                    rv[u] = r[i];
+                    d[u] = jacobi_load<T, F, ONFLY>(dinv, diag_hq, i);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecU; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n_elems) {
+                x[i] = v_add(xv[u], s_mul(alpha, pv[u]));
+                if (act) p[i] = v_add(jacobi_mul<T, ONFLY>(d[u], w2, rv[u]), s_mul(beta, pv[u]));
+            }
         }
     }
 }
@@ -1207,9 +1403,30 @@ struct Launch {
         if (F <= 32) return true;                                          // the plain kernel covers it
         return (size_t)2 * stage_entries<4>(sys, w) * 20 <= 100 * 1024;   // wider: the smallest tile shape must fit
     }
+    // ---- narrow real batches: one lane per row (k_spmv_rows)
+    static bool spmv_rows(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot) {
+        if constexpr (F == 2 || F == 4 || F == 8) {
+            constexpr int BLOCK = (F == 2) ? 512 : 256;
+            constexpr int MINB = (F == 2) ? 2 : (F == 4 ? 3 : 2);
+            constexpr int UNR = (F == 8) ? 2 : 4;
+            const int64_t groups = (w->N + 31) / 32;
+            const int64_t per_block = BLOCK / 32;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + per_block - 1) / per_block, (int64_t)sys->num_sms * MINB));
+            if (dot)
+                k_spmv_rows<F, true, BLOCK, MINB, UNR><<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p,
+                                                                                      (const double*)x, (double*)y, w->N, w->sc.p, (double*)w->partial.p);
+            else
+                k_spmv_rows<F, false, BLOCK, MINB, UNR><<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p,
+                                                                                       (const double*)x, (double*)y, w->N, w->sc.p, (double*)w->partial.p);
+            return true;
+        } else {
+            return false;
+        }
+    }
     static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         if (w->real) {
             if (w->spmv_cfg == 0 && spmv_blob<false>(sys, w, x, y, dot, false)) return;
+            if (w->spmv_cfg == 0 && w->rows_kernel && spmv_rows(sys, w, x, y, dot)) return;
             if (w->spmv_cfg < 8 && spmv_tma_cfg<false>(sys, w, x, y, dot, false)) return;
             spmv_ldg<double>(sys, w, (const double*)x, (double*)y, dot, false);
             return;
@@ -1354,6 +1571,7 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
         if (const char* e = getenv("FDB_BLOB_DBG")) w->blob_dbg = atoi(e);
+        if (getenv("FDB_NO_ROWS_KERNEL")) w->rows_kernel = false;
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
