@@ -1,0 +1,158 @@
+/*
+ * femder_b200 - C ABI of the B200 (sm_100a) implementation of femder's FEM3D.compute() hot path.
+ *
+ * The reference (gutoalvim/femder) is pure Python and has no FFI layer; its boundary for this path is the
+ * set of Python call sites inside FEM3D.compute() (femder/FEM_3D.py:1242-1432).  Each entry point below
+ * names the reference call site(s) it replaces.  A maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; fdb_last_error() then describes it;
+ *   - plain pointers and sizes only; arrays are C-contiguous; indices are int32 (scipy's index dtype for
+ *     these sizes), values are IEEE double; complex numbers are interleaved (re, im) doubles;
+ *   - every data pointer may be a host pointer OR a device pointer of the system's device (copies use
+ *     cudaMemcpyDefault), so PyTorch-owned device buffers can be passed without staging;
+ *   - a system handle owns its device memory; the library keeps no pointer to caller memory past a call;
+ *   - there is no CPU fallback: without a usable CUDA device every call fails.
+ */
+#ifndef FEMDER_B200_H
+#define FEMDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdb_system fdb_system;
+
+/* ---- library / device ------------------------------------------------------------------------- */
+const char* fdb_last_error(void);
+int fdb_abi_version(void);
+int fdb_device_count(int* count);
+
+/* One system = one mesh on one GPU.  `stream` is a cudaStream_t (0 = library-owned non-blocking stream);
+ * pass torch.cuda.current_stream().cuda_stream to have torch events bracket the library's work. */
+int fdb_system_create(int device, void* stream, fdb_system** out);
+int fdb_system_destroy(fdb_system* sys);
+int fdb_synchronize(fdb_system* sys);
+
+/* ---- volume mesh, CSR pattern, element->nnz map (K4) ------------------------------------------ *
+ * Replaces the COO->CSC conversion inside csc_matrix(...) at femder/fem_numerical.py:337-343 and
+ * coo_matrix(...).tocsc() at femder/FEM_3D.py:413-416: the pattern is the canonical (sorted, duplicate-
+ * free) pattern scipy produces, symmetric, so CSR == CSC.  nper = 4 (Tet4) or 10 (Tet10, gmsh node order). */
+int fdb_set_volume_mesh(fdb_system* sys, int64_t n_nodes, const double* nos /* [n_nodes][3] */,
+                        int64_t n_elem, int nper, const int32_t* conn /* [n_elem][nper] */);
+int fdb_pattern_nnz(fdb_system* sys, int64_t* nnz);
+int fdb_pattern_get(fdb_system* sys, int32_t* indptr /* [n_nodes+1] */, int32_t* indices /* [nnz] */);
+/* elem2nnz[e][a][b] = position in `indices` of entry (row conn[e][a], col conn[e][b]). */
+int fdb_elem2nnz_get(fdb_system* sys, int32_t* elem2nnz /* [n_elem][nper][nper] */);
+/* Use an externally built pattern instead (solver-only use: the reference's own H/Q/A arrays). */
+int fdb_set_pattern(fdb_system* sys, int64_t n_nodes, int64_t nnz, const int32_t* indptr, const int32_t* indices);
+
+/* ---- volume assembly (K1 Tet4, K2 Tet10) ------------------------------------------------------- *
+ * Replaces fem_numerical.pre_compute_volume_assemble_vars + assemble_volume_matrices
+ * (femder/fem_numerical.py:129-150, 267-345; call site FEM_3D.py:1274-1275) for nper = 4 and
+ * assemble_Q_H_4_FAST_2order + int_tetra10_4gauss (FEM_3D.py:398-417, 888-919; call site 1277) for
+ * nper = 10.  FP64 throughout; values land in the pattern's nnz order by a deterministic segmented sum. */
+int fdb_assemble_volume(fdb_system* sys, double rho0, double c0);
+int fdb_get_HQ(fdb_system* sys, double* H_vals /* [nnz] */, double* Q_vals /* [nnz] */);
+int fdb_set_HQ(fdb_system* sys, const double* H_vals, const double* Q_vals);
+/* Element matrices of the last fdb_assemble_volume, [nper*nper][n_elem] (debug / parity). */
+int fdb_get_element_matrices(fdb_system* sys, double* He, double* Qe);
+
+/* ---- surface mesh, Heron areas, admittance matrices (K3) -------------------------------------- *
+ * Replaces compute_areas/area_normal_ph (FEM_3D.py:722-771; call site 1267), assemble_surface_matrices
+ * (FEM_3D.py:475-523; call site 1283) for nper = 3 and assemble_A10_3_FAST + int_tri10_3gauss
+ * (FEM_3D.py:541-554, 1053-1092; call site 1290) for nper = 6.  group_of_tri[t] is an index into the
+ * caller's sorted group list (0..n_groups-1) or -1 for triangles with no boundary condition. */
+int fdb_set_surface_mesh(fdb_system* sys, int64_t n_tri, int nper, const int32_t* conn /* [n_tri][nper] */,
+                         const int32_t* group_of_tri /* [n_tri] */, int n_groups);
+int fdb_heron_areas(fdb_system* sys, double* areas /* [n_tri] */);
+int fdb_assemble_surface(fdb_system* sys);
+int fdb_surface_nnz(fdb_system* sys, int64_t* nnz_b);
+int fdb_surface_pattern_get(fdb_system* sys, int32_t* indptr /* [n_nodes+1] */, int32_t* indices /* [nnz_b] */);
+/* A_vals[g][k] and touched[g][k] (1 where group g has at least one triangle contributing to entry k). */
+int fdb_surface_get(fdb_system* sys, double* A_vals /* [n_groups][nnz_b] */, uint8_t* touched /* same */);
+/* Solver-only use: give the per-group matrices directly, all on one pattern. */
+int fdb_set_surface(fdb_system* sys, int n_groups, int64_t nnz_b, const int32_t* indptr, const int32_t* indices,
+                    const double* A_vals /* [n_groups][nnz_b] */);
+
+/* ---- receivers (K7, set-up half) ------------------------------------------------------------------ *
+ * Batched receiver location: for every query point the 4 nodes and weights with p(point) = sum_j w_j p[node_j].
+ * Replaces, for many points at once, the nearest-node rule of evaluate() (femder/FEM_3D.py:2077-2086) and
+ * closest_node + prob_elem + which_tetra + coord_interpolation (FEM_3D.py:173-224): the closest node if it lies
+ * within `tol`, otherwise linear interpolation in the LAST element around that node that passes the barycentric
+ * test (the last candidate if none does).  The result feeds fdb_sweep_params.rcv_nodes / rcv_w. */
+int fdb_locate_points(fdb_system* sys, int64_t n_pts, const double* pts /* [n_pts][3] */, double tol,
+                      int32_t* nodes /* [n_pts][4] */, double* weights /* [n_pts][4] */);
+
+/* ---- frequency sweep (K5 fused multi-frequency SpMV, K6 COCG, K7 receiver gather) -------------- *
+ * Replaces the hot loop FEM_3D.py:1304-1319: for every frequency n
+ *     G = H + 1j*w[n]*sum_g mu[g][n]*A[g] - w[n]**2*Q ;  b = -1j*w[n]*q ;  pN[n] = solve(G, b)
+ * where the reference factorises G from scratch with PARDISO (pyMKL, mtype 13, phases 12 and 33). */
+typedef struct fdb_sweep_params {
+    int64_t n_freq;
+    const double* omega;      /* [n_freq] angular frequencies w */
+    const double* mu;         /* [n_groups][n_freq] complex admittances, may be NULL when n_groups == 0 */
+    int64_t n_src;
+    const int32_t* src_nodes; /* [n_src]  node of each source (later duplicates overwrite, as the reference) */
+    const double* src_q;      /* [n_src]  complex volume velocities q */
+    /* multi-RHS: the sources are split into n_src_sets right-hand sides sharing G(w) (source/receiver candidate loops,
+     * FEM_3D.py:1633-1648).  0 = one set.  Outputs are then [n_src_sets][n_freq][...]. */
+    int64_t n_src_sets;
+    const int32_t* src_set_ptr; /* [n_src_sets+1] set k = sources src_set_ptr[k] .. src_set_ptr[k+1] */
+    double tol;               /* relative residual ||b - G x|| / ||b|| to reach */
+    int32_t max_iter;
+    int32_t batch;            /* solver slots = frequencies per fused SpMV: 1, 2, 4, 8, 16, 32 or 64 */
+    int32_t check_every;      /* iterations between host convergence checks (one CUDA graph launch) */
+    int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
+    int32_t precond;          /* 0: Jacobi */
+    int32_t arithmetic;       /* 0: automatic (real arithmetic for rigid-wall sweeps with real sources), 1: always complex */
+    /* extra right-hand-side terms (velocity boundary conditions, FEM_3D.py:1320-1347): b_n += sum_k rhs_coef[k][n] * vec_k */
+    int64_t n_rhs_vec;
+    const int32_t* rhs_ptr;   /* [n_rhs_vec+1] vec_k = entries rhs_ptr[k] .. rhs_ptr[k+1] */
+    const int32_t* rhs_nodes; /* node of each entry */
+    const double* rhs_vals;   /* real value of each entry */
+    const double* rhs_coef;   /* [n_rhs_vec][n_freq] complex coefficients (the caller folds -1j*w in) */
+    int64_t n_rcv;            /* receivers: pR[n][i] = sum_j rcv_w[i][j] * p[n][rcv_nodes[i][j]] */
+    const int32_t* rcv_nodes; /* [n_rcv][4] (unused slots: weight 0, any valid node) */
+    const double* rcv_w;      /* [n_rcv][4] */
+} fdb_sweep_params;
+/* Multi-GPU: frequencies are independent, so each rank creates its own system on its own
+ * GPU and passes only the frequencies it owns; there is no collective on this path. */
+
+typedef struct fdb_sweep_result {
+    double* pR;       /* [n_sets][n_freq][n_rcv] complex; may be NULL */
+    double* pN;       /* [n_sets][n_freq][n_nodes] complex; may be NULL */
+    int32_t* iters;   /* [n_sets][n_freq] iterations used; may be NULL */
+    double* relres;   /* [n_sets][n_freq] true relative residual ||b - G x|| / ||b|| of what is returned; may be NULL */
+    double seconds;   /* device time of the sweep (CUDA events on the system's stream) */
+    int64_t n_spmv;   /* fused SpMV launches */
+    int64_t n_kernels;/* all kernel launches of the sweep */
+    int32_t n_unconverged;
+    int32_t real_arithmetic;  /* 1 if the sweep ran in real arithmetic (G real, b imaginary: p = 1j*u) */
+} fdb_sweep_result;
+
+int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);
+/* sizeof(fdb_sweep_params) / sizeof(fdb_sweep_result) as compiled, so a binding can verify its struct layout. */
+int fdb_sizeof_sweep_params(void);
+int fdb_sizeof_sweep_result(void);
+
+/* y = G_f x for a batch of frequencies on caller data: x, y are [n_nodes][batch] complex. (K5 alone; parity) */
+int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu /* [n_groups][batch] complex */,
+             const double* x, double* y);
+/* Time `reps` launches of K5 on resident synthetic vectors; returns mean milliseconds per launch.
+ * flags: bit 0 = include the boundary (admittance) overlay; bit 1 = real-arithmetic variant (what a rigid-wall
+ * sweep with real sources launches; excludes bit 0). */
+#define FDB_SPMV_BOUNDARY 1
+#define FDB_SPMV_REAL 2
+int fdb_spmv_bench(fdb_system* sys, int batch, int reps, int flags, double* ms_per_launch, int64_t* algorithmic_bytes);
+/* Enqueue `reps` launches of K5 (with its dot-product epilogue, as the solver launches it) on the system's
+ * stream and return without synchronising, so the caller can bracket them with its own CUDA events.
+ * Call fdb_spmv_bench once before to fill the resident vectors. */
+int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int flags, int64_t* algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMDER_B200_H */

@@ -28,7 +28,6 @@ struct __align__(16) Scalars {
     double2 rho[kMaxF];    // r^T z (unconjugated)
     double2 pq[kMaxF];     // p^T G p
     double2 beta[kMaxF];
-    double2 alpha[kMaxF];  // step length of the iteration whose x update is still pending (applied by k_pupdate)
     double rr[kMaxF];      // ||r||^2
     double bb[kMaxF];      // ||b||^2
     double w2[kMaxF];      // omega^2
@@ -37,7 +36,6 @@ struct __align__(16) Scalars {
     int active[kMaxF];
     int iters[kMaxF];
     int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
-    int xpend[kMaxF];      // the slot took a step in the last k_update: k_pupdate owes it x += alpha p
     int src_set[kMaxF];    // which source set (right-hand side) the slot solves: multi-RHS sweeps share G(w)
     int bb_from_r0;        // ||b||^2 is taken from the start residual (general right-hand sides, zero starting guess)
     double tol2;
@@ -68,8 +66,6 @@ struct SweepWork {
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
-    bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
-    int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
     bool graph_real = false;
 };
@@ -150,22 +146,9 @@ __device__ __forceinline__ void finalize_last_block(double* __restrict__ partial
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0;
     if (j < TPF) {
-        // U independent loads in flight per round, added in block order: the chain of gridDim.x / TPF dependent L2 round
-        // trips was the tail of every reducing kernel (30 us of k_update's 48 us on a 21 735-DOF mesh at 64 slots)
-        constexpr int U = 8;
-        for (int b = j; b < (int)gridDim.x; b += TPF * U) {
-            double t[U][NV];
+        for (int b = j; b < (int)gridDim.x; b += TPF) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int bb = b + u * TPF;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) t[u][i] = (bb < (int)gridDim.x) ? __ldcg(&partial[((int64_t)bb * F + f) * NV + i]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int i = 0; i < NV; ++i) acc[i] += t[u][i];
-            }
+            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partial[((int64_t)b * F + f) * NV + i]);
         }
     }
     __shared__ double s_fin[BLOCK][NV];
@@ -298,132 +281,6 @@ k_spmv(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_id
     }
     if (DOT) {
         block_reduce_finalize<F, 2, BLOCK>(dot, partial, &sc->ticket[0], [&](int ff, const double* tot) {
-            sc->pq[ff] = make_double2(tot[0], tot[1]);
-        });
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5 for NARROW real batches (F = 2, 4, 8: the tail of a sweep, when the last systems run in a narrowing batch):
-// one lane per ROW, the row's F values in registers.  The plain kernel above gives every (row, f) its own lane, so F
-// lanes fetch the same matrix entry and a warp's matrix loads cover 32/F rows only - at F = 2..4 it is bound by load
-// instructions, not by HBM (197 us per iteration at F = 2 against 88 us at F = 1).  Here the matrix stream is read
-// exactly as at F = 1 (fully coalesced, each lane its own row of a SELL-8 slice) and one 16/32-byte load gathers
-// x[col][0..F).
-// ------------------------------------------------------------------------------------------------
-struct __align__(32) d4x { double v[4]; };
-template <int FPL> struct RowVec { double v[FPL]; };
-template <int FPL>
-__device__ __forceinline__ RowVec<FPL> ld_row(const double* p) {
-    RowVec<FPL> r;
-    if constexpr (FPL == 2) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(p));
-        r.v[0] = t.x; r.v[1] = t.y;
-    } else {
-#pragma unroll
-        for (int h = 0; h < FPL / 4; ++h)
-            asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                         : "=d"(r.v[4 * h]), "=d"(r.v[4 * h + 1]), "=d"(r.v[4 * h + 2]), "=d"(r.v[4 * h + 3]) : "l"(p + 4 * h));
-    }
-    return r;
-}
-template <int FPL>
-__device__ __forceinline__ void st_row(double* p, const RowVec<FPL>& r) {
-    if constexpr (FPL == 2) {
-        *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
-    } else {
-#pragma unroll
-        for (int h = 0; h < FPL / 4; ++h) {
-            d4x t;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) t.v[j] = r.v[4 * h + j];
-            *reinterpret_cast<d4x*>(p + 4 * h) = t;
-        }
-    }
-}
-
-template <int FPL, bool DOT, int BLOCK, int MINB, int UNR>
-__global__ void __launch_bounds__(BLOCK, MINB)
-k_spmv_rows(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx, const double2* __restrict__ sell_hq,
-            const double* __restrict__ x, double* __restrict__ y, int64_t n_rows, Scalars* __restrict__ sc, double* __restrict__ partial) {
-    constexpr int NWARP = BLOCK / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double w2[FPL];
-#pragma unroll
-    for (int j = 0; j < FPL; ++j) w2[j] = sc->w2[j];
-    const int64_t n_groups = (n_rows + 31) / 32;
-    const int64_t gpb = (n_groups + gridDim.x - 1) / gridDim.x;   // contiguous groups of 32 rows per block
-    const int64_t g0 = (int64_t)blockIdx.x * gpb;
-    const int64_t g1 = min(g0 + gpb, n_groups);
-    double dot[FPL];
-#pragma unroll
-    for (int j = 0; j < FPL; ++j) dot[j] = 0.0;
-    for (int64_t g = g0 + warp; g < g1; g += NWARP) {
-        const int64_t row = g * 32 + lane;
-        if (row < n_rows) {
-            const int64_t slice = row >> 3;
-            const int off = sell_off[slice];
-            const int width = sell_off[slice + 1] - off;
-            const int32_t* ip = sell_idx + ((int64_t)off * 8 + (row & 7));
-            const double2* mp = sell_hq + ((int64_t)off * 8 + (row & 7));
-            double acc[FPL];
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) acc[j] = 0.0;
-            int k = 0;
-            for (; k + UNR <= width; k += UNR) {
-                int c[UNR];
-                double2 m[UNR];
-                RowVec<FPL> xv[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) c[u] = __ldg(ip + (k + u) * 8);
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) xv[u] = ld_row<FPL>(x + (int64_t)c[u] * FPL);
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) m[u] = ld_stream(mp + (k + u) * 8);
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-#pragma unroll
-                    for (int j = 0; j < FPL; ++j) acc[j] += (m[u].x - w2[j] * m[u].y) * xv[u].v[j];
-                }
-            }
-            for (; k < width; ++k) {
-                const int c = __ldg(ip + k * 8);
-                const double2 m = ld_stream(mp + k * 8);
-                const RowVec<FPL> xv = ld_row<FPL>(x + (int64_t)c * FPL);
-#pragma unroll
-                for (int j = 0; j < FPL; ++j) acc[j] += (m.x - w2[j] * m.y) * xv.v[j];
-            }
-            RowVec<FPL> out;
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) out.v[j] = acc[j];
-            st_row<FPL>(y + row * FPL, out);
-            if (DOT) {
-                const RowVec<FPL> xo = ld_row<FPL>(x + row * FPL);
-#pragma unroll
-                for (int j = 0; j < FPL; ++j) dot[j] += xo.v[j] * acc[j];
-            }
-        }
-    }
-    if (DOT) {
-        // every lane holds all FPL frequencies: lanes -> warp (shuffles, fixed order) -> block (fixed order) -> last block
-        __shared__ double s_w[NWARP][FPL];
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) {
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) s_w[warp][j] = dot[j];
-        }
-        __syncthreads();
-        if (threadIdx.x < FPL) {
-            double sum = 0.0;
-            for (int k = 0; k < NWARP; ++k) sum += s_w[k][threadIdx.x];
-            partial[((int64_t)blockIdx.x * FPL + threadIdx.x) * 2 + 0] = sum;
-            partial[((int64_t)blockIdx.x * FPL + threadIdx.x) * 2 + 1] = 0.0;
-        }
-        finalize_last_block<FPL, 2, BLOCK>(partial, &sc->ticket[0], [&](int ff, const double* tot) {
             sc->pq[ff] = make_double2(tot[0], tot[1]);
         });
     }
@@ -687,23 +544,20 @@ __device__ __forceinline__ int4 ld_meta(const int4* p) {
     return v;
 }
 
+constexpr int kBlobTile = 128;      // rows per tile (= kTileRows of reorder.cu)
 constexpr int kBlobHdr = 20;        // ints of a tile header (= kTileHdr of reorder.cu)
-// TILE = rows per tile (fdb_system::tile_rows): 128 rows with one resident block per SM, or 64 rows with two - the two
-// blocks of an SM drift apart, so one's fill overlaps the other's compute without a third stage buffer
-constexpr int blob_producers(int tile) { return tile / 32; }   // producer warps
-constexpr int blob_threads(int tile, int lpr) { return tile * lpr + blob_producers(tile) * 32; }
+constexpr int kBlobProducers = 4;   // producer warps
 
-template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE>
-__global__ void __launch_bounds__(blob_threads(TILE, LPR), TILE == 64 ? 2 : 1)
+template <bool CPX, bool DOT, bool OVERLAY, int LPR>
+__global__ void __launch_bounds__(kBlobTile * LPR + kBlobProducers * 32, 1)
 k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
             const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_hdr,
             const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
             const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
-            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial, int dbg) {
+            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial) {
     constexpr int F = CPX ? 8 : 16;
-    constexpr int kBlobTile = TILE;
     constexpr int NCONS = kBlobTile * LPR;            // consumer threads
-    constexpr int NPROD = TILE;                        // producer threads (TILE / 32 warps)
+    constexpr int NPROD = kBlobProducers * 32;        // producer threads
     constexpr int BLOCK = NCONS + NPROD;
     constexpr int NCH = 8 / LPR;      // 16-byte chunks of a row per lane
     constexpr int RPW = 32 / LPR;     // rows per warp
@@ -755,7 +609,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             mbar_wait(&empty[buf], ((it >> 1) & 1u) ^ 1u);    // the consumers released this stage (passes at once for it < 2)
             if (ptid == 0) {
                 const int64_t e0 = (int64_t)m_cur.z * 8;
-                const uint32_t n = (dbg & 4) ? 0u : (uint32_t)m_cur.w;   // dbg: timing experiments only (FDB_BLOB_DBG)
+                const uint32_t n = (uint32_t)m_cur.w;
                 mbar_expect_tx(&full[buf], n * 18u + kBlobHdr * 4u);
                 bulk_g2s(s_hdr + buf * kBlobHdr, tile_hdr + t * kBlobHdr, kBlobHdr * 4u, &full[buf]);
                 if (n) {
@@ -764,7 +618,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                 }
             }
             mbar_wait(&cbar[buf], (it >> 1) & 1u);            // this tile's column list
-            const int C = (dbg & 2) ? 0 : (m_cur.y & 0xffff);
+            const int C = m_cur.y & 0xffff;
             const int32_t* tc = s_cols + buf * cols_cap;
             double* dst = xs + (size_t)buf * x_cap * 16;
             for (int i = ptid; i < C * 8; i += NPROD) {
@@ -801,7 +655,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             mbar_wait(&full[buf], (it >> 1) & 1u);
             const int32_t* hd = s_hdr + buf * kBlobHdr;
             const int o = hd[rin >> 3];
-            const int width = (valid && !(dbg & 1)) ? hd[(rin >> 3) + 1] - o : 0;
+            const int width = valid ? hd[(rin >> 3) + 1] - o : 0;
             const int self0 = hd[17];
             const double2* thq = s_hq + (size_t)buf * stage_entries + o * 8 + (rin & 7);
             const uint16_t* tlx = s_lx + (size_t)buf * stage_entries + o * 8 + (rin & 7);
@@ -894,41 +748,26 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6a: alpha = rho / pq ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
-// finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count, alpha kept for K6b
-// The x update of the step is DEFERRED to K6b, which streams p anyway: x += alpha p there costs a read and a write
-// of x, here it would cost those plus a read of p (one vector pass less per iteration, same arithmetic).
+// K6a: alpha = rho / pq ; x += alpha p ; r -= alpha q ; rho' = r^T (dinv r) ; rr = ||r||^2
+// finalize: beta = rho'/rho, rho = rho', convergence flag, iteration count
 // ------------------------------------------------------------------------------------------------
 // Jacobi preconditioner z = r / diag(G_f).  ONFLY (no boundary term in the sweep): the diagonal is rebuilt from
 // (H_rr, Q_rr) - 16 bytes per ROW instead of 16 bytes per (row, frequency); otherwise the precomputed 1/diag is read.
 template <typename T, int F, bool ONFLY>
-__device__ __forceinline__ double2 jacobi_load(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq, int64_t i) {
-    if constexpr (ONFLY) return __ldg(&diag_hq[i / F]);
-    else return dinv[i];
-}
-template <typename T, bool ONFLY>
-__device__ __forceinline__ T jacobi_mul(double2 d, double w2, T rv) {
+__device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
+                                          int64_t i, double w2, T rv) {
     if constexpr (ONFLY) {
+        const double2 d = __ldg(&diag_hq[i / F]);
         const double g = d.x - w2 * d.y;
         const double inv = (g == 0.0) ? 1.0 : 1.0 / g;
         return r_mul(inv, rv);
     } else {
-        return s_mul(d, rv);   // complex sweeps only
+        return s_mul(dinv[i], rv);   // complex sweeps only
     }
 }
-template <typename T, int F, bool ONFLY>
-__device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
-                                          int64_t i, double w2, T rv) {
-    return jacobi_mul<T, ONFLY>(jacobi_load<T, F, ONFLY>(dinv, diag_hq, i), w2, rv);
-}
-
-// The streaming loops below handle kVecU elements per thread and round, ALL loads of a round issued before the first
-// store: a thread of a real sweep moves 8 bytes per access, and with one element per round (the store to r ahead of
-// the next round's loads, which the compiler must keep in order) a full SM has only ~32 KB in flight - 3 TB/s.
-constexpr int kVecU = 4;
 
 template <typename T, int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
+__global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                     const T* __restrict__ q, const double2* __restrict__ dinv,
                                                     const double2* __restrict__ diag_hq, int64_t n_elems,
                                                     Scalars* __restrict__ sc, double* __restrict__ partial) {
@@ -942,41 +781,21 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
     }
     double v[3] = {0.0, 0.0, 0.0};
     if (act) {
-        const int64_t stride = (int64_t)gridDim.x * kBlock;   // a multiple of F: every element of a thread belongs to frequency f
-        for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
-            T rv[kVecU], qv[kVecU];
-            double2 d[kVecU];
-#pragma unroll
-            for (int u = 0; u < kVecU; ++u) {
-                const int64_t i = i0 + u * stride;
-                if (i < n_elems) {
-                    rv[u] = r[i];
-                    qv[u] = q[i];
-                    d[u] = jacobi_load<T, F, ONFLY>(dinv, diag_hq, i);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kVecU; ++u) {
-                const int64_t i = i0 + u * stride;
-                if (i < n_elems) {
-                    const T rn = v_sub(rv[u], s_mul(alpha, qv[u]));
-                    r[i] = rn;
-                    const T z = jacobi_mul<T, ONFLY>(d[u], w2, rn);
-                    const double2 rz = v_dot(rn, z);
-                    v[0] += rz.x;
-                    v[1] += rz.y;
-                    v[2] += v_n2(rn);
-                }
-            }
+        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+            const T rv = v_sub(r[i], s_mul(alpha, q[i]));
+            x[i] = v_add(x[i], s_mul(alpha, p[i]));
+            r[i] = rv;
+            const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, rv);
+            const double2 rz = v_dot(rv, z);
+            v[0] += rz.x;
+            v[1] += rz.y;
+            v[2] += v_n2(rv);
         }
     }
     block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
         if (sc->active[ff]) {
             const double2 rho_old = sc->rho[ff];
             const double2 rho_new = make_double2(tot[0], tot[1]);
-            const double2 pq = sc->pq[ff];
-            sc->alpha[ff] = (pq.x != 0.0 || pq.y != 0.0) ? cdiv(rho_old, pq) : make_double2(0.0, 0.0);   // what every block used above
-            sc->xpend[ff] = 1;
             double2 beta = make_double2(0.0, 0.0);
             if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
             sc->rho[ff] = rho_new;
@@ -987,45 +806,22 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
             sc->beta[ff] = beta;
         } else {
             sc->beta[ff] = make_double2(0.0, 0.0);
-            sc->xpend[ff] = 0;
         }
     });
 }
 
-// K6b: x += alpha p (the step K6a took) ; p = z + beta p
+// K6b: p = z + beta p
 template <typename T, int F, bool ONFLY>
-__global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r,
+__global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ p, const T* __restrict__ r,
                                                      const double2* __restrict__ dinv, const double2* __restrict__ diag_hq,
                                                      int64_t n_elems, const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
-    if (!sc->xpend[f]) return;   // frozen frequency: nothing pending, p is not used while alpha = 0
-    const bool act = sc->active[f] != 0;   // false: the slot converged in this iteration, only its last step is owed
-    const double2 alpha = sc->alpha[f], beta = sc->beta[f];
+    const double2 beta = sc->beta[f];
     const double w2 = sc->w2[f];
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
-        T xv[kVecU], pv[kVecU], rv[kVecU];
-        double2 d[kVecU];
-#pragma unroll
-        for (int u = 0; u < kVecU; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < n_elems) {
-                xv[u] = x[i];
-                pv[u] = p[i];
-                if (act) {
-                    rv[u] = r[i];
-                    d[u] = jacobi_load<T, F, ONFLY>(dinv, diag_hq, i);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kVecU; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < n_elems) {
-                x[i] = v_add(xv[u], s_mul(alpha, pv[u]));
-                if (act) p[i] = v_add(jacobi_mul<T, ONFLY>(d[u], w2, rv[u]), s_mul(beta, pv[u]));
-            }
-        }
+    if (!sc->active[f]) return;  // frozen frequency: p is not used while alpha = 0
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
+        const T z = jacobi_apply<T, F, ONFLY>(dinv, diag_hq, i, w2, r[i]);
+        p[i] = v_add(z, s_mul(beta, p[i]));
     }
 }
 
@@ -1338,42 +1134,36 @@ struct Launch {
             return false;
         } else {
             if (sys->n_tiles == 0) return false;
-            const int tile = sys->tile_rows;
-            const int x_cap = std::max(sys->max_tile_cols, tile);
+            const int x_cap = std::max(sys->max_tile_cols, 128);
             const int se = sys->max_tile_entries;
             const size_t smem = (size_t)2 * x_cap * 128 + (size_t)2 * se * 18 + (size_t)2 * (((x_cap + 3) & ~3) + kBlobHdr) * 4;
-            // long rows (Tet10) or a mesh without locality: the L1 kernels
-            if (tile == 64 ? smem > 110 * 1024 : smem > 220 * 1024) return false;
-            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * (tile == 64 ? 2 : 1));
-            auto launch = [&](auto kern, int threads) {
+            if (smem > 220 * 1024) return false;   // long rows (Tet10) or a mesh without locality: the L1 kernels
+            const int grid = (int)std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms);
+            auto launch = [&](auto kern, int lpr) {
                 static thread_local std::map<std::pair<int, const void*>, size_t> granted;
                 size_t& have = granted[{sys->device, (const void*)kern}];
                 if (smem > have) {
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     have = smem;
                 }
-                kern<<<grid, threads, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
+                kern<<<grid, kBlobTile * lpr + kBlobProducers * 32, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
                                                              sys->tile_cols.p, sys->tile_hdr.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
                                                              w->coef.p, (const double*)x, (double*)y, w->N, sys->n_tiles,
-                                                             x_cap, se, w->sc.p, (double*)w->partial.p, w->blob_dbg);
+                                                             x_cap, se, w->sc.p, (double*)w->partial.p);
             };
-            auto pick = [&](auto lpr, auto tl) {
-                constexpr int L = decltype(lpr)::value, T = decltype(tl)::value;
-                constexpr int TH = blob_threads(T, L);
+            auto pick = [&](auto lpr) {
+                constexpr int L = decltype(lpr)::value;
                 if constexpr (CPX) {
                     if (dot) {
-                        if (overlay) launch(k_spmv_blob<true, true, true, L, T>, TH); else launch(k_spmv_blob<true, true, false, L, T>, TH);
+                        if (overlay) launch(k_spmv_blob<true, true, true, L>, L); else launch(k_spmv_blob<true, true, false, L>, L);
                     } else {
-                        if (overlay) launch(k_spmv_blob<true, false, true, L, T>, TH); else launch(k_spmv_blob<true, false, false, L, T>, TH);
+                        if (overlay) launch(k_spmv_blob<true, false, true, L>, L); else launch(k_spmv_blob<true, false, false, L>, L);
                     }
                 } else {
-                    if (dot) launch(k_spmv_blob<false, true, false, L, T>, TH); else launch(k_spmv_blob<false, false, false, L, T>, TH);
+                    if (dot) launch(k_spmv_blob<false, true, false, L>, L); else launch(k_spmv_blob<false, false, false, L>, L);
                 }
             };
-            using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
-            using T64 = std::integral_constant<int, 64>; using T128 = std::integral_constant<int, 128>;
-            if (tile == 64) { if (w->blob_lpr == 4) pick(I4{}, T64{}); else pick(I2{}, T64{}); }
-            else            { if (w->blob_lpr == 4) pick(I4{}, T128{}); else pick(I2{}, T128{}); }
+            if (w->blob_lpr == 4) pick(std::integral_constant<int, 4>{}); else pick(std::integral_constant<int, 2>{});
             return true;
         }
     }
@@ -1382,30 +1172,9 @@ struct Launch {
         if (F <= 32) return true;                                          // the plain kernel covers it
         return (size_t)2 * stage_entries<4>(sys, w) * 20 <= 100 * 1024;   // wider: the smallest tile shape must fit
     }
-    // ---- narrow real batches: one lane per row (k_spmv_rows)
-    static bool spmv_rows(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot) {
-        if constexpr (F == 2 || F == 4 || F == 8) {
-            constexpr int BLOCK = (F == 2) ? 512 : 256;
-            constexpr int MINB = (F == 2) ? 2 : (F == 4 ? 3 : 2);
-            constexpr int UNR = (F == 8) ? 2 : 4;
-            const int64_t groups = (w->N + 31) / 32;
-            const int64_t per_block = BLOCK / 32;
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + per_block - 1) / per_block, (int64_t)sys->num_sms * MINB));
-            if (dot)
-                k_spmv_rows<F, true, BLOCK, MINB, UNR><<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p,
-                                                                                      (const double*)x, (double*)y, w->N, w->sc.p, (double*)w->partial.p);
-            else
-                k_spmv_rows<F, false, BLOCK, MINB, UNR><<<grid, BLOCK, 0, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p,
-                                                                                       (const double*)x, (double*)y, w->N, w->sc.p, (double*)w->partial.p);
-            return true;
-        } else {
-            return false;
-        }
-    }
     static void spmv(fdb_system* sys, SweepWork* w, const void* x, void* y, bool dot, bool overlay) {
         if (w->real) {
             if (w->spmv_cfg == 0 && spmv_blob<false>(sys, w, x, y, dot, false)) return;
-            if (w->spmv_cfg == 0 && w->rows_kernel && spmv_rows(sys, w, x, y, dot)) return;
             if (w->spmv_cfg < 8 && spmv_tma_cfg<false>(sys, w, x, y, dot, false)) return;
             spmv_ldg<double>(sys, w, (const double*)x, (double*)y, dot, false);
             return;
@@ -1415,11 +1184,8 @@ struct Launch {
         spmv_ldg<double2>(sys, w, (const double2*)x, (double2*)y, dot, overlay);
     }
 
-    // vector kernels: up to 8 blocks per SM, but at least 16 elements per thread - on a small mesh a thin grid leaves
-    // the reducing kernels fewer block partials to sum in their last block
     static int egrid(SweepWork* w) {
-        const int64_t want = (w->N * F + (int64_t)kBlock * 16 - 1) / ((int64_t)kBlock * 16);
-        return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)w->grid));
+        return (int)std::min<int64_t>((w->N * F + kBlock - 1) / kBlock, (int64_t)w->grid);
     }
     template <typename T>
     static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
@@ -1428,12 +1194,12 @@ struct Launch {
         spmv(sys, w, p, q, true, overlay);
         if (overlay) {
             if constexpr (std::is_same<T, double2>::value) {
-                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
             }
         } else {
-            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, p, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
         }
     }
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
@@ -1549,8 +1315,6 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
-        if (const char* e = getenv("FDB_BLOB_DBG")) w->blob_dbg = atoi(e);
-        if (getenv("FDB_NO_ROWS_KERNEL")) w->rows_kernel = false;
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);

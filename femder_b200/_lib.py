@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfemder_b200.so")
+LIB_PATH = os.environ.get("FDB_LIB_PATH") or os.path.join(_HERE, "libfemder_b200.so")   # FDB_LIB_PATH: A/B timing of two builds
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

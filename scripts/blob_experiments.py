@@ -9,11 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
 
 grid = fd.shoebox_tet4(99, 133, 74)
-names = {8: "full kernel without the L2 prefetch of the tile after next", 0: "full kernel", 1: "no compute (fill + y store)", 2: "no x fill (matrix stream + compute)", 3: "matrix stream + y store only",
+names = {0: "full kernel", 1: "no compute (fill + y store)", 2: "no x fill (matrix stream + compute)", 3: "matrix stream + y store only",
          4: "x fill + compute on a stale matrix", 5: "x fill + y store only", 7: "y store only"}
 TILES = [int(t) for t in os.environ.get("EXP_TILES", "128,64").split(",")]
 LPRS = [int(t) for t in os.environ.get("EXP_LPRS", "2,4").split(",")]
-DBGS = [int(t) for t in os.environ.get("EXP_DBGS", "0,8,1,2,3,5,7").split(",")]
+DBGS = [int(t) for t in os.environ.get("EXP_DBGS", "0,1,2,3,5,7").split(",")]
 for tile in TILES:
     os.environ["FDB_TILE_ROWS"] = str(tile)   # read when the internal order is built
     s = fd.System(0)
