@@ -124,6 +124,9 @@ struct fdb_system {
     fdb::DevBuf<int32_t> tile_cols;    // column lists (new-order ids, ascending), each padded to a multiple of 4
     fdb::DevBuf<int32_t> tile_hdr;     // [n_tiles][20] relative SELL slice offsets (17), first own row's position, column count
     fdb::DevBuf<uint16_t> sell_lidx;   // [sell_entries]
+    // block-Jacobi preconditioner: FP32 inverse of the tile's diagonal block of H (128 x 128, symmetric), per re-assembly
+    fdb::DevBuf<float> blk_inv;        // [n_tiles][8256] packed lower triangles
+    bool have_blk = false;
 
     // surface
     int64_t n_tri = 0;
@@ -160,6 +163,7 @@ void assemble_surface(fdb_system* sys);
 void build_overlay(fdb_system* sys);
 void extract_diagonal(fdb_system* sys);
 void build_sell(fdb_system* sys);    // reorder.cu: SELL values from the CSR values
+void build_block_prec(fdb_system* sys);   // reorder.cu: inverses of the tiles' diagonal blocks of H (block-Jacobi), on demand
 void build_order(fdb_system* sys);   // reorder.cu: internal order + SELL structure + tile tables, once per pattern
 void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double tol, int32_t* nodes_dev, double* weights_dev);
 void interleave_hq(fdb_system* sys, const double* H, const double* Q);

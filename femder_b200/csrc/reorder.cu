@@ -235,10 +235,92 @@ __global__ void k_sell_values(const int32_t* __restrict__ src, const double2* __
 void build_sell(fdb_system* sys) {
     FDB_REQUIRE(sys->have_order, "internal order missing");
     const int64_t n = sys->sell_entries;
+    sys->have_blk = false;   // the block-Jacobi inverses belong to the previous values
     sys->sell_hq.alloc(n ? n : 1);
     if (n) k_sell_values<<<grid_for(n, 256), 256, 0, sys->stream>>>(sys->sell_src.p, sys->hq.p, n, sys->sell_hq.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(sys->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-Jacobi preconditioner of the sweep: B_t = ((H + shift Q) restricted to the 128 rows of tile t)^-1, one dense symmetric block
+// per tile of the blob order.  The diagonal blocks of H are principal submatrices of a positive semi-definite matrix
+// whose only null vector is the constant, hence positive definite: Gauss-Jordan without pivoting, FP64 in shared
+// memory, result symmetrised and stored in FP32 as a packed lower triangle (a preconditioner needs no more: a quarter
+// of the bytes of a full FP64 block).
+// Frequency independent: at the mesh sizes a sweep resolves (k h <= 0.3) the -w^2 Q part of a 128-node block is a small
+// perturbation of its stiffness (tests/research/block_jacobi_prototype.py: same iteration counts as the exact
+// (H - w^2 Q) block, about half of point Jacobi's).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlk = 128;
+constexpr int kBlkPacked = kBlk * (kBlk + 1) / 2;   // 8256 floats = 33 024 bytes per tile
+__global__ void __launch_bounds__(256) k_block_inverse(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx,
+                                                        const double2* __restrict__ sell_hq, int64_t n_rows, double shift, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* A = reinterpret_cast<double*>(smem_raw);          // [128][128]
+    double* colk = A + kBlk * kBlk;                            // [128]
+    double* rowk = colk + kBlk;                                // [128]
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * kBlk;
+    const int rows = (int)min((int64_t)kBlk, n_rows - row0);
+    for (int i = tid; i < kBlk * kBlk; i += 256) A[i] = 0.0;
+    __syncthreads();
+    if (tid < kBlk) {
+        if (tid < rows) {
+            const int64_t r = row0 + tid;
+            const int64_t slice = r >> 3;
+            const int off = sell_off[slice];
+            const int width = sell_off[slice + 1] - off;
+            for (int k = 0; k < width; ++k) {
+                const int64_t e = ((int64_t)off + k) * 8 + (r & 7);
+                const int64_t c = sell_idx[e];
+                if (c >= row0 && c < row0 + kBlk) {
+                    const double2 m = sell_hq[e];   // padding entries add 0
+                    A[tid * kBlk + (int)(c - row0)] += m.x + shift * m.y;
+                }
+            }
+        } else {
+            A[tid * kBlk + tid] = 1.0;   // rows past the end of the last tile
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < kBlk; ++k) {
+        if (tid < kBlk) { colk[tid] = A[tid * kBlk + k]; rowk[tid] = A[k * kBlk + tid]; }
+        __syncthreads();
+        const double pv = colk[k];
+        const double pinv = (pv != 0.0) ? 1.0 / pv : 1.0;
+        for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
+            const int i = idx >> 7, j = idx & (kBlk - 1);
+            double v;
+            if (i == k) v = (j == k) ? pinv : rowk[j] * pinv;
+            else if (j == k) v = -colk[i] * pinv;
+            else v = A[idx] - colk[i] * (rowk[j] * pinv);
+            A[idx] = v;
+        }
+        __syncthreads();
+    }
+    // lower triangle, row-major: entry (i, k <= i) at i (i + 1) / 2 + k - the product kernel reads it conflict-free both
+    // along rows and along columns (triangular numbers mod 32 are a permutation of 0..31)
+    float* o = out + (int64_t)blockIdx.x * kBlkPacked;
+    for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
+        const int i = idx >> 7, j = idx & (kBlk - 1);
+        if (j <= i) o[i * (i + 1) / 2 + j] = (float)(0.5 * (A[i * kBlk + j] + A[j * kBlk + i]));
+    }
+}
+
+void build_block_prec(fdb_system* sys) {
+    if (sys->have_blk) return;
+    FDB_REQUIRE(sys->have_order && sys->tile_rows == kBlk && sys->n_tiles > 0, "block-Jacobi needs the 128-row tiles of the internal order");
+    sys->blk_inv.alloc((size_t)sys->n_tiles * kBlkPacked);
+    const size_t smem = (size_t)(kBlk * kBlk + 2 * kBlk) * sizeof(double);
+    FDB_CUDA(cudaFuncSetAttribute(k_block_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // H + shift Q with a small positive shift (w = 2 pi 50 Hz, far below a block's own eigenvalues): a tile that holds a whole
+    // connected component (meshes of up to 128 nodes) has a singular H block, and H + shift Q is positive definite always
+    const double shift = (2.0 * 3.14159265358979323846 * 50.0) * (2.0 * 3.14159265358979323846 * 50.0);
+    k_block_inverse<<<(unsigned)sys->n_tiles, 256, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->n_nodes,
+                                                                         shift, sys->blk_inv.p);
+    FDB_CUDA(cudaGetLastError());
+    sys->have_blk = true;
 }
 
 }  // namespace fdb

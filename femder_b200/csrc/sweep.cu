@@ -68,6 +68,9 @@ struct SweepWork {
     int tma_stage_entries[3] = {0, 0, 0};
     int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
     int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
+    int precond = 0;              // 0 Jacobi, 1 block-Jacobi (real sweeps, F <= 16, 128-row tiles)
+    bool graph_precond = false;
+    DevBuf<float> z32;            // [N][F] preconditioned residual of the block-Jacobi path
     bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
     int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
     bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
@@ -922,6 +925,40 @@ __device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, cons
     return jacobi_mul<T, ONFLY>(jacobi_load<T, F, ONFLY>(dinv, diag_hq, i), w2, rv);
 }
 
+// last-block finalisation of K6a: beta = rho'/rho, rho = rho', convergence flag, iteration count, alpha kept for K6b
+__device__ __forceinline__ void fin_update(Scalars* __restrict__ sc, int ff, const double* tot) {
+    if (sc->active[ff]) {
+        const double2 rho_old = sc->rho[ff];
+        const double2 rho_new = make_double2(tot[0], tot[1]);
+        const double2 pq = sc->pq[ff];
+        sc->alpha[ff] = (pq.x != 0.0 || pq.y != 0.0) ? cdiv(rho_old, pq) : make_double2(0.0, 0.0);   // what every block used
+        sc->xpend[ff] = 1;
+        double2 beta = make_double2(0.0, 0.0);
+        if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
+        sc->rho[ff] = rho_new;
+        sc->rr[ff] = tot[2];
+        sc->iters[ff] += 1;
+        const bool conv = !(tot[2] > sc->tol2 * sc->bb[ff]);  // also stops on NaN
+        if (conv) { sc->active[ff] = 0; beta = make_double2(0.0, 0.0); }
+        sc->beta[ff] = beta;
+    } else {
+        sc->beta[ff] = make_double2(0.0, 0.0);
+        sc->xpend[ff] = 0;
+    }
+}
+// ... of the slot (re)load: rho = r^T z, activate the slot if its residual is above tolerance
+__device__ __forceinline__ void fin_start(Scalars* __restrict__ sc, int ff, const double* tot) {
+    if (!sc->reset[ff]) return;
+    sc->rho[ff] = make_double2(tot[0], tot[1]);
+    sc->rr[ff] = tot[2];
+    sc->beta[ff] = make_double2(0.0, 0.0);
+    sc->pq[ff] = make_double2(0.0, 0.0);
+    sc->iters[ff] = 0;
+    if (sc->bb_from_r0) sc->bb[ff] = tot[2];
+    sc->active[ff] = (tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
+    sc->reset[ff] = 0;
+}
+
 // The streaming loops below handle kVecU elements per thread and round, ALL loads of a round issued before the first
 // store: a thread of a real sweep moves 8 bytes per access, and with one element per round (the store to r ahead of
 // the next round's loads, which the compiler must keep in order) a full SM has only ~32 KB in flight - 3 TB/s.
@@ -970,26 +1007,7 @@ __global__ void __launch_bounds__(kBlock) k_update(T* __restrict__ r,
             }
         }
     }
-    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) {
-        if (sc->active[ff]) {
-            const double2 rho_old = sc->rho[ff];
-            const double2 rho_new = make_double2(tot[0], tot[1]);
-            const double2 pq = sc->pq[ff];
-            sc->alpha[ff] = (pq.x != 0.0 || pq.y != 0.0) ? cdiv(rho_old, pq) : make_double2(0.0, 0.0);   // what every block used above
-            sc->xpend[ff] = 1;
-            double2 beta = make_double2(0.0, 0.0);
-            if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
-            sc->rho[ff] = rho_new;
-            sc->rr[ff] = tot[2];
-            sc->iters[ff] += 1;
-            const bool conv = !(tot[2] > sc->tol2 * sc->bb[ff]);  // also stops on NaN
-            if (conv) { sc->active[ff] = 0; beta = make_double2(0.0, 0.0); }
-            sc->beta[ff] = beta;
-        } else {
-            sc->beta[ff] = make_double2(0.0, 0.0);
-            sc->xpend[ff] = 0;
-        }
-    });
+    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) { fin_update(sc, ff, tot); });
 }
 
 // K6b: x += alpha p (the step K6a took) ; p = z + beta p
@@ -1024,6 +1042,157 @@ __global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ x, T* __rest
             if (i < n_elems) {
                 x[i] = v_add(xv[u], s_mul(alpha, pv[u]));
                 if (act) p[i] = v_add(jacobi_mul<T, ONFLY>(d[u], w2, rv[u]), s_mul(beta, pv[u]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 with the BLOCK-JACOBI preconditioner (real sweeps, F <= 16): z = B_t r on every 128-row tile of the blob order, B_t the
+// FP32 inverse of the tile's diagonal block of H (reorder.cu).  About half of point Jacobi's iterations for 0.5 GB more
+// per iteration.  K6a becomes a tile kernel: r -= alpha q in FP64, the tile's new residual rounded to FP32 in shared
+// memory, z = B r as a 128 x 128 x F FP32 product out of shared memory (B arrives by 16-byte cp.async while the
+// residual is updated), z stored in FP32 (K6b reads it instead of r: the vector passes stay at 8), rho' = r^T z and
+// ||r||^2 accumulated in FP64.  Fixed summation order everywhere: a sweep stays bit-reproducible.
+// START: the same kernel loads a slot (r as it stands, no q): p = z, rho, ||r||^2 for the slots flagged in sc.reset.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBjTile = 128;
+constexpr int kBjPacked = kBjTile * (kBjTile + 1) / 2;   // floats of a packed lower triangle (reorder.cu)
+template <int F, bool START>
+__global__ void __launch_bounds__(256, 3)
+k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* __restrict__ binv, float* __restrict__ z32,
+            double* __restrict__ p_start, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    static_assert(F >= 1 && F <= 16, "block-Jacobi kernels cover batches up to 16");
+    constexpr int EPT = (kBjTile * F + 255) / 256;     // elements of a tile per thread
+    constexpr int CPT = (F >= 2) ? F / 2 : 1;          // columns per thread in the product
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Bs = reinterpret_cast<float*>(smem_raw);                   // packed lower triangle: (i, k <= i) at i (i + 1) / 2 + k
+    float* r32 = Bs + kBjPacked;                                      // [128][F]
+    float* zp = r32 + kBjTile * F;                                    // [128][F]
+    const int tid = threadIdx.x;
+    const int f = tid % F;
+    const bool act = START ? (sc->reset[f] != 0) : (sc->active[f] != 0);
+    double alpha = 0.0;
+    if (!START && act) {
+        const double2 pq = sc->pq[f];
+        if (pq.x != 0.0 || pq.y != 0.0) alpha = cdiv(sc->rho[f], pq).x;
+    }
+    const int rp = tid & 63, ch = (tid >> 6) & 1, kh = tid >> 7;
+    const int c0 = ch * CPT;
+    const bool prod = (F >= 2) || ch == 0;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const float* bt = binv + t * (int64_t)kBjPacked;
+        for (int i = tid; i < kBjPacked / 4; i += 256) cp_async16(Bs + i * 4, bt + i * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int64_t base = t * (int64_t)kBjTile * F;
+        const int n_el = (int)min((int64_t)kBjTile, n_rows - t * kBjTile) * F;
+        double rn[EPT];
+        {
+            double rv[EPT], qv[EPT];
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const int e = tid + 256 * u;
+                rv[u] = 0.0; qv[u] = 0.0;
+                if (e < n_el) {
+                    rv[u] = r[base + e];
+                    if (!START) qv[u] = q[base + e];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const int e = tid + 256 * u;
+                rn[u] = rv[u] - alpha * qv[u];
+                if (e < kBjTile * F) r32[e] = (act && e < n_el) ? (float)rn[u] : 0.0f;
+                if (!START && act && e < n_el) r[base + e] = rn[u];
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        float a0[CPT], a1[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) a0[c] = a1[c] = 0.0f;
+        if (prod) {
+            // B(row, k) = B(k, row): whichever of the two lies in the stored triangle.  Lanes of a warp hold 32 consecutive
+            // rows starting at a multiple of 32, so both the row walk (offsets T(row) + k) and the column walk (T(k) + row) hit
+            // 32 different banks.
+            const int k0 = kh * (kBjTile / 2);
+            const int r0i = rp, r1i = rp + 64;
+            const int t0 = r0i * (r0i + 1) / 2, t1 = r1i * (r1i + 1) / 2;
+#pragma unroll 4
+            for (int k = k0; k < k0 + kBjTile / 2; ++k) {
+                const int tk = k * (k + 1) / 2;
+                const float b0 = Bs[(k <= r0i) ? t0 + k : tk + r0i], b1 = Bs[(k <= r1i) ? t1 + k : tk + r1i];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const float rr = r32[k * F + c0 + c];
+                    a0[c] += b0 * rr;
+                    a1[c] += b1 * rr;
+                }
+            }
+            if (kh == 1) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) { zp[rp * F + c0 + c] = a0[c]; zp[(rp + 64) * F + c0 + c] = a1[c]; }
+            }
+        }
+        __syncthreads();
+        if (prod && kh == 0) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                zp[rp * F + c0 + c] = a0[c] + zp[rp * F + c0 + c];
+                zp[(rp + 64) * F + c0 + c] = a1[c] + zp[(rp + 64) * F + c0 + c];
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const int e = tid + 256 * u;
+                if (e < n_el) {
+                    const float z = zp[e];
+                    if constexpr (START) p_start[base + e] = (double)z;   // first search direction of the slot
+                    else z32[base + e] = z;
+                    v[0] += rn[u] * (double)z;
+                    v[2] += rn[u] * rn[u];
+                }
+            }
+        }
+        __syncthreads();   // the next tile overwrites Bs, r32, zp
+    }
+    if constexpr (START) {
+        block_reduce_finalize<F, 3, 256>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) { fin_start(sc, ff, tot); });
+    } else {
+        block_reduce_finalize<F, 3, 256>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) { fin_update(sc, ff, tot); });
+    }
+}
+
+// K6b with z read from the FP32 array K6a left: x += alpha p ; p = z + beta p.
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pupdate_bj(double* __restrict__ x, double* __restrict__ p, const float* __restrict__ z32,
+                                                        int64_t n_elems, const Scalars* __restrict__ sc) {
+    const int f = threadIdx.x % F;
+    if (!sc->xpend[f]) return;
+    const bool act = sc->active[f] != 0;
+    const double alpha = sc->alpha[f].x, beta = sc->beta[f].x;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
+        double xv[kVecU], pv[kVecU];
+        float zv[kVecU];
+#pragma unroll
+        for (int u = 0; u < kVecU; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n_elems) {
+                xv[u] = x[i];
+                pv[u] = p[i];
+                if (act) zv[u] = z32[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecU; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n_elems) {
+                x[i] = xv[u] + alpha * pv[u];
+                if (act) p[i] = (double)zv[u] + beta * pv[u];
             }
         }
     }
@@ -1135,17 +1304,7 @@ __global__ void __launch_bounds__(kBlock) k_start(T* __restrict__ p, const T* __
             v[2] += v_n2(rv);
         }
     }
-    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) {
-        if (!sc->reset[ff]) return;
-        sc->rho[ff] = make_double2(tot[0], tot[1]);
-        sc->rr[ff] = tot[2];
-        sc->beta[ff] = make_double2(0.0, 0.0);
-        sc->pq[ff] = make_double2(0.0, 0.0);
-        sc->iters[ff] = 0;
-        if (sc->bb_from_r0) sc->bb[ff] = tot[2];
-        sc->active[ff] = (tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
-        sc->reset[ff] = 0;
-    });
+    block_reduce_finalize<F, 3, kBlock>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) { fin_start(sc, ff, tot); });
 }
 
 // true residual norm of what is returned: rt = ||b - q||^2 with b rebuilt, q = G x
@@ -1415,6 +1574,21 @@ struct Launch {
         spmv_ldg<double2>(sys, w, (const double2*)x, (double2*)y, dot, overlay);
     }
 
+    // block-Jacobi tile kernels: 48 KB of shared memory per block at F = 16 (packed FP32 block + two 128 x F tiles)
+    static size_t bj_smem() { return (size_t)kBjPacked * 4 + (size_t)2 * kBjTile * (F <= 16 ? F : 16) * 4; }
+    static int bj_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * 3)); }
+    static void bj_prepare(fdb_system* sys, SweepWork* w) {
+        if constexpr (F <= 16) {
+            build_block_prec(sys);
+            w->z32.alloc((size_t)w->N * F);
+            static thread_local std::map<int, bool> done;
+            if (!done[sys->device]) {
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem()));
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem()));
+                done[sys->device] = true;
+            }
+        }
+    }
     // vector kernels: up to 8 blocks per SM, but at least 16 elements per thread - on a small mesh a thin grid leaves
     // the reducing kernels fewer block partials to sum in their last block
     static int egrid(SweepWork* w) {
@@ -1426,6 +1600,14 @@ struct Launch {
         const int64_t ne = w->N * F;
         T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *q = (T*)w->q.p;
         spmv(sys, w, p, q, true, overlay);
+        if constexpr (std::is_same<T, double>::value && F <= 16) {
+            if (w->precond == 1) {
+                k_update_bj<F, false><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, (const double*)q, sys->blk_inv.p, w->z32.p, nullptr,
+                                                                                    w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
+                k_pupdate_bj<F><<<egrid(w), kBlock, 0, sys->stream>>>((double*)x, (double*)p, w->z32.p, ne, w->sc.p);
+                return;
+            }
+        }
         if (overlay) {
             if constexpr (std::is_same<T, double2>::value) {
                 k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
@@ -1468,7 +1650,16 @@ struct Launch {
             k_sub<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(r, qq, ne, w->sc.p);
             nk += 2;
         }
-        if (overlay) {
+        bool started = false;
+        if constexpr (std::is_same<T, double>::value && F <= 16) {
+            if (w->precond == 1) {
+                k_update_bj<F, true><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, nullptr, sys->blk_inv.p, w->z32.p, (double*)p,
+                                                                                   w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
+                started = true;
+            }
+        }
+        if (started) {
+        } else if (overlay) {
             if constexpr (std::is_same<T, double2>::value)
                 k_start<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
         } else {
@@ -1593,7 +1784,8 @@ static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, cons
 }
 
 static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool overlay) {
-    if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay && w->graph_real == w->real) return;
+    if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay && w->graph_real == w->real &&
+        w->graph_precond == (w->precond == 1)) return;
     if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
     cudaGraph_t g = nullptr;
     FDB_CUDA(cudaStreamBeginCapture(sys->stream, cudaStreamCaptureModeThreadLocal));
@@ -1608,7 +1800,7 @@ static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool o
     cudaError_t e = cudaGraphInstantiate(&w->graph, g, 0);
     cudaGraphDestroy(g);
     FDB_CUDA(e);
-    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real;
+    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real; w->graph_precond = (w->precond == 1);
 }
 
 static void k_jacobi_launch(fdb_system* sys, SweepWork* w, int F) {
@@ -1755,6 +1947,12 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     }
     w->real = real;
     res->real_arithmetic = real ? 1 : 0;
+    // Preconditioner: block-Jacobi over the 128-row tiles of the internal order where it is implemented (real sweeps in
+    // batches of up to 16), point Jacobi otherwise.  prm->precond: 0 = Jacobi, 1 = block-Jacobi where possible.
+    static const bool no_bj = getenv("FDB_NO_BLOCK_JACOBI") != nullptr;   // A/B aid
+    const bool use_bj = prm->precond == 1 && !no_bj && real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;
+    w->precond = use_bj ? 1 : 0;
+    if (use_bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
     w->n_rn = (int)rn_nodes.size();
     if (general_rhs) {
         w->rn_nodes.alloc(rn_nodes.size()); w->rn_ptr.alloc(rn_ptr.size()); w->rn_vec.alloc(rn_vec.size()); w->rn_val.alloc(rn_val.size());
@@ -1925,6 +2123,8 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             if (F2 < F) {
                 SweepWork* w2 = new_work(sys, F2);
                 w2->real = w->real;
+                w2->precond = w->precond;
+                if (w2->precond == 1) { FDB_DISPATCH_F(F2, bj_prepare(sys, w2)); }
                 SlotMap map;
                 Scalars h2;
                 memset(&h2, 0, sizeof(h2));

@@ -77,7 +77,7 @@ def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
 
 class FEM3D:
     def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=200000, batch="auto",
-                 check_every=32, warm_start=False, compat_complex64=False, shard=True):
+                 check_every=32, warm_start=False, compat_complex64=False, shard=True, precond="block"):
         self.BC = BC
         if BC is not None:
             self.mu = BC.mu
@@ -126,6 +126,7 @@ class FEM3D:
         self.max_iter = max_iter
         self.batch = batch
         self.check_every = check_every
+        self.precond = precond
         self.warm_start = warm_start
         self.compat_complex64 = compat_complex64
         self.shard = shard  # under torch.distributed: split the frequencies over the ranks and gather the rows at the end
@@ -282,7 +283,7 @@ class FEM3D:
         owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch,
-                                  check_every=self.check_every, warm_start=self.warm_start, rhs_vecs=rhs_vecs,
+                                  check_every=self.check_every, warm_start=self.warm_start, precond=self.precond, rhs_vecs=rhs_vecs,
                                   rhs_coef=None if rhs_coef is None else rhs_coef[:, owned])
         self.stats = stats
         if world > 1:

@@ -260,6 +260,35 @@ def test_real_arithmetic_narrow_batches(gpu_lib, batch, monkeypatch):
     assert sc.real_arithmetic and _rel_rows(a, c).max() < 1e-8
 
 
+@pytest.mark.parametrize("batch", [16, 4, 1])
+def test_block_jacobi_preconditioner(gpu_lib, batch):
+    """Block-Jacobi (FP32 inverses of the 128-row diagonal blocks of H, real sweeps): same solutions as point Jacobi, true
+    residual checked with scipy, clearly fewer iterations, bit-equal repeats; the narrowing tail keeps the preconditioner."""
+    from femder_b200 import System
+    from femder_b200.mesh import shoebox_tet4
+    grid = shoebox_tet4(26, 34, 22, jitter=0.2)
+    s = System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.assemble_volume(1.21, 343.0)
+    H, Q = s.get_HQ()
+    freq = np.linspace(30.0, 260.0, 21)
+    w = 2 * np.pi * freq
+    mu = np.zeros((0, len(freq)), dtype=complex)
+    src = grid.closest_node([1.0, 1.0, 1.2])
+    a, _, sa = s.sweep(w, mu, [src], [1e-4], tol=1e-10, batch=batch, check_every=16, precond="block", max_iter=100000)
+    b, _, sb = s.sweep(w, mu, [src], [1e-4], tol=1e-10, batch=batch, check_every=16, precond="jacobi", max_iter=100000)
+    assert sa.real_arithmetic and sb.real_arithmetic and sa.n_unconverged == 0 and sb.n_unconverged == 0
+    assert _rel_rows(a, b).max() < 1e-7
+    assert sa.iters.sum() < 0.75 * sb.iters.sum(), (sa.iters.sum(), sb.iters.sum())
+    q = np.zeros(grid.NumNosC, dtype=complex); q[src] = 1e-4
+    for n in (0, 10, 20):
+        G = O.system_matrix(H, Q, [], [], w[n])
+        rhs = -1j * w[n] * q
+        assert np.linalg.norm(rhs - G @ a[n]) / np.linalg.norm(rhs) < 1e-9
+    a2, _, sa2 = s.sweep(w, mu, [src], [1e-4], tol=1e-10, batch=batch, check_every=16, precond="block", max_iter=100000)
+    assert np.array_equal(a, a2) and np.array_equal(sa.iters, sa2.iters)
+
+
 def test_results_land_at_their_frequency_index(gpu_lib):
     """Slots are loaded in descending frequency order and refilled as they converge: outputs stay in input order."""
     from conftest import Golden
