@@ -264,31 +264,47 @@ def run_ours(args):
                "d2h_bytes_per_step": int(d2h_holder[0]), "ms_per_step": ms_e / args.steps,
                "call": "FEM3D.compute(keep_pN=False): mesh upload, pattern + assembly, receiver location, sweep, receiver read-back"}
 
-    # ---- roofline of the dominant kernel (fused multi-frequency SpMV), measured live with CUDA events ----
+    # ---- rooflines of the three kernels of a solver iteration, each measured live with CUDA events on the launching
+    #      stream (50 back-to-back launches on resident vectors, working set > L2); `roofline` = the dominant one ----
     peaks, peak_src = measured_peaks()
     reps = 50
     real = F >= 4  # the rigid workload runs in real arithmetic whenever the batch width allows it
-    sysm.spmv_bench(F, 5, with_boundary=False, real=real)  # fills the resident vectors, warms up (the sweep's variant)
-    barrier()
-    with torch.cuda.stream(stream):
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        nbytes = sysm.spmv_enqueue(F, reps, with_boundary=False, real=real)
-        a1.record(stream)
-    torch.cuda.synchronize()
-    spmv_ms = a0.elapsed_time(a1) / reps
-    achieved = nbytes / (spmv_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    bj = real and F <= 16
+    traffic_file = {}
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.isfile(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic_file = json.load(open(tp))
         except Exception:
-            traffic = None
-    roofline = {"kernel": "k_spmv_blob (fused multi-frequency SpMV, shared-memory x tiles, batch %d, %s arithmetic)" % (F, "real" if real else "complex"), "bound": "hbm", "achieved": achieved,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                "algorithmic_bytes_per_launch": int(nbytes), "us_per_launch": spmv_ms * 1e3, "peak_source": peak_src,
-                "how": f"{reps} back-to-back launches on resident vectors (matrix+vectors 0.56 GB > L2), torch CUDA events on the launching stream"}
+            traffic_file = {}
+    names = {0: ("K5", "k_spmv_blob (fused multi-frequency SpMV, shared-memory x tiles)"),
+             1: ("K6a", "k_update_bj (residual update + block-Jacobi z = B r out of shared memory + rho, ||r||^2)" if bj
+                 else "k_update (residual update + Jacobi + rho, ||r||^2)"),
+             2: ("K6b", "k_pupdate_bj (x += alpha p, p = z + beta p)" if bj else "k_pupdate (x += alpha p, p = z + beta p)")}
+    sysm.iteration_enqueue(F, 1, -1, real=real, block_jacobi=bj)
+    kernels = []
+    for which in (0, 1, 2):
+        sysm.iteration_enqueue(F, 5, which, real=real, block_jacobi=bj)   # warm-up
+        barrier()
+        with torch.cuda.stream(stream):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            nbytes = sysm.iteration_enqueue(F, reps, which, real=real, block_jacobi=bj)
+            a1.record(stream)
+        torch.cuda.synchronize()
+        us = a0.elapsed_time(a1) / reps * 1e3
+        achieved = nbytes / (us * 1e-6) / 1e9
+        kernels.append({"id": names[which][0], "kernel": names[which][1] + ", batch %d, %s arithmetic" % (F, "real" if real else "complex"),
+                        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                        "traffic": traffic_file.get(names[which][0]), "algorithmic_bytes_per_launch": int(nbytes), "us_per_launch": us})
+    dom = max(kernels, key=lambda k: k["us_per_launch"])
+    roofline = dict(dom)
+    roofline.update({"peak_source": peak_src,
+                     "how": f"{reps} back-to-back launches on resident vectors (matrix + vectors > L2), torch CUDA events on the launching stream",
+                     "iteration_kernels": kernels,
+                     "iteration": {"us": sum(k["us_per_launch"] for k in kernels),
+                                   "algorithmic_bytes": sum(k["algorithmic_bytes_per_launch"] for k in kernels),
+                                   "frac": sum(k["algorithmic_bytes_per_launch"] for k in kernels) / (sum(k["us_per_launch"] for k in kernels) * 1e-6) / 1e9 / peaks["hbm_gbs"]}})
 
     # ---- the CPU baseline's own mesh (config 1, 21 735 DOF) through the same public call: the two arms' `value`s are on
     #      different problem sizes (the reference cannot factorise 1M DOF), this one is the like-for-like comparison

@@ -65,6 +65,7 @@ SIGNATURES = {
     "fdb_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i64p]),
     "fdb_spmv_enqueue": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i64p]),
+    "fdb_iteration_enqueue": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
 void run_spmv(fdb_system* sys, int F, const double* omega, const double* mu, const double* x, double* y);
 void run_spmv_bench(fdb_system* sys, int F, int reps, int flags, double* ms_per_launch, int64_t* bytes);
 void run_spmv_enqueue(fdb_system* sys, int F, int reps, int flags, int64_t* bytes);
+void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int which, int64_t* bytes);
 
 struct DeviceGuard {
     int prev = 0;
@@ -383,6 +384,15 @@ int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int flags, int64_t* a
     FDB_SYS(sys);
     FDB_REQUIRE(reps > 0, "reps must be positive");
     fdb::run_spmv_enqueue(sys, batch, reps, flags, algorithmic_bytes);
+    FDB_API_END
+}
+
+int fdb_iteration_enqueue(fdb_system* sys, int batch, int reps, int flags, int which, int64_t* algorithmic_bytes) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    FDB_REQUIRE(which < 0 || reps > 0, "reps must be positive");
+    FDB_REQUIRE(which >= -1 && which <= 2, "which must be -1 (prepare), 0 (K5), 1 (K6a) or 2 (K6b)");
+    fdb::run_iteration_enqueue(sys, batch, reps, flags, which, algorithmic_bytes);
     FDB_API_END
 }
 

@@ -1595,28 +1595,39 @@ struct Launch {
         const int64_t want = (w->N * F + (int64_t)kBlock * 16 - 1) / ((int64_t)kBlock * 16);
         return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)w->grid));
     }
+    // K6a / K6b of one iteration (which = 1 / 2), K5 is spmv() above
     template <typename T>
-    static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
+    static void vec_kernel_t(fdb_system* sys, SweepWork* w, bool overlay, int which) {
         const int64_t ne = w->N * F;
         T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *q = (T*)w->q.p;
-        spmv(sys, w, p, q, true, overlay);
         if constexpr (std::is_same<T, double>::value && F <= 16) {
             if (w->precond == 1) {
-                k_update_bj<F, false><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, (const double*)q, sys->blk_inv.p, w->z32.p, nullptr,
-                                                                                    w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
-                k_pupdate_bj<F><<<egrid(w), kBlock, 0, sys->stream>>>((double*)x, (double*)p, w->z32.p, ne, w->sc.p);
+                if (which == 1)
+                    k_update_bj<F, false><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, (const double*)q, sys->blk_inv.p, w->z32.p, nullptr,
+                                                                                        w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
+                else
+                    k_pupdate_bj<F><<<egrid(w), kBlock, 0, sys->stream>>>((double*)x, (double*)p, w->z32.p, ne, w->sc.p);
                 return;
             }
         }
         if (overlay) {
             if constexpr (std::is_same<T, double2>::value) {
-                k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-                k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+                if (which == 1) k_update<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+                else k_pupdate<T, F, false><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
             }
         } else {
-            k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
-            k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
+            if (which == 1) k_update<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(r, q, w->dinv.p, sys->diag_hq.p, ne, w->sc.p, (double*)w->partial.p);
+            else k_pupdate<T, F, true><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, r, w->dinv.p, sys->diag_hq.p, ne, w->sc.p);
         }
+    }
+    static void vec_kernel(fdb_system* sys, SweepWork* w, bool overlay, int which) {
+        if (w->real) vec_kernel_t<double>(sys, w, false, which); else vec_kernel_t<double2>(sys, w, overlay, which);
+    }
+    template <typename T>
+    static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
+        spmv(sys, w, w->p.p, w->q.p, true, overlay);
+        vec_kernel_t<T>(sys, w, overlay, 1);
+        vec_kernel_t<T>(sys, w, overlay, 2);
     }
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
         if (w->real) iteration_t<double>(sys, w, false); else iteration_t<double2>(sys, w, overlay);
@@ -2273,6 +2284,53 @@ void run_spmv_enqueue(fdb_system* sys, int F, int reps, int flags, int64_t* byte
     for (int i = 0; i < reps; ++i) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, has_overlay)); }
     FDB_CUDA(cudaGetLastError());
     if (bytes) *bytes = spmv_algorithmic_bytes(sys, F, with_boundary, w->real);
+}
+
+// One kernel of a solver iteration, `reps` times on resident synthetic vectors, enqueued on the system's stream without
+// synchronising so the caller brackets it with its own CUDA events.  which: -1 = prepare (fill the vectors, every slot
+// active), 0 = K5 (SpMV with its dot-product epilogue), 1 = K6a (k_update / k_update_bj), 2 = K6b (k_pupdate / k_pupdate_bj).
+// flags: FDB_SPMV_REAL, FDB_ITER_BLOCK_JACOBI.  bytes = the kernel's algorithmic bytes per launch.
+void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int which, int64_t* bytes) {
+    FDB_REQUIRE(!(flags & 1), "the iteration bench covers rigid-wall sweeps");
+    SweepWork* w = get_work(sys, F);
+    w->real = bench_real(sys, w, F, flags);
+    const bool bj = (flags & 4) && w->real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;
+    w->precond = bj ? 1 : 0;
+    if (bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
+    const int64_t N = w->N, ne = N * F;
+    const int64_t vb = (w->real ? 8 : 16) * ne;   // bytes of one vector pass
+    if (which < 0) {
+        Scalars h;
+        memset(&h, 0, sizeof(h));
+        std::vector<double2> coef((size_t)std::max(1, w->n_groups) * F, make_double2(0.0, 0.0));
+        for (int f = 0; f < F; ++f) {
+            fill_slot(h, coef, F, w->n_groups, f, 2.0 * 3.141592653589793 * (100.0 + f), nullptr, 0.0);
+            h.active[f] = 1; h.xpend[f] = 1;
+            h.rho[f] = make_double2(1.0, 0.0); h.pq[f] = make_double2(1e6, 0.0);
+            h.alpha[f] = make_double2(1e-6, 0.0); h.beta[f] = make_double2(0.5, 0.0);
+            h.bb[f] = 0.0;   // never "converged": rr > tol2 * 0
+        }
+        h.tol2 = 1.0;
+        upload_scalars(sys, w, h, coef);
+        const int64_t n2 = w->real ? (ne + 1) / 2 : ne;   // buffers are sized in double2
+        k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->p.p, n2);
+        k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->r.p, n2);
+        k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->x.p, n2);
+        k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->q.p, n2);
+        if (bj) FDB_CUDA(cudaMemsetAsync(w->z32.p, 0, (size_t)ne * sizeof(float), sys->stream));
+        FDB_CUDA(cudaGetLastError());
+        return;
+    }
+    for (int i = 0; i < reps; ++i) {
+        if (which == 0) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, false)); }
+        else { FDB_DISPATCH_F(F, vec_kernel(sys, w, false, which)); }
+    }
+    FDB_CUDA(cudaGetLastError());
+    if (bytes) {
+        if (which == 0) *bytes = spmv_algorithmic_bytes(sys, F, false, w->real);
+        else if (which == 1) *bytes = bj ? 3 * vb + 4 * ne + sys->n_tiles * (int64_t)kBjPacked * 4 : 3 * vb + 16 * N;
+        else *bytes = bj ? 4 * vb + 4 * ne : 5 * vb + 16 * N;
+    }
 }
 
 void run_spmv_bench(fdb_system* sys, int F, int reps, int flags, double* ms_per_launch, int64_t* bytes) {

@@ -46,7 +46,7 @@ def launches():
         agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(OUT, f"{R}_launches.md"), "w") as f:
-        f.write(f"# {R}: kernel launch list of `bench.py --steps 1 --warmup 3 --no-e2e --no-cpu`\n\n"
+        f.write(f"# {R}: kernel launch list of `bench.py --stride 15 --steps 1 --warmup 3 --no-e2e --no-cpu` (a step of 32 frequencies keeps the run under ncu short)\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 900` (cold-cache, serialised launches: compare SHARES).\n\n"
                 "| kernel | launches | mean us | share of captured time |\n|---|---:|---:|---:|\n")
         for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -60,9 +60,13 @@ def launches():
 
 def capture(name, title):
     rep = os.path.join(GO, f"{name}_{R}.ncu-rep")
-    if not os.path.isfile(rep):
+    rawf = os.path.join(GO, f"{name}_{R}.raw.csv")
+    if os.path.isfile(rawf) and os.path.getsize(rawf):
+        raw = open(rawf).read()
+    elif os.path.isfile(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, d = rows[0], rows[1], rows[2]
     vals = {}
@@ -83,10 +87,19 @@ def to_bytes(v):
 
 
 launches()
-v = capture("spmv_real16", "fused multi-frequency SpMV, batch 16, real arithmetic (the variant the rigid benchmark sweep launches)")
-capture("spmv_cpx8", "fused multi-frequency SpMV, batch 8, complex arithmetic (admittance sweeps)")
-if v:
-    tr = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
-    json.dump({"kernel": "k_spmv_blob<real, F=16>", "dram_bytes_per_launch": tr, "source": f"profiles/{R}_spmv_real16.md"},
-              open(os.path.join(OUT, "spmv_traffic.json"), "w"))
+traffic = {}
+for name, kid, title in (("spmv_real16", "K5", "K5 fused multi-frequency SpMV k_spmv_blob, batch 16, real arithmetic (the variant the rigid benchmark sweep launches)"),
+                         ("update_bj_real16", "K6a", "K6a k_update_bj, batch 16 real: residual update + block-Jacobi z = B r out of shared memory + reductions"),
+                         ("pupdate_bj_real16", "K6b", "K6b k_pupdate_bj, batch 16 real: x += alpha p, p = z + beta p"),
+                         ("spmv_cpx8", None, "K5 fused multi-frequency SpMV, batch 8, complex arithmetic (admittance sweeps)")):
+    v = capture(name, title)
+    if v and kid:
+        traffic[kid] = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
+if traffic:
+    traffic["source"] = f"profiles/{R}_spmv_real16.md, {R}_update_bj_real16.md, {R}_pupdate_bj_real16.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    json.dump(traffic, open(os.path.join(OUT, "kernel_traffic.json"), "w"))
+for fn in ("bench_%s.json" % R,):
+    src = os.path.join(GO, fn)
+    if os.path.isfile(src) and os.path.getsize(src):
+        open(os.path.join(OUT, f"{R}_bench.json"), "w").write(open(src).read())
 print(os.listdir(OUT))
