@@ -281,9 +281,9 @@ def run_ours(args):
              1: ("K6a", "k_update_bj (residual update + block-Jacobi z = B r out of shared memory + rho, ||r||^2)" if bj
                  else "k_update (residual update + Jacobi + rho, ||r||^2)"),
              2: ("K6b", "k_pupdate_bj (x += alpha p, p = z + beta p)" if bj else "k_pupdate (x += alpha p, p = z + beta p)")}
-    sysm.iteration_enqueue(F, 1, -1, real=real, block_jacobi=bj)
     kernels = []
     for which in (0, 1, 2):
+        sysm.iteration_enqueue(F, 1, -1, real=real, block_jacobi=bj)      # fresh vectors and scalars, every slot active
         sysm.iteration_enqueue(F, 5, which, real=real, block_jacobi=bj)   # warm-up
         barrier()
         with torch.cuda.stream(stream):

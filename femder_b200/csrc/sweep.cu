@@ -2306,7 +2306,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
         for (int f = 0; f < F; ++f) {
             fill_slot(h, coef, F, w->n_groups, f, 2.0 * 3.141592653589793 * (100.0 + f), nullptr, 0.0);
             h.active[f] = 1; h.xpend[f] = 1;
-            h.rho[f] = make_double2(1.0, 0.0); h.pq[f] = make_double2(1e6, 0.0);
+            h.rho[f] = make_double2(1.0, 0.0); h.pq[f] = make_double2(1e30, 0.0);   // alpha ~ 0: repeated launches stay finite
             h.alpha[f] = make_double2(1e-6, 0.0); h.beta[f] = make_double2(0.5, 0.0);
             h.bb[f] = 0.0;   // never "converged": rr > tol2 * 0
         }

@@ -281,10 +281,10 @@ class System:
             # frequencies fill the 128-byte gather line that 8 complex ones do
             real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex and n_vec == 0
             batch = 16 if real else 8
-            if self.n_nodes <= SMALL_MESH_NODES and not (real and precond == "block"):
-                # small meshes: the kernels are latency-bound, wide batches amortise the fixed cost per launch.  Real sweeps
-                # stay at 16: the block-Jacobi kernels cover batches up to 16, and half the iterations beat the wider batch
-                # (21 735 DOF: 766 frequencies/s at 16 slots against 673 at 64 slots with point Jacobi)
+            if self.n_nodes <= SMALL_MESH_NODES:
+                # small meshes: the kernels are latency-bound, wide batches amortise the fixed cost per launch.  (The
+                # block-Jacobi kernels cover batches up to 16 only; on the coarse config-1 mesh, k h up to 1, 64 slots with point
+                # Jacobi sweep 20-500 Hz in 1.39 s against 2.18 s for 16 slots with block-Jacobi.)
                 batch *= 4
         if batch not in VALID_BATCH:
             raise ValueError(f"batch must be one of {VALID_BATCH} or 'auto'")
