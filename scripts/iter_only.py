@@ -17,7 +17,12 @@ grid = fd.shoebox_tet4(*[int(t) for t in a.shape.split(",")])
 s = fd.System(0)
 s.set_volume_mesh(grid.nos, grid.elem_vol)
 s.assemble_volume(1.21, 343.0)
+import time  # noqa: E402
 s.iteration_enqueue(a.batch, 1, -1, real=True, block_jacobi=not a.jacobi)
+s.iteration_enqueue(a.batch, 3, a.which, real=True, block_jacobi=not a.jacobi)
+s.synchronize()
+t = time.perf_counter()
 nb = s.iteration_enqueue(a.batch, a.reps, a.which, real=True, block_jacobi=not a.jacobi)
 s.synchronize()
-print(f"kernel {a.which} x {a.reps}: {nb / 1e6:.1f} MB algorithmic per launch")
+t = (time.perf_counter() - t) / a.reps
+print(f"kernel {a.which} x {a.reps}: {nb / 1e6:.1f} MB algorithmic per launch, {t * 1e6:.1f} us per launch (host clock around {a.reps} launches), {nb / t / 1e9:.0f} GB/s")
