@@ -1058,35 +1058,40 @@ __global__ void __launch_bounds__(kBlock) k_pupdate(T* __restrict__ x, T* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kBjTile = 128;
 constexpr int kBjPacked = kBjTile * (kBjTile + 1) / 2;   // floats of a packed lower triangle (reorder.cu)
-template <int F, bool START>
+// CPX: a complex batch of F slots is 2 F real columns per row (re, im interleaved): the product treats them as independent
+// reals (B is real), only alpha and the unconjugated rho' = r^T z couple a slot's two columns (partner = lane ^ 1).
+template <int F, bool START, bool CPX>
 __global__ void __launch_bounds__(256, 3)
 k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* __restrict__ binv, float* __restrict__ z32,
             double* __restrict__ p_start, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
-    static_assert(F >= 1 && F <= 16, "block-Jacobi kernels cover batches up to 16");
-    constexpr int EPT = (kBjTile * F + 255) / 256;     // elements of a tile per thread
-    constexpr int CPT = (F >= 2) ? F / 2 : 1;          // columns per thread in the product
+    constexpr int NC = CPX ? 2 * F : F;                 // real columns per row
+    static_assert(NC >= 1 && NC <= 16, "block-Jacobi kernels cover 16 real columns per row");
+    constexpr int EPT = (kBjTile * NC + 255) / 256;     // elements of a tile per thread
+    constexpr int CPT = (NC >= 2) ? NC / 2 : 1;         // columns per thread in the product
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* Bs = reinterpret_cast<float*>(smem_raw);                   // packed lower triangle: (i, k <= i) at i (i + 1) / 2 + k
-    float* r32 = Bs + kBjPacked;                                      // [128][F]
-    float* zp = r32 + kBjTile * F;                                    // [128][F]
+    float* r32 = Bs + kBjPacked;                                      // [128][NC]
+    float* zp = r32 + kBjTile * NC;                                   // [128][NC]
     const int tid = threadIdx.x;
-    const int f = tid % F;
+    const int col = tid % NC;                     // 256 % NC == 0: every element tid + 256 u of a thread lies in this column
+    const int f = CPX ? col / 2 : col;
+    const bool im = CPX && (col & 1);
     const bool act = START ? (sc->reset[f] != 0) : (sc->active[f] != 0);
-    double alpha = 0.0;
+    double2 alpha = make_double2(0.0, 0.0);
     if (!START && act) {
         const double2 pq = sc->pq[f];
-        if (pq.x != 0.0 || pq.y != 0.0) alpha = cdiv(sc->rho[f], pq).x;
+        if (pq.x != 0.0 || pq.y != 0.0) alpha = cdiv(sc->rho[f], pq);
     }
     const int rp = tid & 63, ch = (tid >> 6) & 1, kh = tid >> 7;
     const int c0 = ch * CPT;
-    const bool prod = (F >= 2) || ch == 0;
+    const bool prod = (NC >= 2) || ch == 0;
     double v[3] = {0.0, 0.0, 0.0};
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const float* bt = binv + t * (int64_t)kBjPacked;
         for (int i = tid; i < kBjPacked / 4; i += 256) cp_async16(Bs + i * 4, bt + i * 4);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const int64_t base = t * (int64_t)kBjTile * F;
-        const int n_el = (int)min((int64_t)kBjTile, n_rows - t * kBjTile) * F;
+        const int64_t base = t * (int64_t)kBjTile * NC;
+        const int n_el = (int)min((int64_t)kBjTile, n_rows - t * kBjTile) * NC;
         double rn[EPT];
         {
             double rv[EPT], qv[EPT];
@@ -1102,8 +1107,13 @@ k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* _
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 const int e = tid + 256 * u;
-                rn[u] = rv[u] - alpha * qv[u];
-                if (e < kBjTile * F) r32[e] = (act && e < n_el) ? (float)rn[u] : 0.0f;
+                if constexpr (CPX) {
+                    const double qo = __shfl_xor_sync(0xffffffffu, qv[u], 1);   // the slot's other component
+                    rn[u] = rv[u] - (im ? alpha.x * qv[u] + alpha.y * qo : alpha.x * qv[u] - alpha.y * qo);
+                } else {
+                    rn[u] = rv[u] - alpha.x * qv[u];
+                }
+                if (e < kBjTile * NC) r32[e] = (act && e < n_el) ? (float)rn[u] : 0.0f;
                 if (!START && act && e < n_el) r[base + e] = rn[u];
             }
         }
@@ -1125,33 +1135,47 @@ k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* _
                 const float b0 = Bs[(k <= r0i) ? t0 + k : tk + r0i], b1 = Bs[(k <= r1i) ? t1 + k : tk + r1i];
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    const float rr = r32[k * F + c0 + c];
+                    const float rr = r32[k * NC + c0 + c];
                     a0[c] += b0 * rr;
                     a1[c] += b1 * rr;
                 }
             }
             if (kh == 1) {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) { zp[rp * F + c0 + c] = a0[c]; zp[(rp + 64) * F + c0 + c] = a1[c]; }
+                for (int c = 0; c < CPT; ++c) { zp[rp * NC + c0 + c] = a0[c]; zp[(rp + 64) * NC + c0 + c] = a1[c]; }
             }
         }
         __syncthreads();
         if (prod && kh == 0) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                zp[rp * F + c0 + c] = a0[c] + zp[rp * F + c0 + c];
-                zp[(rp + 64) * F + c0 + c] = a1[c] + zp[(rp + 64) * F + c0 + c];
+                zp[rp * NC + c0 + c] = a0[c] + zp[rp * NC + c0 + c];
+                zp[(rp + 64) * NC + c0 + c] = a1[c] + zp[(rp + 64) * NC + c0 + c];
             }
         }
         __syncthreads();
-        if (act) {
 #pragma unroll
-            for (int u = 0; u < EPT; ++u) {
-                const int e = tid + 256 * u;
-                if (e < n_el) {
-                    const float z = zp[e];
-                    if constexpr (START) p_start[base + e] = (double)z;   // first search direction of the slot
-                    else z32[base + e] = z;
+        for (int u = 0; u < EPT; ++u) {
+            const int e = tid + 256 * u;
+            const bool ok = act && e < n_el;
+            const float z = (e < kBjTile * NC) ? zp[e] : 0.0f;
+            if (ok) {
+                if constexpr (START) p_start[base + e] = (double)z;   // first search direction of the slot
+                else z32[base + e] = z;
+            }
+            if constexpr (CPX) {
+                // (rr + j ri)(zr + j zi), accumulated by the lane that holds the real part
+                const double ro = __shfl_xor_sync(0xffffffffu, rn[u], 1);
+                const double zo = (double)__shfl_xor_sync(0xffffffffu, z, 1);
+                if (ok) {
+                    if (!im) {
+                        v[0] += rn[u] * (double)z - ro * zo;
+                        v[1] += rn[u] * zo + ro * (double)z;
+                    }
+                    v[2] += rn[u] * rn[u];
+                }
+            } else {
+                if (ok) {
                     v[0] += rn[u] * (double)z;
                     v[2] += rn[u] * rn[u];
                 }
@@ -1159,40 +1183,65 @@ k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* _
         }
         __syncthreads();   // the next tile overwrites Bs, r32, zp
     }
-    if constexpr (START) {
-        block_reduce_finalize<F, 3, 256>(v, partial, &sc->ticket[2], [&](int ff, const double* tot) { fin_start(sc, ff, tot); });
+    auto fin = [&](int ff, const double* tot) {
+        if constexpr (START) fin_start(sc, ff, tot); else fin_update(sc, ff, tot);
+    };
+    unsigned int* ticket = &sc->ticket[START ? 2 : 1];
+    if constexpr (CPX) {
+        // threads of slot f: columns 2f, 2f+1 of every group of NC threads; fixed order
+        __shared__ double s_v[256][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_v[tid][i] = v[i];
+        __syncthreads();
+        if (tid < F) {
+            double sum[3] = {0.0, 0.0, 0.0};
+            for (int th = 2 * tid; th < 256; th += NC) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sum[i] += s_v[th][i] + s_v[th + 1][i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) partial[((int64_t)blockIdx.x * F + tid) * 3 + i] = sum[i];
+        }
+        finalize_last_block<F, 3, 256>(partial, ticket, fin);
     } else {
-        block_reduce_finalize<F, 3, 256>(v, partial, &sc->ticket[1], [&](int ff, const double* tot) { fin_update(sc, ff, tot); });
+        block_reduce_finalize<F, 3, 256>(v, partial, ticket, fin);
     }
 }
 
-// K6b with z read from the FP32 array K6a left: x += alpha p ; p = z + beta p.
-template <int F>
-__global__ void __launch_bounds__(kBlock) k_pupdate_bj(double* __restrict__ x, double* __restrict__ p, const float* __restrict__ z32,
+// K6b with z read from the FP32 array K6a left: x += alpha p ; p = z + beta p.  T = double (real sweep) or double2.
+template <typename T, int F>
+__global__ void __launch_bounds__(kBlock) k_pupdate_bj(T* __restrict__ x, T* __restrict__ p, const float* __restrict__ z32,
                                                         int64_t n_elems, const Scalars* __restrict__ sc) {
+    constexpr bool CPX = std::is_same<T, double2>::value;
     const int f = threadIdx.x % F;
     if (!sc->xpend[f]) return;
     const bool act = sc->active[f] != 0;
-    const double alpha = sc->alpha[f].x, beta = sc->beta[f].x;
+    const double2 alpha = sc->alpha[f], beta = sc->beta[f];
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; i0 < n_elems; i0 += stride * kVecU) {
-        double xv[kVecU], pv[kVecU];
-        float zv[kVecU];
+        T xv[kVecU], pv[kVecU], zv[kVecU];
 #pragma unroll
         for (int u = 0; u < kVecU; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < n_elems) {
                 xv[u] = x[i];
                 pv[u] = p[i];
-                if (act) zv[u] = z32[i];
+                if (act) {
+                    if constexpr (CPX) {
+                        const float2 zf = reinterpret_cast<const float2*>(z32)[i];
+                        zv[u] = make_double2((double)zf.x, (double)zf.y);
+                    } else {
+                        zv[u] = (double)z32[i];
+                    }
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < kVecU; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < n_elems) {
-                x[i] = xv[u] + alpha * pv[u];
-                if (act) p[i] = (double)zv[u] + beta * pv[u];
+                x[i] = v_add(xv[u], s_mul(alpha, pv[u]));
+                if (act) p[i] = v_add(zv[u], s_mul(beta, pv[u]));
             }
         }
     }
@@ -1575,18 +1624,44 @@ struct Launch {
     }
 
     // block-Jacobi tile kernels: 48 KB of shared memory per block at F = 16 (packed FP32 block + two 128 x F tiles)
-    static size_t bj_smem() { return (size_t)kBjPacked * 4 + (size_t)2 * kBjTile * (F <= 16 ? F : 16) * 4; }
+    static constexpr bool kBjReal = F <= 16, kBjCpx = F <= 8;   // 16 real columns per row at most
+    static size_t bj_smem(bool cpx) { return (size_t)kBjPacked * 4 + (size_t)2 * kBjTile * std::min(16, cpx ? 2 * F : F) * 4; }
     static int bj_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * 3)); }
+    static void bj_supported(SweepWork* w, bool* ok) { *ok = w->real ? kBjReal : kBjCpx; }
     static void bj_prepare(fdb_system* sys, SweepWork* w) {
-        if constexpr (F <= 16) {
-            build_block_prec(sys);
-            w->z32.alloc((size_t)w->N * F);
-            static thread_local std::map<int, bool> done;
-            if (!done[sys->device]) {
-                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem()));
-                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem()));
-                done[sys->device] = true;
+        build_block_prec(sys);
+        w->z32.alloc((size_t)w->N * F * (w->real ? 1 : 2));
+        static thread_local std::map<std::pair<int, bool>, bool> done;
+        bool& d = done[{sys->device, w->real}];
+        if (d) return;
+        if (w->real) {
+            if constexpr (kBjReal) {
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
             }
+        } else {
+            if constexpr (kBjCpx) {
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
+                FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
+            }
+        }
+        d = true;
+    }
+    // K6a (start = false) or the slot load (start = true) of the block-Jacobi path; false if this width has no such kernel
+    template <typename T>
+    static bool bj_update(fdb_system* sys, SweepWork* w, bool start) {
+        constexpr bool CPX = std::is_same<T, double2>::value;
+        if constexpr (CPX ? kBjCpx : kBjReal) {
+            double *r = (double*)w->r.p, *q = (double*)w->q.p, *p = (double*)w->p.p;
+            if (start)
+                k_update_bj<F, true, CPX><<<bj_grid(sys), 256, bj_smem(CPX), sys->stream>>>(r, nullptr, sys->blk_inv.p, w->z32.p, p, w->N, sys->n_tiles,
+                                                                                           w->sc.p, (double*)w->partial.p);
+            else
+                k_update_bj<F, false, CPX><<<bj_grid(sys), 256, bj_smem(CPX), sys->stream>>>(r, q, sys->blk_inv.p, w->z32.p, nullptr, w->N, sys->n_tiles,
+                                                                                            w->sc.p, (double*)w->partial.p);
+            return true;
+        } else {
+            return false;
         }
     }
     // vector kernels: up to 8 blocks per SM, but at least 16 elements per thread - on a small mesh a thin grid leaves
@@ -1600,13 +1675,10 @@ struct Launch {
     static void vec_kernel_t(fdb_system* sys, SweepWork* w, bool overlay, int which) {
         const int64_t ne = w->N * F;
         T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *q = (T*)w->q.p;
-        if constexpr (std::is_same<T, double>::value && F <= 16) {
-            if (w->precond == 1) {
-                if (which == 1)
-                    k_update_bj<F, false><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, (const double*)q, sys->blk_inv.p, w->z32.p, nullptr,
-                                                                                        w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
-                else
-                    k_pupdate_bj<F><<<egrid(w), kBlock, 0, sys->stream>>>((double*)x, (double*)p, w->z32.p, ne, w->sc.p);
+        if (w->precond == 1) {
+            if (which == 1) { if (bj_update<T>(sys, w, false)) return; }
+            else if constexpr (std::is_same<T, double2>::value ? kBjCpx : kBjReal) {
+                k_pupdate_bj<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, w->z32.p, ne, w->sc.p);
                 return;
             }
         }
@@ -1662,13 +1734,7 @@ struct Launch {
             nk += 2;
         }
         bool started = false;
-        if constexpr (std::is_same<T, double>::value && F <= 16) {
-            if (w->precond == 1) {
-                k_update_bj<F, true><<<bj_grid(sys), 256, bj_smem(), sys->stream>>>((double*)r, nullptr, sys->blk_inv.p, w->z32.p, (double*)p,
-                                                                                   w->N, sys->n_tiles, w->sc.p, (double*)w->partial.p);
-                started = true;
-            }
-        }
+        if (w->precond == 1) started = bj_update<T>(sys, w, true);
         if (started) {
         } else if (overlay) {
             if constexpr (std::is_same<T, double2>::value)
@@ -1959,9 +2025,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     w->real = real;
     res->real_arithmetic = real ? 1 : 0;
     // Preconditioner: block-Jacobi over the 128-row tiles of the internal order where it is implemented (real sweeps in
-    // batches of up to 16), point Jacobi otherwise.  prm->precond: 0 = Jacobi, 1 = block-Jacobi where possible.
+    // batches of up to 16, complex sweeps in batches of up to 8), point Jacobi otherwise.  prm->precond: 0 = Jacobi, 1 = block-Jacobi where possible.
     static const bool no_bj = getenv("FDB_NO_BLOCK_JACOBI") != nullptr;   // A/B aid
-    const bool use_bj = prm->precond == 1 && !no_bj && real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;
+    bool use_bj = prm->precond == 1 && !no_bj && sys->n_tiles > 0 && sys->tile_rows == 128;
+    if (use_bj) { FDB_DISPATCH_F(F, bj_supported(w, &use_bj)); }   // 16 real columns per row at most: F <= 16 real, F <= 8 complex
     w->precond = use_bj ? 1 : 0;
     if (use_bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
     w->n_rn = (int)rn_nodes.size();
@@ -2134,7 +2201,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             if (F2 < F) {
                 SweepWork* w2 = new_work(sys, F2);
                 w2->real = w->real;
-                w2->precond = w->precond;
+                w2->precond = w->precond;   // a narrower batch always has the kernels a wider one has
                 if (w2->precond == 1) { FDB_DISPATCH_F(F2, bj_prepare(sys, w2)); }
                 SlotMap map;
                 Scalars h2;
@@ -2294,7 +2361,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
     FDB_REQUIRE(!(flags & 1), "the iteration bench covers rigid-wall sweeps");
     SweepWork* w = get_work(sys, F);
     w->real = bench_real(sys, w, F, flags);
-    const bool bj = (flags & 4) && w->real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;
+    const bool bj = (flags & 4) && w->real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;   // the bench covers real sweeps
     w->precond = bj ? 1 : 0;
     if (bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
     const int64_t N = w->N, ne = N * F;

@@ -7,7 +7,7 @@ through ``libfemder_b200.so``.  There is no CPU fallback.
 Differences from the reference, all deliberate:
 * Tet4 ``H, Q`` are float64 csc; the reference rounds them to complex64 (``fem_numerical.py:307-312``).
   ``compat_complex64=True`` reproduces that rounding (values rounded to float32 before the solve).
-* every frequency is solved by preconditioned COCG (block-Jacobi for rigid-wall sweeps, point Jacobi otherwise) to
+* every frequency is solved by preconditioned COCG (block-Jacobi, point Jacobi in the wide batches of small meshes) to
   ``tol`` instead of a PARDISO factorisation.
 * a surface group without a boundary condition raises ``KeyError`` as in the reference (``FEM_3D.py:1310``);
   ``mu`` keys are paired with their own group instead of by position.

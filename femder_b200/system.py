@@ -260,7 +260,7 @@ class System:
         (velocity boundary conditions).  ``src_sets`` = list of ``(nodes, q)`` pairs solves several right-hand sides
         per frequency in the same batches (source candidate loops); outputs then carry a leading set axis.
         ``precond``: "block" = block-Jacobi over the 128-row tiles of the sweep's internal order where implemented
-        (real-arithmetic sweeps, batch <= 16), point Jacobi elsewhere; "jacobi" = point Jacobi everywhere.
+        (batches of up to 16 real or 8 complex slots), point Jacobi elsewhere; "jacobi" = point Jacobi everywhere.
         Returns (pN or None, pR or None, SweepStats)."""
         omega = _f64(np.atleast_1d(omega))
         nf = len(omega)

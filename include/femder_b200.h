@@ -107,7 +107,7 @@ typedef struct fdb_sweep_params {
     int32_t check_every;      /* iterations between host convergence checks (one CUDA graph launch) */
     int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
     int32_t precond;          /* 0: point Jacobi; 1: block-Jacobi (FP32 inverses of the 128-row diagonal blocks of H) where it is
-                               * implemented - real-arithmetic sweeps in batches of up to 16 - and point Jacobi elsewhere */
+                               * implemented - batches of up to 16 real or 8 complex slots - and point Jacobi elsewhere */
     int32_t arithmetic;       /* 0: automatic (real arithmetic for rigid-wall sweeps with real sources), 1: always complex */
     /* extra right-hand-side terms (velocity boundary conditions, FEM_3D.py:1320-1347): b_n += sum_k rhs_coef[k][n] * vec_k */
     int64_t n_rhs_vec;
