@@ -326,6 +326,32 @@ def test_block_jacobi_complex_sweep(gpu_lib, batch):
     assert np.array_equal(a, a2) and np.array_equal(sa.iters, sa2.iters)
 
 
+@pytest.mark.parametrize("block_jacobi", [True, False])
+def test_iteration_enqueue_runs_every_kernel(gpu_lib, block_jacobi):
+    """fdb_iteration_enqueue (bench.py's per-kernel rooflines): prepare, then K5 / K6a / K6b on resident vectors; the
+    algorithmic bytes follow DESIGN.md section 4."""
+    from femder_b200 import System
+    from femder_b200.mesh import shoebox_tet4
+    grid = shoebox_tet4(12, 14, 10)
+    s = System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.assemble_volume(1.21, 343.0)
+    N, F = grid.NumNosC, 16
+    H, _ = s.get_HQ()
+    n_tiles = (N + 127) // 128
+    s.iteration_enqueue(F, 1, -1, real=True, block_jacobi=block_jacobi)
+    nb = [s.iteration_enqueue(F, 3, which, real=True, block_jacobi=block_jacobi) for which in (0, 1, 2)]
+    s.synchronize()
+    vb = 8 * N * F
+    assert nb[0] == 4 * (N + 1) + 20 * H.nnz + 2 * vb
+    if block_jacobi:
+        assert nb[1] == 3 * vb + 4 * N * F + n_tiles * 8256 * 4 and nb[2] == 4 * vb + 4 * N * F
+    else:
+        assert nb[1] == 3 * vb + 16 * N and nb[2] == 5 * vb + 16 * N
+    with pytest.raises(Exception):
+        s.iteration_enqueue(F, 3, 5)
+
+
 def test_results_land_at_their_frequency_index(gpu_lib):
     """Slots are loaded in descending frequency order and refilled as they converge: outputs stay in input order."""
     from conftest import Golden
