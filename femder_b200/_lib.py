@@ -25,13 +25,14 @@ class SweepParams(C.Structure):
                 ("tol", C.c_double), ("max_iter", C.c_int32),
                 ("batch", C.c_int32), ("check_every", C.c_int32), ("warm_start", C.c_int32), ("precond", C.c_int32),
                 ("arithmetic", C.c_int32), ("n_rhs_vec", C.c_int64), ("rhs_ptr", C.c_void_p), ("rhs_nodes", C.c_void_p),
-                ("rhs_vals", C.c_void_p), ("rhs_coef", C.c_void_p), ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p)]
+                ("rhs_vals", C.c_void_p), ("rhs_coef", C.c_void_p), ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p),
+                ("modal_delta_hz", C.c_double)]
 
 
 class SweepResult(C.Structure):
     _fields_ = [("pR", C.c_void_p), ("pN", C.c_void_p), ("iters", C.c_void_p), ("relres", C.c_void_p),
                 ("seconds", C.c_double), ("n_spmv", C.c_int64), ("n_kernels", C.c_int64),
-                ("n_unconverged", C.c_int32), ("real_arithmetic", C.c_int32)]
+                ("n_unconverged", C.c_int32), ("real_arithmetic", C.c_int32), ("n_resumed", C.c_int32), ("precond_used", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/femder_b200.h declares
@@ -62,6 +63,12 @@ SIGNATURES = {
     "fdb_sweep": (C.c_int, [C.c_void_p, C.POINTER(SweepParams), C.POINTER(SweepResult)]),
     "fdb_sizeof_sweep_params": (C.c_int, []),
     "fdb_sizeof_sweep_result": (C.c_int, []),
+    "fdb_modal_compute": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int)]),
+    "fdb_modal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p, C.c_void_p]),
+    "fdb_modal_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "fdb_modal_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "fdb_modal_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdb_modal_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fdb_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i64p]),
     "fdb_spmv_enqueue": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i64p]),

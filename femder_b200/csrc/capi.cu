@@ -1,7 +1,6 @@
 // extern "C" entry points declared in include/femder_b200.h.  Exceptions never cross the boundary:
 // every call returns a status and records a message for fdb_last_error().
-#include "common.cuh"
-#include "../../include/femder_b200.h"
+#include "solver.cuh"
 
 namespace fdb {
 static thread_local std::string g_last_error;
@@ -53,7 +52,7 @@ using namespace fdb;
 extern "C" {
 
 const char* fdb_last_error(void) { return fdb::g_last_error.c_str(); }
-int fdb_abi_version(void) { return 1; }
+int fdb_abi_version(void) { return 2; }
 
 int fdb_device_count(int* count) {
     FDB_API_BEGIN
@@ -104,6 +103,7 @@ int fdb_system_destroy(fdb_system* sys) {
         cudaStreamSynchronize(sys->stream);
         fdb::free_sweep_work(sys->work);
         sys->work = nullptr;
+        fdb::modal_free_handles(sys);
         if (sys->own_stream) cudaStreamDestroy(sys->stream);
         delete sys;
     }
@@ -362,6 +362,55 @@ int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* re
 
 int fdb_sizeof_sweep_params(void) { return (int)sizeof(fdb_sweep_params); }
 int fdb_sizeof_sweep_result(void) { return (int)sizeof(fdb_sweep_result); }
+
+int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    fdb::modal_compute(sys, f_cut_hz, f_acc_hz, n_modes_hint, tol, max_outer, n_modes_found);
+    FDB_API_END
+}
+
+int fdb_modal_info(fdb_system* sys, int* outer_iterations, int* block_columns, int* mass_order, double* worst_residual, double* residuals) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    FDB_REQUIRE(sys->have_modes, "no modes");
+    if (outer_iterations) *outer_iterations = sys->modal_outer;
+    if (block_columns) *block_columns = sys->modal_block;
+    if (mass_order) *mass_order = sys->modal_order;
+    if (worst_residual) *worst_residual = sys->modal_resid;
+    if (residuals) FDB_CUDA(cudaMemcpy(residuals, sys->modal_res_host.data(), sys->n_modes * sizeof(double), cudaMemcpyDefault));
+    FDB_API_END
+}
+
+int fdb_modal_set(fdb_system* sys, int n_modes, const double* lam, const double* V) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    fdb::modal_set(sys, n_modes, lam, V);
+    FDB_API_END
+}
+
+int fdb_modal_count(fdb_system* sys, int* n_modes) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    FDB_REQUIRE(n_modes != nullptr, "null argument");
+    *n_modes = sys->have_modes ? sys->n_modes : 0;
+    FDB_API_END
+}
+
+int fdb_modal_get(fdb_system* sys, double* lam, double* V) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    fdb::modal_get(sys, lam, V);
+    FDB_API_END
+}
+
+int fdb_modal_apply(fdb_system* sys, const double* omega, int n_modes_use, const double* r, double* z) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    FDB_REQUIRE(omega && r && z, "null argument");
+    fdb::run_modal_apply(sys, omega, n_modes_use, r, z);
+    FDB_API_END
+}
 
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu, const double* x, double* y) {
     FDB_API_BEGIN

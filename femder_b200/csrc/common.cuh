@@ -146,6 +146,23 @@ struct fdb_system {
     fdb::DevBuf<double> ov_val;      // [n_ov]
     bool have_overlay = false;
 
+    // Low room modes (modal.cu): H v = lambda Q v, V^T Q V = I.  Coarse correction of the sweep's preconditioner
+    // (the modal path, femder/FEM_3D.py:1699-1768, as a deflation basis).
+    int n_modes = 0;
+    int mode_chunks = 0;               // 128-mode chunks stored per tile
+    std::vector<double> modal_lam_host;
+    fdb::DevBuf<double> modal_lam;     // [n_modes] ascending
+    fdb::DevBuf<double> modal_res;     // [n_modes] ||H v - lambda Q v|| / ||Q v||: how far each stored vector is from an eigenvector
+    std::vector<double> modal_res_host;
+    fdb::DevBuf<uint16_t> modal_v;     // bf16 [n_tiles][mode_chunks][16 mode blocks][16 node blocks][8 nodes][8 modes]
+    fdb::DevBuf<double> modal_x;       // FP64 modes [ceil(n_modes / 16)][n_nodes (internal order)][16], kept on request
+    fdb::DevBuf<double> modal_adiag;   // [n_groups][n_modes] v_i^T A_g v_i (damping of mode i by group g), built on demand
+    bool have_modes = false, have_adiag = false;
+    void* cublas = nullptr;            // cublasHandle_t / cusolverDnHandle_t of the modal set-up (dense Gram products, Rayleigh-Ritz)
+    void* cusolver = nullptr;
+    int modal_outer = 0, modal_block = 0, modal_order = 0;   // diagnostics of the last fdb_modal_compute: outer iterations, block width, mass order
+    double modal_resid = 0.0;               // ... worst relative residual of the kept pairs
+
     fdb::SweepWork* work = nullptr;
 };
 
@@ -168,6 +185,10 @@ void build_order(fdb_system* sys);   // reorder.cu: internal order + SELL struct
 void locate_points(fdb_system* sys, int64_t n_pts, const double* pts_dev, double tol, int32_t* nodes_dev, double* weights_dev);
 void interleave_hq(fdb_system* sys, const double* H, const double* Q);
 void deinterleave_hq(fdb_system* sys, double* H, double* Q);
+
+// ---- modal.cu ----
+void modal_reset(fdb_system* sys);   // the modes belong to the previous H, Q
+void modal_free_handles(fdb_system* sys);
 
 // ---- sweep.cu ----
 void free_sweep_work(SweepWork* w);

@@ -1,0 +1,999 @@
+// Low room modes as a coarse correction of the sweep's preconditioner, on the tensor cores.
+//
+// The reference computes room modes in FEM3D.eigenfrequency (femder/FEM_3D.py:1699-1768: spsolve(Q, H) + eigs) and uses them for
+// modal superposition (1842-1934).  Here the same eigenpairs  H v_i = lambda_i Q v_i,  V^T Q V = I  make the Krylov solver
+// of FEM3D.compute() (sweep.cu) independent of how many room modes lie below the drive frequency:
+//
+//     M^-1 = B + V diag(d) V^T ,   d_i = 1 / (lambda_i - w^2 + 1j w sum_g mu_g v_i^T A_g v_i)
+//
+// B = block-Jacobi (sweep.cu).  G = H - w^2 Q has one negative eigenvalue per mode below the drive frequency and a
+// near-zero one at every resonance - that, not the mesh, is what makes COCG need thousands of iterations; V diag(d) V^T
+// inverts G exactly on span(V), so with all modes below sqrt(f^2 + D^2) in V the preconditioned operator is positive
+// with its spectrum bounded away from zero (tests/research/modal_deflation_prototype.py: 1879 -> 37 iterations at 300 Hz on
+// the config-1 mesh; bfloat16 V and modes of the lumped-mass problem do as well as exact FP64 modes).
+//
+// The two products per iteration are the ONE dense contraction of the hot path, and they run on tcgen05:
+//   projection  c = V^T r     (k_modal_project)   D[128 modes x 32] += A[128 modes x 16 nodes] B[16 nodes x 32]
+//   expansion   z += V e      (k_modal_expand)    D[128 nodes x 32] += A[128 nodes x 16 modes] B[16 modes x 32]
+// Both read the SAME bytes of V: a tile of 128 nodes x 128 modes is stored as 8 x 8 bf16 core matrices, the expansion reads
+// it K-major, the projection MN-major (tc.cuh).  The 32 operand columns are the batch's 16 real columns (16 real slots or
+// 8 complex ones) split into bf16 (hi, lo) pairs: 16 mantissa bits of the FP32 value, accumulated in FP32 in TMEM.
+// Both kernels are bound by the HBM stream of V (2 bytes per node and mode): the tensor pipe is ~10 % busy.
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include "solver.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace fdb {
+
+constexpr int kMC = 128;                       // modes per chunk = rows of one projection accumulator
+constexpr int kModalMaxChunks = 8;             // 1024 modes: 8 x 32 TMEM columns in the projection, 64 KB coefficient image
+constexpr int kModalMaxModes = kMC * kModalMaxChunks;
+constexpr int kChunkBytes = 128 * kMC * 2;     // one tile of V for one chunk of modes: 32 KB
+constexpr int kStages = 4;                     // ring of V chunks in shared memory
+constexpr int kModalThreads = 192;             // warp 0 producer, warp 1 MMA issue + TMEM owner, warps 2..5 operand / epilogue
+constexpr uint32_t kSm = 2048, kSn = 128;      // byte strides of a chunk: mode block (8 modes), node block (8 nodes)
+// k_modal_coef keeps |lambda - w^2| >= res^2 / lambda (res = the stored vector's residual): below that the inexact vector cannot
+// tell which side of the resonance the drive frequency is on.  Nothing coarser: a bound proportional to res itself was tried
+// and makes V diag(d) V^T stop being the inverse of G on span(V), which the indefinite CG recurrence does not survive
+// (measured: occasional stagnation with the bound, none without, on modes with 5e-3 relative residual).
+
+void modal_reset(fdb_system* sys) {
+    sys->have_modes = false;
+    sys->have_adiag = false;
+    sys->n_modes = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// storage: FP64 modes in batches [b][row][16] (internal order) -> bf16 tiles
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_modal_pack(const double* __restrict__ X, int64_t n_rows, int64_t n_tiles, int n_modes, int n_chunks,
+                                                    uint16_t* __restrict__ V) {
+    // one thread per (row of the padded tiles, block of 8 modes); rows fastest: 8 consecutive threads write one 128-byte core matrix
+    const int64_t rows_pad = n_tiles * 128;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_pad * n_chunks * 16) return;
+    const int64_t row = idx % rows_pad;
+    const int mbg = (int)(idx / rows_pad);          // global mode block
+    const int j = mbg >> 4, mb = mbg & 15;
+    const int64_t t = row >> 7;
+    const int rin = (int)(row & 127), nb = rin >> 3, ni = rin & 7;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (row < n_rows) {
+        const int m0 = mbg * 8;
+        const double* src = X + ((int64_t)(m0 >> 4) * n_rows + row) * 16 + (m0 & 15);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t h = (m0 + k < n_modes) ? bf16_rn((float)src[k]) : 0u;
+            w[k >> 1] |= h << (16 * (k & 1));
+        }
+    }
+    uint16_t* dst = V + (((int64_t)t * n_chunks + j) * (kChunkBytes / 2)) + (mb * kSm + nb * kSn + ni * 16) / 2;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// X[i / 16][perm[n]][i % 16] = v[n]  (one mode from the caller's numbering into the batch layout)
+__global__ void k_modal_scatter(const double* __restrict__ v, const int32_t* __restrict__ perm, int64_t n_rows, int mode, double* __restrict__ X) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < n_rows) X[((int64_t)(mode >> 4) * n_rows + perm[n]) * 16 + (mode & 15)] = v[n];
+}
+__global__ void k_modal_gather(const double* __restrict__ X, const int32_t* __restrict__ perm, int64_t n_rows, int mode, double* __restrict__ v) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < n_rows) v[n] = X[((int64_t)(mode >> 4) * n_rows + perm[n]) * 16 + (mode & 15)];
+}
+
+// adiag[g][i] = v_i^T A_g v_i from the boundary overlay (rows in the internal order): one block per mode, fixed-order sums
+__global__ void __launch_bounds__(256) k_modal_adiag(const double* __restrict__ X, const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg,
+                                                     const double* __restrict__ ov_val, int64_t n_rows, int n_groups, int n_modes,
+                                                     double* __restrict__ adiag) {
+    const int i = blockIdx.x;
+    const double* x = X + (int64_t)(i >> 4) * n_rows * 16 + (i & 15);
+    extern __shared__ double s_acc[];   // [256][n_groups]
+    for (int g = 0; g < n_groups; ++g) s_acc[threadIdx.x * n_groups + g] = 0.0;
+    for (int64_t r = threadIdx.x; r < n_rows; r += 256) {
+        const int ob = ov_ptr[r], oe = ov_ptr[r + 1];
+        if (ob == oe) continue;
+        const double xr = x[r * 16];
+        for (int o = ob; o < oe; ++o) {
+            const int2 cg = ov_cg[o];
+            s_acc[threadIdx.x * n_groups + cg.y] += xr * ov_val[o] * x[(int64_t)cg.x * 16];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_groups) {
+        double s = 0.0;
+        for (int k = 0; k < 256; ++k) s += s_acc[k * n_groups + threadIdx.x];
+        adiag[(int64_t)threadIdx.x * n_modes + i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection  c = V^T r :  per block, partial sums over its tiles in TMEM; c_part[block][mode][16]
+// ------------------------------------------------------------------------------------------------
+struct ModalSmem {
+    uint64_t a_full[kStages], a_empty[kStages];
+    uint64_t b_full[2], b_empty[2];
+    uint64_t e_full, done;
+    uint32_t tmem_base;
+};
+
+// chunks and the bytes / K steps of the last one for `modes_use` modes (a multiple of 16)
+__device__ __forceinline__ void modal_shape(int modes_use, int& n_use, uint32_t& bytes_last, int& ksteps_last) {
+    n_use = (modes_use + kMC - 1) / kMC;
+    const int last = modes_use - (n_use - 1) * kMC;          // modes in the last chunk
+    bytes_last = (uint32_t)((last + 7) / 8) * kSm;
+    ksteps_last = last / 16;
+}
+
+// the V chunks of this block's tiles, in order, into the ring (one thread)
+__device__ __forceinline__ void modal_produce(const uint16_t* __restrict__ V, int n_chunks, int64_t n_tiles, int n_use, uint32_t bytes_last,
+                                              unsigned char* ring, ModalSmem* sm) {
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int j = 0; j < n_use; ++j, ++it) {
+            const int st = it % kStages;
+            mbar_wait_bounded(&sm->a_empty[st], ((it / kStages) & 1u) ^ 1u);
+            const uint32_t bytes = (j == n_use - 1) ? bytes_last : (uint32_t)kChunkBytes;
+            mbar_expect_tx(&sm->a_full[st], bytes);
+            bulk_g2s(ring + (size_t)st * kChunkBytes, V + ((int64_t)t * n_chunks + j) * (kChunkBytes / 2), bytes, &sm->a_full[st]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kModalThreads, 1)
+k_modal_project(const double* __restrict__ r, const uint16_t* __restrict__ V, int n_chunks, int64_t n_rows, int64_t n_tiles,
+                const Scalars* __restrict__ sc, float* __restrict__ c_part) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;                                      // [kStages][32 KB]
+    unsigned char* bimg = smem_raw + (size_t)kStages * kChunkBytes;      // [2][8 KB]: (hi, lo) image of a residual tile
+    ModalSmem* sm = reinterpret_cast<ModalSmem*>(bimg + 2 * 8192);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n_use, ksteps_last;
+    uint32_t bytes_last;
+    modal_shape(sc->modes_use, n_use, bytes_last, ksteps_last);
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm->a_full[i], 1); mbar_init(&sm->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->b_full[i], 128); mbar_init(&sm->b_empty[i], 1); }
+        mbar_init(&sm->done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&sm->tmem_base, 32 * kModalMaxChunks);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) modal_produce(V, n_chunks, n_tiles, n_use, bytes_last, ring, sm);
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_bf16(128, 32, 1, 1);   // A = V^T chunk, MN-major; B = residual image, MN-major
+            uint32_t it = 0, ti = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+                const int bb = ti & 1;
+                mbar_wait_bounded(&sm->b_full[bb], (ti >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(bimg + bb * 8192);
+                for (int j = 0; j < n_use; ++j, ++it) {
+                    const int st = it % kStages;
+                    mbar_wait_bounded(&sm->a_full[st], (it / kStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)   // K = 16 nodes per step: two node blocks
+                        tc_mma_bf16(tmem + 32 * j, tc_desc(a_addr + ks * 2 * kSn, kSn, kSm), tc_desc(b_addr + ks * 256, 128, 2048), idesc,
+                                    ti > 0 || ks > 0);
+                    tc_commit(&sm->a_empty[st]);
+                }
+                tc_commit(&sm->b_empty[bb]);
+            }
+            tc_commit(&sm->done);
+        }
+    } else {
+        // ---- residual tile -> bf16 (hi, lo) operand image: thread = node row ----
+        const int i = tid - 64;
+        uint32_t ti = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int bb = ti & 1;
+            const int64_t row = t * 128 + i;
+            double v[16];
+            if (row < n_rows) {
+                const double4* src = reinterpret_cast<const double4*>(r + row * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double4 d = src[k];
+                    v[4 * k] = d.x; v[4 * k + 1] = d.y; v[4 * k + 2] = d.z; v[4 * k + 3] = d.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = 0.0;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t h0, l0, h1, l1;
+                bf16_split((float)v[2 * k], h0, l0);
+                bf16_split((float)v[2 * k + 1], h1, l1);
+                hi[k] = h0 | (h1 << 16);
+                lo[k] = l0 | (l1 << 16);
+            }
+            mbar_wait_bounded(&sm->b_empty[bb], ((ti >> 1) & 1u) ^ 1u);
+            unsigned char* img = bimg + bb * 8192 + i * 16;   // core (node block, column block) at column block * 2048 + node block * 128
+            *reinterpret_cast<uint4*>(img) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(img + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(img + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(img + 6144) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            fence_proxy_async();
+            mbar_arrive(&sm->b_full[bb]);
+        }
+        // ---- epilogue: this block's partial sums, thread = mode row of a chunk ----
+        mbar_wait_bounded(&sm->done, 0);
+        tc_fence_after();
+        const int q = warp & 3;   // the TMEM lanes a warp may read: 32 (warp % 4) .. + 31
+        float* out = c_part + (int64_t)blockIdx.x * kModalMaxModes * 16;
+        for (int j = 0; j < n_use; ++j) {
+            float acc[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * j, acc);
+            float4* o = reinterpret_cast<float4*>(out + (int64_t)(j * kMC + q * 32 + lane) * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o[k] = make_float4(acc[4 * k] + acc[16 + 4 * k], acc[4 * k + 1] + acc[17 + 4 * k], acc[4 * k + 2] + acc[18 + 4 * k],
+                                   acc[4 * k + 3] + acc[19 + 4 * k]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 32 * kModalMaxChunks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// coefficients  e = d * c :  fixed-order sum of the block partials, d from lambda, w^2 and the modes' boundary damping;
+// written as the bf16 (hi, lo) MN-major operand image of the expansion: chunk j, column block cb, mode k at
+// j * 8192 + cb * 2048 + k * 16 (+ 2 bytes per column)
+// ------------------------------------------------------------------------------------------------
+template <bool CPX>
+__global__ void __launch_bounds__(256) k_modal_coef(const float* __restrict__ c_part, int n_blocks, const double* __restrict__ lam,
+                                                    const double* __restrict__ res, int n_modes, const double* __restrict__ adiag, const double2* __restrict__ coef, int n_groups, int F,
+                                                    const Scalars* __restrict__ sc, uint16_t* __restrict__ e_img) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int i = idx >> 4, c = idx & 15;          // mode, real column
+    if (i >= sc->modes_use) return;                // uniform per 16 threads
+    double s = 0.0;
+    for (int b0 = 0; b0 < n_blocks; b0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (b0 + u < n_blocks) ? __ldcg(&c_part[((int64_t)(b0 + u) * kModalMaxModes + i) * 16 + c]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)t[u];
+    }
+    double e = 0.0;
+    double so = 0.0;
+    if constexpr (CPX) so = __shfl_xor_sync(0xffffffffu, s, 1);            // the slot's other component (all lanes take part)
+    if (i < n_modes) {
+        const double l = lam[i];
+        const double floor_den = res[i] * res[i] / fmax(fabs(l), 1e-300) + 1e-13 * fabs(l);
+        if constexpr (CPX) {
+            const int f = c >> 1;
+            double2 den = make_double2(l - sc->w2[f], 0.0);
+            for (int g = 0; g < n_groups; ++g) {
+                const double2 cf = coef[g * F + f];
+                const double a = adiag[(int64_t)g * n_modes + i];
+                den.x += cf.x * a;
+                den.y += cf.y * a;
+            }
+            double dn = den.x * den.x + den.y * den.y;
+            if (dn < floor_den * floor_den) {
+                if (dn > 0.0) { const double g = floor_den / sqrt(dn); den.x *= g; den.y *= g; } else { den = make_double2(floor_den, 0.0); }
+                dn = floor_den * floor_den;
+            }
+            if (f < F && dn > 0.0) {
+                const double2 cv = (c & 1) ? make_double2(so, s) : make_double2(s, so);
+                const double2 ev = cdiv(cv, den);
+                e = (c & 1) ? ev.y : ev.x;
+            }
+        } else {
+            double den = l - sc->w2[c];
+            if (fabs(den) < floor_den) den = den < 0.0 ? -floor_den : floor_den;
+            if (c < F && den != 0.0) e = s / den;
+        }
+    }
+    uint32_t hi, lo;
+    bf16_split((float)e, hi, lo);
+    const int j = i >> 7, k = i & 127;
+    unsigned char* base = reinterpret_cast<unsigned char*>(e_img) + (size_t)j * 8192 + (size_t)k * 16 + (c & 7) * 2;
+    *reinterpret_cast<uint16_t*>(base + (c >> 3) * 2048) = (uint16_t)hi;
+    *reinterpret_cast<uint16_t*>(base + (2 + (c >> 3)) * 2048) = (uint16_t)lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// expansion  z += V e , then with the complete z:  rho' = r^T z, ||r||^2 and the finalisation of the iteration
+// (fin_update) or of the slot load (START: p = z, fin_start).  T = double (real sweep, 16 slots) or double2 (8 complex).
+// ------------------------------------------------------------------------------------------------
+template <bool CPX, bool START>
+__global__ void __launch_bounds__(kModalThreads, 1)
+k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __restrict__ p_start, const uint16_t* __restrict__ V, int n_chunks,
+               const uint16_t* __restrict__ e_img, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int F = CPX ? 8 : 16;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;                                      // [kStages][32 KB]
+    unsigned char* eimg = smem_raw + (size_t)kStages * kChunkBytes;      // [kModalMaxChunks][8 KB]
+    ModalSmem* sm = reinterpret_cast<ModalSmem*>(eimg + (size_t)kModalMaxChunks * 8192);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n_use, ksteps_last;
+    uint32_t bytes_last;
+    modal_shape(sc->modes_use, n_use, bytes_last, ksteps_last);
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm->a_full[i], 1); mbar_init(&sm->a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 128); }   // here: accumulator full / drained
+        mbar_init(&sm->e_full, 1);
+        mbar_init(&sm->done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&sm->tmem_base, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+    double acc_rho[16], acc_rr[F];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc_rho[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F; ++k) acc_rr[k] = 0.0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t eb = (uint32_t)(n_use - 1) * 8192u + 8192u;
+            mbar_expect_tx(&sm->e_full, eb);
+            bulk_g2s(eimg, e_img, eb, &sm->e_full);
+            modal_produce(V, n_chunks, n_tiles, n_use, bytes_last, ring, sm);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_bf16(128, 32, 0, 1);   // A = V tile, K-major; B = coefficient image, MN-major
+            mbar_wait_bounded(&sm->e_full, 0);
+            tc_fence_after();
+            uint32_t it = 0, ti = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+                const int ab = ti & 1;
+                mbar_wait_bounded(&sm->b_empty[ab], ((ti >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (int j = 0; j < n_use; ++j, ++it) {
+                    const int st = it % kStages;
+                    mbar_wait_bounded(&sm->a_full[st], (it / kStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
+                    const uint32_t b_addr = smem_u32(eimg + (size_t)j * 8192);
+                    const int ksn = (j == n_use - 1) ? ksteps_last : 8;
+                    for (int ks = 0; ks < ksn; ++ks)   // K = 16 modes per step: two mode blocks
+                        tc_mma_bf16(tmem + 32 * ab, tc_desc(a_addr + ks * 2 * kSm, kSm, kSn), tc_desc(b_addr + ks * 256, 128, 2048), idesc,
+                                    j > 0 || ks > 0);
+                    tc_commit(&sm->a_empty[st]);
+                }
+                tc_commit(&sm->b_full[ab]);
+            }
+        }
+    } else {
+        // ---- epilogue: thread = node row of the tile ----
+        const int q = warp & 3;
+        const int rin = q * 32 + lane;
+        uint32_t ti = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int ab = ti & 1;
+            const int64_t row = t * 128 + rin;
+            const bool valid = row < n_rows;
+            // the row's residual and block-Jacobi part while the tensor core works
+            double rv[16];
+            float zv[16];
+            if (valid) {
+                const double4* src = reinterpret_cast<const double4*>(r + row * 16);
+                const float4* zs = reinterpret_cast<const float4*>(z32 + row * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double4 d = src[k];
+                    rv[4 * k] = d.x; rv[4 * k + 1] = d.y; rv[4 * k + 2] = d.z; rv[4 * k + 3] = d.w;
+                    const float4 zf = zs[k];
+                    zv[4 * k] = zf.x; zv[4 * k + 1] = zf.y; zv[4 * k + 2] = zf.z; zv[4 * k + 3] = zf.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { rv[k] = 0.0; zv[k] = 0.f; }
+            }
+            mbar_wait_bounded(&sm->b_full[ab], (ti >> 1) & 1u);
+            tc_fence_after();
+            float acc[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ab, acc);
+            tc_fence_before();
+            mbar_arrive(&sm->b_empty[ab]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zv[k] += acc[k] + acc[16 + k];
+            if (valid) {
+                float4* zd = reinterpret_cast<float4*>(z32 + row * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) zd[k] = make_float4(zv[4 * k], zv[4 * k + 1], zv[4 * k + 2], zv[4 * k + 3]);
+                if constexpr (START) {
+                    // first search direction of the slots being loaded
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (sc->reset[CPX ? (k >> 1) : k]) p_start[row * 16 + k] = (double)zv[k];
+                }
+                if constexpr (CPX) {
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) {
+                        const double zr = (double)zv[2 * f], zi = (double)zv[2 * f + 1];
+                        acc_rho[2 * f] += rv[2 * f] * zr - rv[2 * f + 1] * zi;
+                        acc_rho[2 * f + 1] += rv[2 * f] * zi + rv[2 * f + 1] * zr;
+                        acc_rr[f] += rv[2 * f] * rv[2 * f] + rv[2 * f + 1] * rv[2 * f + 1];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        acc_rho[k] += rv[k] * (double)zv[k];
+                        acc_rr[k] += rv[k] * rv[k];
+                    }
+                }
+            }
+        }
+    }
+    // ---- block sums in a fixed order (the ring is free: every MMA that reads it has been waited for), then the last block ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 64);
+    double* s_red = reinterpret_cast<double*>(ring);   // [128][3 F]
+    if (tid >= 64) {
+        const int e = tid - 64;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            s_red[e * 3 * F + 3 * f] = CPX ? acc_rho[2 * f] : acc_rho[f];
+            s_red[e * 3 * F + 3 * f + 1] = CPX ? acc_rho[2 * f + 1] : 0.0;
+            s_red[e * 3 * F + 3 * f + 2] = acc_rr[f];
+        }
+    }
+    __syncthreads();
+    if (tid < 3 * F) {
+        double s = 0.0;
+        for (int e = 0; e < 128; ++e) s += s_red[e * 3 * F + tid];
+        partial[(int64_t)blockIdx.x * 3 * F + tid] = s;
+    }
+    finalize_last_block<F, 3, kModalThreads>(partial, &sc->ticket[START ? 2 : 1], [&](int ff, const double* tot) {
+        if constexpr (START) fin_start(sc, ff, tot); else fin_update(sc, ff, tot);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static size_t project_smem() { return (size_t)kStages * kChunkBytes + 2 * 8192 + sizeof(ModalSmem) + 64; }
+static size_t expand_smem() { return (size_t)kStages * kChunkBytes + (size_t)kModalMaxChunks * 8192 + sizeof(ModalSmem) + 64; }
+
+int modal_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, sys->num_sms)); }
+
+void modal_prepare(fdb_system* sys, SweepWork* w) {
+    FDB_REQUIRE(sys->have_modes && sys->n_modes > 0, "no modes: call fdb_modal_compute or fdb_modal_set first");
+    FDB_REQUIRE(sys->tile_rows == 128 && sys->n_tiles > 0, "the modal correction needs the 128-row tiles of the internal order");
+    w->c_part.alloc((size_t)modal_grid(sys) * kModalMaxModes * 16);
+    w->e_img.alloc((size_t)kModalMaxChunks * 4096);
+    static thread_local bool done[64] = {};
+    FDB_REQUIRE(sys->device >= 0 && sys->device < 64, "device index out of range");
+    if (!done[sys->device]) {
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)project_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        done[sys->device] = true;
+    }
+}
+
+// modes the current batch applies: every mode below sqrt(f_max^2 + delta^2), a multiple of 16, at most what is stored
+int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz) {
+    const double two_pi = 6.283185307179586;
+    const double lam_cut = w2_max + (two_pi * delta_hz) * (two_pi * delta_hz);
+    const auto& l = sys->modal_lam_host;
+    int m = (int)(std::upper_bound(l.begin(), l.end(), lam_cut) - l.begin());
+    m = std::max(m, std::min<int>(16, (int)l.size()));
+    m = ((m + 15) / 16) * 16;
+    return std::min(m, sys->mode_chunks * kMC);
+}
+
+// the three launches between K6a and K6b: c = V^T r, e = d c, z += V e (+ rho', ||r||^2, finalisation)
+void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start) {
+    const int G = modal_grid(sys);
+    const double* r = (const double*)w->r.p;
+    k_modal_project<<<G, kModalThreads, project_smem(), sys->stream>>>(r, sys->modal_v.p, sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
+    const int cg = grid_for((int64_t)sys->mode_chunks * kMC * 16, 256);
+    if (w->real)
+        k_modal_coef<false><<<cg, 256, 0, sys->stream>>>(w->c_part.p, G, sys->modal_lam.p, sys->modal_res.p, sys->n_modes, nullptr, w->coef.p, 0, w->F,
+                                                        w->sc.p, w->e_img.p);
+    else
+        k_modal_coef<true><<<cg, 256, 0, sys->stream>>>(w->c_part.p, G, sys->modal_lam.p, sys->modal_res.p, sys->n_modes, sys->modal_adiag.p, w->coef.p,
+                                                       overlay ? sys->n_groups : 0, w->F, w->sc.p, w->e_img.p);
+    double* part = (double*)w->partial.p;
+    auto go = [&](auto kern) {
+        kern<<<G, kModalThreads, expand_smem(), sys->stream>>>(r, w->z32.p, (double*)w->p.p, sys->modal_v.p, sys->mode_chunks, w->e_img.p, w->N,
+                                                              sys->n_tiles, w->sc.p, part);
+    };
+    if (w->real) { if (start) go(k_modal_expand<false, true>); else go(k_modal_expand<false, false>); }
+    else { if (start) go(k_modal_expand<true, true>); else go(k_modal_expand<true, false>); }
+}
+
+// boundary damping of the modes, once per surface assembly
+void modal_build_adiag(fdb_system* sys) {
+    if (sys->have_adiag) return;
+    FDB_REQUIRE(sys->have_modes && sys->modal_x.p, "FP64 modes are needed for the boundary damping terms");
+    const int ng = std::max(1, sys->n_groups);
+    sys->modal_adiag.alloc((size_t)ng * sys->n_modes);
+    sys->modal_adiag.zero(sys->stream);
+    if (sys->n_groups > 0 && sys->have_overlay && sys->n_ov > 0)
+        k_modal_adiag<<<sys->n_modes, 256, (size_t)256 * ng * sizeof(double), sys->stream>>>(sys->modal_x.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
+                                                                                          sys->n_nodes, sys->n_groups, sys->n_modes, sys->modal_adiag.p);
+    FDB_CUDA(cudaGetLastError());
+    sys->have_adiag = true;
+}
+
+// ================================================================================================
+// Modal set-up on the GPU: all modes of H v = lambda Q v below f_cut (FEM3D.eigenfrequency's job, femder/FEM_3D.py:1699-1768,
+// which runs spsolve(Q, H) + ARPACK on the CPU).
+//
+// Chebyshev-filtered subspace iteration.  The filter is a polynomial in Qt^-1 H where Qt^-1 is a fixed, cheap approximation
+// of the inverse mass matrix (no mass solves, no factorisation):
+//     Qt^-1 = sum_{j <= t} (I - D^-1 Q)^j D^-1 ,   D = diag(Q) scaled to the total mass,
+// the order-t Taylor expansion of 1/x around the point of the mass spectrum where smooth functions sit (D^-1 Q u ~ u).
+// t = 0 is mass lumping: its low invariant subspace differs from that of the consistent pencil by O((k h)^2), too much for
+// a mode that a drive frequency comes close to (the coupling its residual leaves is amplified by 1 / (lambda - w^2));
+// t = 1, 2 cost one or two more SpMVs per filter step and leave O((k h)^4), O((k h)^6).  The first outer iteration runs
+// lumped (random start), the following ones raise t until the residuals of the CONSISTENT pencil meet the tolerance.
+// Every outer iteration ends with a Rayleigh-Ritz step on (X^T H X, X^T Q X), so eigenvalues, Q-orthonormality and the
+// residuals that decide convergence are those of (H, Q).  H X and Q X come from the sweep's own fused SpMV (16 columns per
+// launch; Q x = (H + s Q) x / s with s so large that H x / s is below rounding); the dense FP64 Gram products and the small
+// symmetric-definite eigenproblem are cuBLAS / cuSOLVER calls (plain library GEMMs: set-up, not the solver iteration).
+// ================================================================================================
+#define FDB_CUBLAS(expr)                                                                              \
+    do {                                                                                              \
+        cublasStatus_t _s = (expr);                                                                   \
+        if (_s != CUBLAS_STATUS_SUCCESS) throw Error(std::string("femder_b200: cuBLAS call failed: ") + #expr + " (" + std::to_string((int)_s) + ")"); \
+    } while (0)
+#define FDB_CUSOLVER(expr)                                                                            \
+    do {                                                                                              \
+        cusolverStatus_t _s = (expr);                                                                 \
+        if (_s != CUSOLVER_STATUS_SUCCESS) throw Error(std::string("femder_b200: cuSOLVER call failed: ") + #expr + " (" + std::to_string((int)_s) + ")"); \
+    } while (0)
+
+void modal_free_handles(fdb_system* sys) {
+    if (sys->cublas) cublasDestroy((cublasHandle_t)sys->cublas);
+    if (sys->cusolver) cusolverDnDestroy((cusolverDnHandle_t)sys->cusolver);
+    sys->cublas = sys->cusolver = nullptr;
+}
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// batch layout [b][row][16]: column c of batch b is mode 16 b + c
+__global__ void k_modal_random(double* __restrict__ X, int64_t n, uint32_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        X[i] = (double)hash32((uint32_t)i * 2654435761u + seed + (uint32_t)(i >> 32)) * (2.0 / 4294967296.0) - 1.0;
+}
+// row sums of Q and Gershgorin bound: qsum[row] = sum_k Q_k, gmax = max_row sum_k |H_k| / Q_rr   (SELL stream, internal order)
+__global__ void __launch_bounds__(256) k_modal_rows(const int32_t* __restrict__ sell_off, const double2* __restrict__ sell_hq,
+                                                    const double2* __restrict__ diag_hq, int64_t n_rows, double* __restrict__ qsum_rows,
+                                                    unsigned long long* __restrict__ gmax_bits) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double g = 0.0;
+    if (row < n_rows) {
+        const int64_t slice = row >> 3;
+        const int off = sell_off[slice], width = sell_off[slice + 1] - off;
+        double ah = 0.0, sq = 0.0;
+        for (int k = 0; k < width; ++k) {
+            const double2 m = sell_hq[((int64_t)off + k) * 8 + (row & 7)];
+            ah += fabs(m.x);
+            sq += m.y;
+        }
+        qsum_rows[row] = sq;
+        const double d = diag_hq[row].y;
+        g = d > 0.0 ? ah / d : 0.0;
+    }
+    __shared__ double s_g[256];
+    s_g[threadIdx.x] = g;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_g[threadIdx.x] = fmax(s_g[threadIdx.x], s_g[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(s_g[0]));   // non-negative doubles order like integers
+}
+// u = g / d  (and v = u: start of the Taylor sum), d = mass_scale * Q_rr
+__global__ void __launch_bounds__(256) k_mass_start(const double* __restrict__ g, const double2* __restrict__ diag_hq, double mass_scale, int64_t n_elems,
+                                                    double* __restrict__ u, double* __restrict__ v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = g[i] / (diag_hq[i >> 4].y * mass_scale);
+        u[i] = t;
+        if (v) v[i] = t;
+    }
+}
+// v <- v - (qv * qscale) / d ; u += v     (qv = s Q v from the SpMV, qscale = 1 / s)
+__global__ void __launch_bounds__(256) k_mass_term(const double* __restrict__ qv, double qscale, const double2* __restrict__ diag_hq, double mass_scale,
+                                                   int64_t n_elems, double* __restrict__ v, double* __restrict__ u) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = v[i] - qv[i] * qscale / (diag_hq[i >> 4].y * mass_scale);
+        v[i] = t;
+        u[i] += t;
+    }
+}
+// one Chebyshev step on a batch: Ynew = c1 * AY + c2 * Y + c3 * Xold   (Ynew may alias Xold)
+__global__ void __launch_bounds__(256) k_cheb_step(const double* __restrict__ AY, const double* __restrict__ Y, const double* Xold, double c1,
+                                                   double c2, double c3, int64_t n_elems, double* Ynew) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = c1 * AY[i] + c2 * Y[i];
+        if (c3 != 0.0) v += c3 * Xold[i];
+        Ynew[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_modal_scale(double* __restrict__ x, double a, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+// batch [row][16] <-> columns [16 b, 16 b + 16) of the big row-major matrix [row][nb]
+__global__ void __launch_bounds__(256) k_modal_to_big(const double* __restrict__ Xb, int64_t n_rows, int nb, int b, double* __restrict__ big) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 16; i += (int64_t)gridDim.x * blockDim.x)
+        big[(i >> 4) * nb + 16 * b + (i & 15)] = Xb[i];
+}
+__global__ void __launch_bounds__(256) k_modal_from_big(const double* __restrict__ big, int64_t n_rows, int nb, int b, double* __restrict__ Xb) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 16; i += (int64_t)gridDim.x * blockDim.x)
+        Xb[i] = big[(i >> 4) * nb + 16 * b + (i & 15)];
+}
+// per column of a batch: partial[block][c] = sum over the block's rows of (HX - theta_c QX)^2 and of QX^2 (fixed order)
+__global__ void __launch_bounds__(256) k_modal_resid(const double* __restrict__ HX, const double* __restrict__ QX, const double* __restrict__ theta,
+                                                     int64_t n_rows, double* __restrict__ partial /* [grid][32] */) {
+    const int c = threadIdx.x & 15;
+    const double th = theta[c];
+    double a = 0.0, q = 0.0;
+    const int64_t rpb = (n_rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rpb, r1 = min(n_rows, r0 + rpb);
+    for (int64_t r = r0 + (threadIdx.x >> 4); r < r1; r += 16) {
+        const double h = HX[r * 16 + c], qq = QX[r * 16 + c];
+        const double d = h - th * qq;
+        a += d * d;
+        q += qq * qq;
+    }
+    __shared__ double s_a[256], s_q[256];
+    s_a[threadIdx.x] = a; s_q[threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double ta = 0.0, tq = 0.0;
+        for (int k = 0; k < 16; ++k) { ta += s_a[k * 16 + threadIdx.x]; tq += s_q[k * 16 + threadIdx.x]; }
+        partial[(int64_t)blockIdx.x * 32 + threadIdx.x] = ta;
+        partial[(int64_t)blockIdx.x * 32 + 16 + threadIdx.x] = tq;
+    }
+}
+__global__ void k_modal_symmetrize(double* __restrict__ A, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i < n && j < i) {
+        const double v = 0.5 * (A[(int64_t)j * n + i] + A[(int64_t)i * n + j]);
+        A[(int64_t)j * n + i] = v;
+        A[(int64_t)i * n + j] = v;
+    }
+}
+
+// scale s of (H + s Q): s |Q| >> 1e16 |H|, so ((H + s Q) x) / s is Q x to the last bit that matters
+static double modal_qscale(double b_up) { return b_up * 1e22; }
+
+// res[i] = ||H x_i - theta_i Q x_i||_2 / ||Q x_i||_2 (eigenvalue units) of the first n columns of the batches X
+static void modal_residuals(fdb_system* sys, SweepWork* w, const double* X, const std::vector<double>& theta, int n, double s_q,
+                            DevBuf<double>& HX, DevBuf<double>& QX, std::vector<double>& res) {
+    const int64_t N = sys->n_nodes;
+    cudaStream_t s = sys->stream;
+    const size_t bsz = (size_t)N * 16;
+    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>(sys->num_sms * 2, (N + 255) / 256));
+    const int fgrid = (int)std::min<int64_t>(grid_for(N * 16, 256), (int64_t)sys->num_sms * 8);
+    DevBuf<double> dtheta, rpart;
+    dtheta.alloc(16);
+    rpart.alloc((size_t)rgrid * 32);
+    HX.alloc(bsz); QX.alloc(bsz);
+    std::vector<double> hp((size_t)rgrid * 32), th16(16);
+    res.assign(n, 0.0);
+    for (int bt = 0; 16 * bt < n; ++bt) {
+        const double* xb = X + (size_t)bt * bsz;
+        modal_spmv_w2(sys, w, 0.0);
+        modal_spmv(sys, w, xb, HX.p);
+        modal_spmv_w2(sys, w, -s_q);
+        modal_spmv(sys, w, xb, QX.p);
+        k_modal_scale<<<fgrid, 256, 0, s>>>(QX.p, 1.0 / s_q, (int64_t)bsz);
+        for (int c = 0; c < 16; ++c) th16[c] = (16 * bt + c < (int)theta.size()) ? theta[16 * bt + c] : 0.0;
+        FDB_CUDA(cudaMemcpyAsync(dtheta.p, th16.data(), 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+        k_modal_resid<<<rgrid, 256, 0, s>>>(HX.p, QX.p, dtheta.p, N, rpart.p);
+        FDB_CUDA(cudaMemcpyAsync(hp.data(), rpart.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FDB_CUDA(cudaStreamSynchronize(s));
+        for (int c = 0; c < 16 && 16 * bt + c < n; ++c) {
+            double ra = 0.0, rq = 0.0;
+            for (int g = 0; g < rgrid; ++g) { ra += hp[(size_t)g * 32 + c]; rq += hp[(size_t)g * 32 + 16 + c]; }
+            res[16 * bt + c] = std::sqrt(ra) / (std::sqrt(rq) + 1e-300);
+        }
+    }
+    FDB_CUDA(cudaGetLastError());
+}
+
+// upper bound of the spectrum of D^-1 H (Gershgorin) and the total-mass scale of D = mass_scale * diag(Q)
+static void modal_bounds(fdb_system* sys, double& mass_scale, double& b_up) {
+    const int64_t N = sys->n_nodes;
+    cudaStream_t s = sys->stream;
+    DevBuf<double> qrow;
+    DevBuf<unsigned long long> gbits;
+    qrow.alloc(N);
+    gbits.alloc(1);
+    gbits.zero(s);
+    k_modal_rows<<<grid_for(N, 256), 256, 0, s>>>(sys->sell_off.p, sys->sell_hq.p, sys->diag_hq.p, N, qrow.p, gbits.p);
+    FDB_CUDA(cudaGetLastError());
+    std::vector<double> h_qrow(N);
+    std::vector<double2> h_diag(N);
+    unsigned long long h_g = 0;
+    FDB_CUDA(cudaMemcpyAsync(h_qrow.data(), qrow.p, N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FDB_CUDA(cudaMemcpyAsync(h_diag.data(), sys->diag_hq.p, N * sizeof(double2), cudaMemcpyDeviceToHost, s));
+    FDB_CUDA(cudaMemcpyAsync(&h_g, gbits.p, sizeof(h_g), cudaMemcpyDeviceToHost, s));
+    FDB_CUDA(cudaStreamSynchronize(s));
+    double mass = 0.0, trq = 0.0;
+    for (int64_t i = 0; i < N; ++i) { mass += h_qrow[i]; trq += h_diag[i].y; }
+    FDB_REQUIRE(mass > 0.0 && trq > 0.0, "the mass matrix has no positive total mass");
+    mass_scale = mass / trq;
+    double gersh;
+    memcpy(&gersh, &h_g, sizeof(double));
+    b_up = 1.01 * gersh / mass_scale;
+    FDB_REQUIRE(b_up > 0.0 && std::isfinite(b_up), "could not bound the spectrum of D^-1 H");
+}
+
+// modal_x (FP64 batches) + modal_lam_host -> bf16 tiles, device eigenvalues, per-mode residuals of the consistent pencil
+void modal_finish(fdb_system* sys, int n_modes) {
+    FDB_REQUIRE(sys->have_order && sys->tile_rows == 128, "the modal correction needs the 128-row tiles of the internal order");
+    n_modes = std::min(n_modes, kModalMaxModes);
+    sys->n_modes = n_modes;
+    sys->modal_lam_host.resize(n_modes);
+    sys->mode_chunks = (n_modes + kMC - 1) / kMC;
+    sys->modal_lam.alloc(n_modes);
+    FDB_CUDA(cudaMemcpyAsync(sys->modal_lam.p, sys->modal_lam_host.data(), n_modes * sizeof(double), cudaMemcpyHostToDevice, sys->stream));
+    sys->modal_v.alloc((size_t)sys->n_tiles * sys->mode_chunks * (kChunkBytes / 2));
+    const int64_t work = sys->n_tiles * 128 * sys->mode_chunks * 16;
+    k_modal_pack<<<grid_for(work, 256), 256, 0, sys->stream>>>(sys->modal_x.p, sys->n_nodes, sys->n_tiles, n_modes, sys->mode_chunks, sys->modal_v.p);
+    FDB_CUDA(cudaGetLastError());
+    // How far each stored vector is from an eigenvector: k_modal_coef bounds 1 / (lambda - w^2) by it, so an inaccurate mode that a
+    // drive frequency comes close to is deflated only as far as it can be trusted.
+    double mass_scale, b_up;
+    modal_bounds(sys, mass_scale, b_up);
+    SweepWork* w = modal_spmv_begin(sys);
+    DevBuf<double> HX, QX;
+    std::vector<double> res;
+    modal_residuals(sys, w, sys->modal_x.p, sys->modal_lam_host, n_modes, modal_qscale(b_up), HX, QX, res);
+    sys->modal_res_host = res;
+    sys->modal_res.alloc(n_modes);
+    FDB_CUDA(cudaMemcpyAsync(sys->modal_res.p, res.data(), n_modes * sizeof(double), cudaMemcpyHostToDevice, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
+    sys->have_modes = true;
+    sys->have_adiag = false;
+    invalidate_graph(sys);
+}
+
+void modal_set(fdb_system* sys, int n_modes, const double* lam, const double* V) {
+    FDB_REQUIRE(sys->have_order && sys->have_hq, "set the pattern and H, Q before the modes");
+    FDB_REQUIRE(n_modes > 0 && lam && V, "bad arguments");
+    const int64_t N = sys->n_nodes;
+    const int m = std::min(n_modes, kModalMaxModes);
+    sys->modal_lam_host.resize(m);
+    FDB_CUDA(cudaMemcpy(sys->modal_lam_host.data(), lam, m * sizeof(double), cudaMemcpyDefault));
+    for (int i = 1; i < m; ++i) FDB_REQUIRE(sys->modal_lam_host[i] >= sys->modal_lam_host[i - 1], "eigenvalues must ascend");
+    const int nb = (m + 15) / 16;
+    sys->modal_x.alloc((size_t)nb * N * 16);
+    sys->modal_x.zero(sys->stream);
+    DevBuf<double> tmp;
+    tmp.alloc(N);
+    for (int i = 0; i < m; ++i) {
+        FDB_CUDA(cudaMemcpyAsync(tmp.p, V + (int64_t)i * N, N * sizeof(double), cudaMemcpyDefault, sys->stream));
+        k_modal_scatter<<<grid_for(N, 256), 256, 0, sys->stream>>>(tmp.p, sys->perm.p, N, i, sys->modal_x.p);
+    }
+    FDB_CUDA(cudaGetLastError());
+    modal_finish(sys, m);
+}
+
+void modal_get(fdb_system* sys, double* lam, double* V) {
+    FDB_REQUIRE(sys->have_modes, "no modes");
+    const int64_t N = sys->n_nodes;
+    if (lam) FDB_CUDA(cudaMemcpy(lam, sys->modal_lam_host.data(), sys->n_modes * sizeof(double), cudaMemcpyDefault));
+    if (V) {
+        FDB_REQUIRE(sys->modal_x.p, "the FP64 modes were released");
+        DevBuf<double> tmp;
+        tmp.alloc(N);
+        for (int i = 0; i < sys->n_modes; ++i) {
+            k_modal_gather<<<grid_for(N, 256), 256, 0, sys->stream>>>(sys->modal_x.p, sys->perm.p, N, i, tmp.p);
+            FDB_CUDA(cudaMemcpyAsync(V + (int64_t)i * N, tmp.p, N * sizeof(double), cudaMemcpyDefault, sys->stream));
+        }
+        FDB_CUDA(cudaStreamSynchronize(sys->stream));
+    }
+}
+
+// f_cut_hz: every mode below it is kept.  f_acc_hz (<= f_cut_hz): the modes below it are the ones a drive frequency can come
+// close to - they must meet `tol` (relative residual ||H x - theta Q x|| / (theta ||Q x||) of the consistent pencil); the modes
+// between f_acc and f_cut only ever see |lambda - w^2| >= lambda_cut - lambda_acc and may stay an order of magnitude coarser.
+void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint, double tol, int max_outer, int* n_found) {
+    FDB_REQUIRE(sys->have_order && sys->have_hq, "set the pattern and H, Q before the modes");
+    FDB_REQUIRE(sys->tile_rows == 128 && sys->n_tiles > 0, "the modal set-up needs the 128-row tiles of the internal order");
+    FDB_REQUIRE(f_cut_hz > 0.0, "f_cut_hz must be positive");
+    if (tol <= 0.0) tol = 2e-2;   // what the coarse correction needs (tests/research/modal_deflation_variants.py); modal analysis asks for less
+    if (max_outer <= 0) max_outer = 12;
+    if (f_acc_hz <= 0.0 || f_acc_hz > f_cut_hz) f_acc_hz = f_cut_hz;
+    const int64_t N = sys->n_nodes;
+    cudaStream_t s = sys->stream;
+    const double two_pi = 6.283185307179586;
+    const double lam_cut = (two_pi * f_cut_hz) * (two_pi * f_cut_hz);
+    const double lam_acc = (two_pi * f_acc_hz) * (two_pi * f_acc_hz);
+    if (!sys->cublas) {
+        cublasHandle_t h;
+        FDB_CUBLAS(cublasCreate(&h));
+        sys->cublas = h;
+    }
+    if (!sys->cusolver) {
+        cusolverDnHandle_t h;
+        FDB_CUSOLVER(cusolverDnCreate(&h));
+        sys->cusolver = h;
+    }
+    cublasHandle_t cb = (cublasHandle_t)sys->cublas;
+    cusolverDnHandle_t cs = (cusolverDnHandle_t)sys->cusolver;
+    FDB_CUBLAS(cublasSetStream(cb, s));
+    FDB_CUSOLVER(cusolverDnSetStream(cs, s));
+
+    double mass_scale, b_up;
+    modal_bounds(sys, mass_scale, b_up);
+    const double s_q = modal_qscale(b_up);
+
+    // block size: the caller's estimate of the mode count plus a guard band, in batches of 16 columns
+    const int cap_cols = (int)std::min<int64_t>(kModalMaxModes + 128, std::max<int64_t>(16, (N / 3 / 16) * 16));
+    int nb = n_hint > 0 ? ((int)(1.12 * n_hint) + 24 + 15) / 16 * 16 : 64;
+    nb = std::max(16, std::min(nb, cap_cols));
+
+    SweepWork* w = modal_spmv_begin(sys);
+    const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr;   // progress lines on stderr; changes nothing that is computed
+    std::vector<double> theta, res;
+    int wanted = 0, outer = 0, order_t = 0;
+    const int max_order = tol < 1e-2 ? 4 : 1;
+    double worst = 0.0, worst_prev = 1e300;
+    DevBuf<double> X, Y, U, V1, T, big_x, big_hx, big_qx, big_new, Hs, Qs, W;
+    DevBuf<int> dinfo;
+    dinfo.alloc(1);
+    const int fgrid = (int)std::min<int64_t>(grid_for(N * 16, 256), (int64_t)sys->num_sms * 8);
+    bool have_ritz = false;
+    double a_low = lam_cut * 1.21;   // lower edge of the interval the filter damps (1.1 f_cut until the block's own upper edge is known)
+    const size_t bsz = (size_t)N * 16;
+    // u = Qt^-1 (H y) for one batch: order_t extra SpMVs with Q
+    auto apply_a = [&](const double* y, double* u) {
+        modal_spmv_w2(sys, w, 0.0);
+        modal_spmv(sys, w, y, T.p);
+        k_mass_start<<<fgrid, 256, 0, s>>>(T.p, sys->diag_hq.p, mass_scale, (int64_t)bsz, u, order_t > 0 ? V1.p : nullptr);
+        if (order_t > 0) modal_spmv_w2(sys, w, -s_q);
+        for (int j = 0; j < order_t; ++j) {
+            modal_spmv(sys, w, V1.p, T.p);
+            k_mass_term<<<fgrid, 256, 0, s>>>(T.p, 1.0 / s_q, sys->diag_hq.p, mass_scale, (int64_t)bsz, V1.p, u);
+        }
+    };
+    for (;;) {
+        const int nbat = nb / 16;
+        if (!have_ritz) {
+            X.alloc((size_t)nbat * bsz);
+            k_modal_random<<<fgrid, 256, 0, s>>>(X.p, (int64_t)nbat * bsz, 12345u);
+        }
+        Y.alloc(bsz); U.alloc(bsz); V1.alloc(bsz); T.alloc(bsz);
+        big_x.alloc((size_t)N * nb); big_hx.alloc((size_t)N * nb); big_qx.alloc((size_t)N * nb); big_new.alloc((size_t)N * nb);
+        Hs.alloc((size_t)nb * nb); Qs.alloc((size_t)nb * nb); W.alloc(nb);
+        int lwork = 0;
+        FDB_CUSOLVER(cusolverDnDsygvd_bufferSize(cs, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, Hs.p, nb, Qs.p, nb,
+                                                 W.p, &lwork));
+        DevBuf<double> work;
+        work.alloc(std::max(1, lwork));
+        bool grown = false, converged = false;
+        for (; outer < max_outer && !converged;) {
+            // ---- filter: X <- p(Qt^-1 H) X, degree from the ratio of the interval to damp and the interval to keep ----
+            // sum_{j <= t} (1 - x)^j <= t + 1 on the mass spectrum x in (0, 1]: a safe upper end for the spectrum of Qt^-1 H (components
+            // above the filter's interval would be amplified, not damped)
+            const double a = a_low, b = b_up * (1.0 + order_t);
+            const int deg = (int)std::max(12.0, std::min(160.0, std::ceil(3.0 * std::sqrt(b / a))));
+            const double e = 0.5 * (b - a), c = 0.5 * (b + a);
+            for (int bt = 0; bt < nbat; ++bt) {
+                double* xb = X.p + (size_t)bt * bsz;
+                double sigma = e / (0.0 - c);
+                const double sigma1 = sigma;
+                apply_a(xb, U.p);
+                k_cheb_step<<<fgrid, 256, 0, s>>>(U.p, xb, nullptr, sigma1 / e, -c * sigma1 / e, 0.0, (int64_t)bsz, Y.p);   // Y = (sigma1 / e)(A X - c X)
+                double *px = xb, *py = Y.p;   // px = previous iterate, py = current one
+                for (int i = 2; i <= deg; ++i) {
+                    const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+                    apply_a(py, U.p);
+                    // Ynew = (2 sigma2 / e)(A Y - c Y) - sigma sigma2 X, written over X (its last use)
+                    k_cheb_step<<<fgrid, 256, 0, s>>>(U.p, py, px, 2.0 * sigma2 / e, -2.0 * sigma2 * c / e, -sigma * sigma2, (int64_t)bsz, px);
+                    std::swap(px, py);
+                    sigma = sigma2;
+                }
+                if (py != xb) FDB_CUDA(cudaMemcpyAsync(xb, py, bsz * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            }
+            FDB_CUDA(cudaGetLastError());
+            // ---- Rayleigh-Ritz on (H, Q) ----
+            for (int bt = 0; bt < nbat; ++bt) {
+                double* xb = X.p + (size_t)bt * bsz;
+                modal_spmv_w2(sys, w, 0.0);
+                modal_spmv(sys, w, xb, Y.p);                 // H X
+                modal_spmv_w2(sys, w, -s_q);
+                modal_spmv(sys, w, xb, T.p);                 // s Q X
+                k_modal_scale<<<fgrid, 256, 0, s>>>(T.p, 1.0 / s_q, (int64_t)bsz);
+                k_modal_to_big<<<fgrid, 256, 0, s>>>(xb, N, nb, bt, big_x.p);
+                k_modal_to_big<<<fgrid, 256, 0, s>>>(Y.p, N, nb, bt, big_hx.p);
+                k_modal_to_big<<<fgrid, 256, 0, s>>>(T.p, N, nb, bt, big_qx.p);
+            }
+            FDB_CUDA(cudaGetLastError());
+            const double one = 1.0, zero = 0.0;
+            // row-major [N][nb] = column-major (nb x N): Hs = X^T (H X), Qs = X^T (Q X)
+            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, (int)N, &one, big_x.p, nb, big_hx.p, nb, &zero, Hs.p, nb));
+            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, (int)N, &one, big_x.p, nb, big_qx.p, nb, &zero, Qs.p, nb));
+            k_modal_symmetrize<<<dim3((nb + 127) / 128, nb), 128, 0, s>>>(Hs.p, nb);
+            k_modal_symmetrize<<<dim3((nb + 127) / 128, nb), 128, 0, s>>>(Qs.p, nb);
+            FDB_CUSOLVER(cusolverDnDsygvd(cs, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nb, Hs.p, nb, Qs.p, nb, W.p,
+                                          work.p, lwork, dinfo.p));
+            int info = 0;
+            theta.resize(nb);
+            FDB_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            FDB_CUDA(cudaMemcpyAsync(theta.data(), W.p, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+            FDB_CUDA(cudaStreamSynchronize(s));
+            FDB_REQUIRE(info == 0, "the Rayleigh-Ritz eigenproblem of the modal set-up failed (the filtered block lost rank)");
+            // X <- X Y (Ritz vectors, Q-orthonormal, ascending): (X Y)^T = Y^T X^T in the column-major view
+            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, nb, (int)N, nb, &one, Hs.p, nb, big_x.p, nb, &zero, big_new.p, nb));
+            for (int bt = 0; bt < nbat; ++bt) k_modal_from_big<<<fgrid, 256, 0, s>>>(big_new.p, N, nb, bt, X.p + (size_t)bt * bsz);
+            have_ritz = true;
+            ++outer;
+            wanted = (int)(std::upper_bound(theta.begin(), theta.end(), lam_cut) - theta.begin());
+            if (wanted >= nb - 8 && nb < cap_cols) { grown = true; break; }   // the block holds no guard band: widen it
+            // ---- residuals of the wanted pairs on the consistent pencil ----
+            modal_residuals(sys, w, X.p, theta, wanted, s_q, Y, T, res);
+            const double th_ref = (two_pi * 10.0) * (two_pi * 10.0);
+            worst = 0.0;
+            double worst_hi = 0.0;
+            for (int i = 0; i < wanted; ++i) {
+                const double rel = res[i] / std::max(std::fabs(theta[i]), th_ref);
+                if (theta[i] <= lam_acc) worst = std::max(worst, rel); else worst_hi = std::max(worst_hi, rel);
+            }
+            a_low = std::max(lam_cut * 1.05, theta[nb - 1]);   // next filter: damp everything above the block's own upper edge
+            if (verbose)
+                fprintf(stderr, "[fdb modal] outer %d: block %d, wanted %d, mass order %d, degree %d, worst rel residual %.3e (below f_acc) %.3e (above), top Ritz f %.1f Hz\n",
+                        outer, nb, wanted, order_t, deg, worst, worst_hi, std::sqrt(std::max(theta[nb - 1], 0.0)) / two_pi);
+            if (worst <= tol && worst_hi <= std::max(10.0 * tol, 0.1)) { converged = true; break; }
+            // the mass approximation of the filter limits what the subspace can reach: raise its order when progress stalls,
+            // stop when the highest order stalls too (the residuals are reported, the sweep does not depend on them being small)
+            if (outer >= 2 && worst > 0.5 * worst_prev) {
+                if (order_t < max_order) ++order_t; else { converged = true; break; }
+            }
+            worst_prev = worst;
+        }
+        if (!grown) break;
+        // widen: keep the Ritz vectors, append random columns
+        const int nb2 = std::min(cap_cols, std::max(nb + 64, (int)(nb * 1.6) / 16 * 16));
+        DevBuf<double> X2;
+        X2.alloc((size_t)(nb2 / 16) * bsz);
+        k_modal_random<<<fgrid, 256, 0, s>>>(X2.p, (int64_t)(nb2 / 16) * bsz, 777u + (uint32_t)nb2);
+        FDB_CUDA(cudaMemcpyAsync(X2.p, X.p, (size_t)nbat * bsz * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        FDB_CUDA(cudaStreamSynchronize(s));
+        std::swap(X.p, X2.p); std::swap(X.n, X2.n);
+        nb = nb2;
+        a_low = lam_cut * 1.21;
+        order_t = 0;
+        worst_prev = 1e300;
+        if (outer >= max_outer) break;
+    }
+    FDB_REQUIRE(wanted > 0, "no mode below f_cut");
+    const int m = std::min(wanted, kModalMaxModes);
+    sys->modal_lam_host.assign(theta.begin(), theta.begin() + m);
+    const int keep_bat = (m + 15) / 16;
+    sys->modal_x.alloc((size_t)keep_bat * N * 16);
+    FDB_CUDA(cudaMemcpyAsync(sys->modal_x.p, X.p, (size_t)keep_bat * N * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    FDB_CUDA(cudaStreamSynchronize(s));
+    modal_finish(sys, m);
+    sys->modal_outer = outer;
+    sys->modal_resid = worst;
+    sys->modal_block = nb;
+    sys->modal_order = order_t;
+    if (n_found) *n_found = m;
+}
+
+}  // namespace fdb

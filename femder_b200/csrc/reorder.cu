@@ -84,7 +84,9 @@ void build_order(fdb_system* sys) {
     FDB_CUDA(cudaStreamSynchronize(s));
 
     int kTileRows = kMaxTileRows;
-    if (const char* e = getenv("FDB_TILE_ROWS")) kTileRows = (atoi(e) == 64) ? 64 : 128;   // tuning aid
+#ifdef FDB_TUNING
+    if (const char* e = getenv("FDB_TILE_ROWS")) kTileRows = (atoi(e) == 64) ? 64 : 128;   // tuning aid (tuning builds only)
+#endif
     sys->tile_rows = kTileRows;
     std::vector<int32_t> order;
     blob_order(N, indptr.data(), indices.data(), kTileRows, order);
@@ -236,6 +238,7 @@ void build_sell(fdb_system* sys) {
     FDB_REQUIRE(sys->have_order, "internal order missing");
     const int64_t n = sys->sell_entries;
     sys->have_blk = false;   // the block-Jacobi inverses belong to the previous values
+    modal_reset(sys);        // ... and so do the modes
     sys->sell_hq.alloc(n ? n : 1);
     if (n) k_sell_values<<<grid_for(n, 256), 256, 0, sys->stream>>>(sys->sell_src.p, sys->hq.p, n, sys->sell_hq.p);
     FDB_CUDA(cudaGetLastError());

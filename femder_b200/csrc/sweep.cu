@@ -11,8 +11,7 @@
 //   overlay        ov_ptr[N+1], ov_cg[n_ov] (col, group), ov_val[n_ov]  boundary admittance entries
 //   vectors        [N][F] complex128 (double2), frequency fastest: a gather of x[col][0..F) is one
 //                  contiguous 16*F-byte segment (a full 128-byte line at F = 8)
-#include "common.cuh"
-#include "../../include/femder_b200.h"
+#include "solver.cuh"
 #include <algorithm>
 #include <array>
 #include <map>
@@ -20,63 +19,6 @@
 #include <type_traits>
 
 namespace fdb {
-
-constexpr int kMaxF = 64;   // widest batch: small meshes are launch-bound, wide batches amortise the fixed costs
-constexpr int kBlock = 256;
-
-struct __align__(16) Scalars {
-    double2 rho[kMaxF];    // r^T z (unconjugated)
-    double2 pq[kMaxF];     // p^T G p
-    double2 beta[kMaxF];
-    double2 alpha[kMaxF];  // step length of the iteration whose x update is still pending (applied by k_pupdate)
-    double rr[kMaxF];      // ||r||^2
-    double bb[kMaxF];      // ||b||^2
-    double w2[kMaxF];      // omega^2
-    double2 rhs_scale[kMaxF];  // -1j*omega
-    double rt[kMaxF];      // ||b - G x||^2 of the returned solution (true residual check)
-    int active[kMaxF];
-    int iters[kMaxF];
-    int reset[kMaxF];      // slots being (re)loaded with a new frequency: set-up kernels touch only these
-    int xpend[kMaxF];      // the slot took a step in the last k_update: k_pupdate owes it x += alpha p
-    int src_set[kMaxF];    // which source set (right-hand side) the slot solves: multi-RHS sweeps share G(w)
-    int bb_from_r0;        // ||b||^2 is taken from the start residual (general right-hand sides, zero starting guess)
-    double tol2;
-    unsigned int ticket[4];
-};
-
-struct SweepWork {
-    int F = 0;
-    int64_t N = 0;
-    int n_groups = 0;
-    int grid = 0;
-    DevBuf<double2> x, r, p, q, dinv, tmp;  // [N][F]
-    DevBuf<double2> coef;              // [n_groups][F]  1j*omega*mu
-    DevBuf<double2> rcoef;             // [n_rhs_vec][F] coefficients of the extra right-hand-side vectors
-    DevBuf<int32_t> src_set_ptr;       // [n_sets+1] partition of the (deduplicated) source arrays into right-hand sides
-    int n_rn = 0;                      // nodes touched by extra right-hand-side vectors (complex sweeps only)
-    DevBuf<int32_t> rn_nodes, rn_ptr, rn_vec;   // per listed node: its (vector, value) terms
-    DevBuf<double> rn_val;
-    DevBuf<double2> partial;           // [grid][F][2]
-    DevBuf<Scalars> sc;
-    DevBuf<double2> stage;             // [F][N] pN export staging
-    DevBuf<double2> rcv_out;           // [F][n_rcv]
-    cudaGraphExec_t graph = nullptr;
-    int graph_iters = 0;
-    int graph_F = 0;
-    bool graph_overlay = false;
-    int spmv_cfg = 0;             // FDB_SPMV_CFG (tuning aid): 0 default, 1..3 other bulk-copy pipeline shapes, >= 8 plain kernel only
-    int tma_stage_entries[3] = {0, 0, 0};
-    int spmv_bps = 0;             // FDB_SPMV_BPS: cap on resident blocks per SM (tuning aid)
-    int blob_lpr = 2;             // FDB_BLOB_LPR: lanes per row of k_spmv_blob (tuning aid)
-    int precond = 0;              // 0 Jacobi, 1 block-Jacobi (real sweeps, F <= 16, 128-row tiles)
-    bool graph_precond = false;
-    DevBuf<float> z32;            // [N][F] preconditioned residual of the block-Jacobi path
-    bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
-    int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
-    bool real = false;            // the current sweep runs in real arithmetic (rigid walls, real sources)
-    bool graph_real = false;
-};
-
 void free_sweep_work(SweepWork* w) {
     if (!w) return;
     if (w->graph) cudaGraphExecDestroy(w->graph);
@@ -91,130 +33,6 @@ void invalidate_graph(fdb_system* sys) {
     }
 }
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
-    const double d = b.x * b.x + b.y * b.y;
-    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
-}
-
-// ---- value type of the Krylov vectors: double2 (complex sweep) or double (rigid-wall sweep, see run_sweep) ----
-// A rigid-wall system G = H - w^2 Q is real and b = -1j*w*q is purely imaginary for real q, so p = 1j*u with
-// G u = -w q: the whole solve runs in real arithmetic on half the bytes.  Scalars (alpha, beta, rho) stay double2.
-__device__ __forceinline__ double2 s_mul(double2 s, double2 v) { return cmul(s, v); }
-__device__ __forceinline__ double s_mul(double2 s, double v) { return s.x * v; }
-__device__ __forceinline__ double2 r_mul(double g, double2 v) { return make_double2(g * v.x, g * v.y); }
-__device__ __forceinline__ double r_mul(double g, double v) { return g * v; }
-__device__ __forceinline__ double2 v_mul(double2 a, double2 b) { return cmul(a, b); }
-__device__ __forceinline__ double v_mul(double a, double b) { return a * b; }
-__device__ __forceinline__ double2 v_dot(double2 a, double2 b) { return cmul(a, b); }   // unconjugated
-__device__ __forceinline__ double2 v_dot(double a, double b) { return make_double2(a * b, 0.0); }
-__device__ __forceinline__ double v_n2(double2 a) { return a.x * a.x + a.y * a.y; }
-__device__ __forceinline__ double v_n2(double a) { return a * a; }
-__device__ __forceinline__ double2 v_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double v_add(double a, double b) { return a + b; }
-__device__ __forceinline__ double2 v_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double v_sub(double a, double b) { return a - b; }
-template <typename T> __device__ __forceinline__ T v_zero();
-template <> __device__ __forceinline__ double2 v_zero<double2>() { return make_double2(0.0, 0.0); }
-template <> __device__ __forceinline__ double v_zero<double>() { return 0.0; }
-// what leaves the solver is always complex: p = u (complex sweep) or p = 1j*u (real sweep)
-__device__ __forceinline__ double2 v_out(double2 a) { return a; }
-__device__ __forceinline__ double2 v_out(double a) { return make_double2(0.0, a); }
-
-// Sum `v` over the lanes that share lane % F, result valid in lanes 0..F-1.
-template <int F>
-__device__ __forceinline__ double warp_sum_by_f(double v) {
-#pragma unroll
-    for (int o = 16; o >= F; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// The last block to arrive adds the per-block partials partial[b][f][slot] of all blocks in a fixed order
-// (deterministic) and calls `fin(f, totals)` from one thread per f.  Call with the block's partials already
-// written by threads that then reach this point (all threads of the block must call it).
-template <int F, int NV, int BLOCK, typename Fin>
-__device__ __forceinline__ void finalize_last_block(double* __restrict__ partial, unsigned int* __restrict__ ticket, Fin fin) {
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // each f gets BLOCK/F threads striding over the blocks, then a fixed-order sum over those threads
-    constexpr int TPF = BLOCK / F;
-    const int f = threadIdx.x % F, j = threadIdx.x / F;
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0;
-    if (j < TPF) {
-        // U independent loads in flight per round, added in block order: the chain of gridDim.x / TPF dependent L2 round
-        // trips was the tail of every reducing kernel (30 us of k_update's 48 us on a 21 735-DOF mesh at 64 slots)
-        constexpr int U = 8;
-        for (int b = j; b < (int)gridDim.x; b += TPF * U) {
-            double t[U][NV];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int bb = b + u * TPF;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) t[u][i] = (bb < (int)gridDim.x) ? __ldcg(&partial[((int64_t)bb * F + f) * NV + i]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int i = 0; i < NV; ++i) acc[i] += t[u][i];
-            }
-        }
-    }
-    __shared__ double s_fin[BLOCK][NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s_fin[threadIdx.x][i] = acc[i];
-    __syncthreads();
-    if (threadIdx.x < F) {
-        double tot[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) tot[i] = 0;
-        for (int k = 0; k < TPF; ++k) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) tot[i] += s_fin[k * F + threadIdx.x][i];
-        }
-        fin(threadIdx.x, tot);
-        if (threadIdx.x == 0) *ticket = 0;
-    }
-}
-
-// lanes = (.., f): per-thread values of frequency f = threadIdx.x % F -> block partial -> finalize
-template <int F, int NV, int BLOCK, typename Fin>
-__device__ __forceinline__ void block_reduce_finalize(const double (&v)[NV], double* __restrict__ partial,
-                                                      unsigned int* __restrict__ ticket, Fin fin) {
-    __shared__ double s_red[BLOCK / 32][32][NV];
-    constexpr int SW = F < 32 ? F : 32;   // distinct frequencies inside one warp
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double w[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) w[i] = warp_sum_by_f<F>(v[i]);
-    if (lane < SW) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s_red[warp][lane][i] = w[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < F) {
-        const int l = threadIdx.x & 31;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double s = 0;
-            for (int k = 0; k < BLOCK / 32; ++k)
-                if ((k * 32 + l) % F == (int)threadIdx.x) s += s_red[k][l][i];   // warps whose lane l carries this frequency
-            partial[((int64_t)blockIdx.x * F + threadIdx.x) * NV + i] = s;
-        }
-    }
-    finalize_last_block<F, NV, BLOCK>(partial, ticket, fin);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K5: y[row][f] = sum_k (H_k - w2_f Q_k) x[col_k][f] + sum_ov (coef[g][f] * A_ov) x[col_ov][f]
@@ -433,35 +251,6 @@ k_spmv_rows(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ se
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 struct __align__(32) d4 { double v[4]; };   // one 256-bit access (LDG/STG.E.256 on sm_100): 2 complex or 4 real values
 __device__ __forceinline__ d4 ld256(const double* p) {
     d4 r;
@@ -925,40 +714,6 @@ __device__ __forceinline__ T jacobi_apply(const double2* __restrict__ dinv, cons
     return jacobi_mul<T, ONFLY>(jacobi_load<T, F, ONFLY>(dinv, diag_hq, i), w2, rv);
 }
 
-// last-block finalisation of K6a: beta = rho'/rho, rho = rho', convergence flag, iteration count, alpha kept for K6b
-__device__ __forceinline__ void fin_update(Scalars* __restrict__ sc, int ff, const double* tot) {
-    if (sc->active[ff]) {
-        const double2 rho_old = sc->rho[ff];
-        const double2 rho_new = make_double2(tot[0], tot[1]);
-        const double2 pq = sc->pq[ff];
-        sc->alpha[ff] = (pq.x != 0.0 || pq.y != 0.0) ? cdiv(rho_old, pq) : make_double2(0.0, 0.0);   // what every block used
-        sc->xpend[ff] = 1;
-        double2 beta = make_double2(0.0, 0.0);
-        if (rho_old.x != 0.0 || rho_old.y != 0.0) beta = cdiv(rho_new, rho_old);
-        sc->rho[ff] = rho_new;
-        sc->rr[ff] = tot[2];
-        sc->iters[ff] += 1;
-        const bool conv = !(tot[2] > sc->tol2 * sc->bb[ff]);  // also stops on NaN
-        if (conv) { sc->active[ff] = 0; beta = make_double2(0.0, 0.0); }
-        sc->beta[ff] = beta;
-    } else {
-        sc->beta[ff] = make_double2(0.0, 0.0);
-        sc->xpend[ff] = 0;
-    }
-}
-// ... of the slot (re)load: rho = r^T z, activate the slot if its residual is above tolerance
-__device__ __forceinline__ void fin_start(Scalars* __restrict__ sc, int ff, const double* tot) {
-    if (!sc->reset[ff]) return;
-    sc->rho[ff] = make_double2(tot[0], tot[1]);
-    sc->rr[ff] = tot[2];
-    sc->beta[ff] = make_double2(0.0, 0.0);
-    sc->pq[ff] = make_double2(0.0, 0.0);
-    sc->iters[ff] = 0;
-    if (sc->bb_from_r0) sc->bb[ff] = tot[2];
-    sc->active[ff] = (tot[2] > sc->tol2 * sc->bb[ff]) ? 1 : 0;
-    sc->reset[ff] = 0;
-}
-
 // The streaming loops below handle kVecU elements per thread and round, ALL loads of a round issued before the first
 // store: a thread of a real sweep moves 8 bytes per access, and with one element per round (the store to r ahead of
 // the next round's loads, which the compiler must keep in order) a full SM has only ~32 KB in flight - 3 TB/s.
@@ -1060,7 +815,9 @@ constexpr int kBjTile = 128;
 constexpr int kBjPacked = kBjTile * (kBjTile + 1) / 2;   // floats of a packed lower triangle (reorder.cu)
 // CPX: a complex batch of F slots is 2 F real columns per row (re, im interleaved): the product treats them as independent
 // reals (B is real), only alpha and the unconjugated rho' = r^T z couple a slot's two columns (partner = lane ^ 1).
-template <int F, bool START, bool CPX>
+// MODAL: the modal coarse correction (modal.cu) completes z, so this kernel only leaves r and z_bj = B r (in z32, also when
+// loading a slot) and reduces nothing: rho' = r^T z, ||r||^2 and the finalisation belong to k_modal_expand.
+template <int F, bool START, bool CPX, bool MODAL = false>
 __global__ void __launch_bounds__(256, 3)
 k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* __restrict__ binv, float* __restrict__ z32,
             double* __restrict__ p_start, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
@@ -1160,10 +917,11 @@ k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* _
             const bool ok = act && e < n_el;
             const float z = (e < kBjTile * NC) ? zp[e] : 0.0f;
             if (ok) {
-                if constexpr (START) p_start[base + e] = (double)z;   // first search direction of the slot
+                if constexpr (START && !MODAL) p_start[base + e] = (double)z;   // first search direction of the slot
                 else z32[base + e] = z;
             }
-            if constexpr (CPX) {
+            if constexpr (MODAL) {
+            } else if constexpr (CPX) {
                 // (rr + j ri)(zr + j zi), accumulated by the lane that holds the real part
                 const double ro = __shfl_xor_sync(0xffffffffu, rn[u], 1);
                 const double zo = (double)__shfl_xor_sync(0xffffffffu, z, 1);
@@ -1187,7 +945,8 @@ k_update_bj(double* __restrict__ r, const double* __restrict__ q, const float* _
         if constexpr (START) fin_start(sc, ff, tot); else fin_update(sc, ff, tot);
     };
     unsigned int* ticket = &sc->ticket[START ? 2 : 1];
-    if constexpr (CPX) {
+    if constexpr (MODAL) {
+    } else if constexpr (CPX) {
         // threads of slot f: columns 2f, 2f+1 of every group of NC threads; fixed order
         __shared__ double s_v[256][3];
 #pragma unroll
@@ -1278,12 +1037,13 @@ __global__ void __launch_bounds__(kBlock) k_jacobi(const double2* __restrict__ d
     dinv[i] = zero ? make_double2(1.0, 0.0) : cdiv(make_double2(1.0, 0.0), g);
 }
 
-// reset slots: r = 0, and x = 0 unless the previous solution of the slot is kept as the starting guess
+// reset slots: r = 0, and x = 0 unless the slot keeps its x as the starting guess (warm start, or a resumed slot: sc.keepx)
 template <typename T, int F>
-__global__ void __launch_bounds__(kBlock) k_slot_clear(T* __restrict__ x, T* __restrict__ r, bool keep_x, int64_t n_elems,
+__global__ void __launch_bounds__(kBlock) k_slot_clear(T* __restrict__ x, T* __restrict__ r, bool keep_all, int64_t n_elems,
                                                         const Scalars* __restrict__ sc) {
     const int f = threadIdx.x % F;
     if (!sc->reset[f]) return;
+    const bool keep_x = keep_all || sc->keepx[f] != 0;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * kBlock) {
         r[i] = v_zero<T>();
         if (!keep_x) x[i] = v_zero<T>();
@@ -1625,6 +1385,8 @@ struct Launch {
 
     // block-Jacobi tile kernels: 48 KB of shared memory per block at F = 16 (packed FP32 block + two 128 x F tiles)
     static constexpr bool kBjReal = F <= 16, kBjCpx = F <= 8;   // 16 real columns per row at most
+    static constexpr bool kModalReal = F == kModalCols, kModalCpx = 2 * F == kModalCols;   // the tensor-core kernels: exactly 16 real columns
+    static void modal_supported(SweepWork* w, bool* ok) { *ok = w->real ? kModalReal : kModalCpx; }
     static size_t bj_smem(bool cpx) { return (size_t)kBjPacked * 4 + (size_t)2 * kBjTile * std::min(16, cpx ? 2 * F : F) * 4; }
     static int bj_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * 3)); }
     static void bj_supported(SweepWork* w, bool* ok) { *ok = w->real ? kBjReal : kBjCpx; }
@@ -1638,11 +1400,19 @@ struct Launch {
             if constexpr (kBjReal) {
                 FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
                 FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
+                if constexpr (kModalReal) {
+                    FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
+                    FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(false)));
+                }
             }
         } else {
             if constexpr (kBjCpx) {
                 FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
                 FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
+                if constexpr (kModalCpx) {
+                    FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
+                    FDB_CUDA(cudaFuncSetAttribute(k_update_bj<F, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_smem(true)));
+                }
             }
         }
         d = true;
@@ -1653,6 +1423,19 @@ struct Launch {
         constexpr bool CPX = std::is_same<T, double2>::value;
         if constexpr (CPX ? kBjCpx : kBjReal) {
             double *r = (double*)w->r.p, *q = (double*)w->q.p, *p = (double*)w->p.p;
+            if (w->precond == 2) {
+                if constexpr (CPX ? kModalCpx : kModalReal) {
+                    if (start)
+                        k_update_bj<F, true, CPX, true><<<bj_grid(sys), 256, bj_smem(CPX), sys->stream>>>(r, nullptr, sys->blk_inv.p, w->z32.p, p, w->N,
+                                                                                                         sys->n_tiles, w->sc.p, (double*)w->partial.p);
+                    else
+                        k_update_bj<F, false, CPX, true><<<bj_grid(sys), 256, bj_smem(CPX), sys->stream>>>(r, q, sys->blk_inv.p, w->z32.p, nullptr, w->N,
+                                                                                                          sys->n_tiles, w->sc.p, (double*)w->partial.p);
+                    return true;
+                } else {
+                    throw Error("femder_b200: the modal correction runs in batches of 16 real or 8 complex slots");
+                }
+            }
             if (start)
                 k_update_bj<F, true, CPX><<<bj_grid(sys), 256, bj_smem(CPX), sys->stream>>>(r, nullptr, sys->blk_inv.p, w->z32.p, p, w->N, sys->n_tiles,
                                                                                            w->sc.p, (double*)w->partial.p);
@@ -1675,7 +1458,7 @@ struct Launch {
     static void vec_kernel_t(fdb_system* sys, SweepWork* w, bool overlay, int which) {
         const int64_t ne = w->N * F;
         T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *q = (T*)w->q.p;
-        if (w->precond == 1) {
+        if (w->precond >= 1) {
             if (which == 1) { if (bj_update<T>(sys, w, false)) return; }
             else if constexpr (std::is_same<T, double2>::value ? kBjCpx : kBjReal) {
                 k_pupdate_bj<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, w->z32.p, ne, w->sc.p);
@@ -1699,6 +1482,7 @@ struct Launch {
     static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
         spmv(sys, w, w->p.p, w->q.p, true, overlay);
         vec_kernel_t<T>(sys, w, overlay, 1);
+        if (w->precond == 2) modal_apply(sys, w, overlay, false);
         vec_kernel_t<T>(sys, w, overlay, 2);
     }
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
@@ -1706,7 +1490,9 @@ struct Launch {
     }
     // (re)load the slots flagged in sc.reset
     template <typename T>
-    static void reload_t(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
+    // keep_all: every slot being loaded starts from the x it holds (warm start); any_keep: some slots are resumed (sc.keepx)
+    static void reload_t(fdb_system* sys, SweepWork* w, bool overlay, bool keep_all, bool any_keep, const int32_t* nodes, const double2* q, int n_src,
+                         int* n_launched) {
         const int64_t ne = w->N * F;
         T *x = (T*)w->x.p, *r = (T*)w->r.p, *p = (T*)w->p.p, *qq = (T*)w->q.p;
         int nk = 0;
@@ -1715,7 +1501,7 @@ struct Launch {
                                                                        w->coef.p, overlay, w->N, w->sc.p, w->dinv.p);
             ++nk;
         }
-        k_slot_clear<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, keep_x, ne, w->sc.p);
+        k_slot_clear<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, r, keep_all, ne, w->sc.p);
         ++nk;
         if (n_src) {
             k_set_rhs<T, F><<<grid_for((int64_t)n_src * F, 128), 128, 0, sys->stream>>>(nodes, q, w->src_set_ptr.p, n_src, false, w->sc.p, r);
@@ -1728,13 +1514,14 @@ struct Launch {
                 ++nk;
             }
         }
-        if (keep_x) {
+        if (keep_all || any_keep) {   // r = b - G x (x = 0 in the slots that keep nothing)
             spmv(sys, w, x, qq, false, overlay);
             k_sub<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(r, qq, ne, w->sc.p);
             nk += 2;
         }
         bool started = false;
-        if (w->precond == 1) started = bj_update<T>(sys, w, true);
+        if (w->precond >= 1) started = bj_update<T>(sys, w, true);
+        if (started && w->precond == 2) { modal_apply(sys, w, overlay, true); nk += 3; }
         if (started) {
         } else if (overlay) {
             if constexpr (std::is_same<T, double2>::value)
@@ -1744,9 +1531,10 @@ struct Launch {
         }
         *n_launched = nk + 1;
     }
-    static void reload(fdb_system* sys, SweepWork* w, bool overlay, bool keep_x, const int32_t* nodes, const double2* q, int n_src, int* n_launched) {
-        if (w->real) reload_t<double>(sys, w, false, keep_x, nodes, q, n_src, n_launched);
-        else reload_t<double2>(sys, w, overlay, keep_x, nodes, q, n_src, n_launched);
+    static void reload(fdb_system* sys, SweepWork* w, bool overlay, bool keep_all, bool any_keep, const int32_t* nodes, const double2* q, int n_src,
+                       int* n_launched) {
+        if (w->real) reload_t<double>(sys, w, false, keep_all, any_keep, nodes, q, n_src, n_launched);
+        else reload_t<double2>(sys, w, overlay, keep_all, any_keep, nodes, q, n_src, n_launched);
     }
     // rt[f] = ||b_f - G_f x_f||^2 for every slot (q and tmp are free between iterations)
     template <typename T>
@@ -1814,11 +1602,15 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         w->N = sys->n_nodes;
         w->n_groups = sys->n_groups;
         w->grid = sys->num_sms * 8;
+#ifdef FDB_TUNING
+        // Tuning knobs that change the code path (FDB_BLOB_DBG even makes results wrong on purpose) exist only in builds made
+        // with -DFDB_TUNING (scripts/build_ab_lib.sh): a stray environment variable cannot change what the product computes.
         if (const char* e = getenv("FDB_SPMV_CFG")) w->spmv_cfg = std::max(0, std::min(12, atoi(e)));
         if (const char* e = getenv("FDB_SPMV_BPS")) w->spmv_bps = std::max(0, atoi(e));
         if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
         if (const char* e = getenv("FDB_BLOB_DBG")) w->blob_dbg = atoi(e);
         if (getenv("FDB_NO_ROWS_KERNEL")) w->rows_kernel = false;
+#endif
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
         w->coef.alloc((size_t)std::max(1, sys->n_groups) * F);
@@ -1862,7 +1654,7 @@ static void upload_scalars(fdb_system* sys, SweepWork* w, const Scalars& h, cons
 
 static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool overlay) {
     if (w->graph && w->graph_iters == iters && w->graph_F == F && w->graph_overlay == overlay && w->graph_real == w->real &&
-        w->graph_precond == (w->precond == 1)) return;
+        w->graph_precond == w->precond) return;
     if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
     cudaGraph_t g = nullptr;
     FDB_CUDA(cudaStreamBeginCapture(sys->stream, cudaStreamCaptureModeThreadLocal));
@@ -1877,7 +1669,7 @@ static void ensure_graph(fdb_system* sys, SweepWork* w, int F, int iters, bool o
     cudaError_t e = cudaGraphInstantiate(&w->graph, g, 0);
     cudaGraphDestroy(g);
     FDB_CUDA(e);
-    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real; w->graph_precond = (w->precond == 1);
+    w->graph_iters = iters; w->graph_F = F; w->graph_overlay = overlay; w->graph_real = w->real; w->graph_precond = w->precond;
 }
 
 static void k_jacobi_launch(fdb_system* sys, SweepWork* w, int F) {
@@ -1918,12 +1710,12 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     if (nf) FDB_CUDA(cudaMemcpy(omega.data(), prm->omega, omega.size() * sizeof(double), cudaMemcpyDefault));
     if (!mu.empty()) FDB_CUDA(cudaMemcpy(mu.data(), prm->mu, mu.size() * sizeof(double), cudaMemcpyDefault));
     // a sweep whose admittances are all exactly zero (rigid walls) has no boundary term: the overlay is skipped
-    bool overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0;
-    if (overlay) {
-        bool any = false;
-        for (double v : mu) any = any || (v != 0.0);
-        overlay = any;
-    }
+    bool any_mu = false;
+    for (double v : mu) any_mu = any_mu || (v != 0.0);
+    // never solve the rigid problem silently: non-zero admittances need the assembled surface matrices
+    FDB_REQUIRE(!(ng > 0 && any_mu) || sys->have_overlay,
+                "non-zero admittances but the surface matrices are not assembled (call fdb_assemble_surface / fdb_set_surface after the last mesh or pattern change)");
+    const bool overlay = sys->have_overlay && sys->n_ov > 0 && ng > 0 && any_mu;
     std::vector<int32_t> src_nodes(prm->n_src);
     std::vector<double2> src_q(prm->n_src);
     if (prm->n_src) {
@@ -2013,8 +1805,16 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     // (real q): p = 1j*u with G u = -w q.  Same COCG recurrences on half the bytes.
     bool real = !overlay && prm->arithmetic != 1 && !general_rhs;
     for (auto& v : u_q) real = real && (v.y == 0.0);
-    // no wider than the number of frequencies needs
-    while (F / 2 >= 1 && F / 2 >= n_sys) F /= 2;
+    // The modal coarse correction (precond 2) runs on 16 real columns per row: 16 real or 8 complex slots.
+    const bool want_modal = prm->precond == 2;
+    if (want_modal) {
+        FDB_REQUIRE(sys->have_modes, "precond = 2 needs the room modes (fdb_modal_compute / fdb_modal_set)");
+        FDB_REQUIRE(sys->n_tiles > 0 && sys->tile_rows == 128, "the modal correction needs the 128-row tiles of the internal order");
+        F = real ? kModalCols : kModalCols / 2;
+    } else {
+        // no wider than the number of frequencies needs
+        while (F / 2 >= 1 && F / 2 >= n_sys) F /= 2;
+    }
     SweepWork* w = get_work(sys, F);
     w->real = false;
     if (real) {
@@ -2026,11 +1826,26 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     res->real_arithmetic = real ? 1 : 0;
     // Preconditioner: block-Jacobi over the 128-row tiles of the internal order where it is implemented (real sweeps in
     // batches of up to 16, complex sweeps in batches of up to 8), point Jacobi otherwise.  prm->precond: 0 = Jacobi, 1 = block-Jacobi where possible.
-    static const bool no_bj = getenv("FDB_NO_BLOCK_JACOBI") != nullptr;   // A/B aid
-    bool use_bj = prm->precond == 1 && !no_bj && sys->n_tiles > 0 && sys->tile_rows == 128;
+#ifdef FDB_TUNING
+    static const bool no_bj = getenv("FDB_NO_BLOCK_JACOBI") != nullptr;   // A/B aid (tuning builds only)
+#else
+    constexpr bool no_bj = false;
+#endif
+    bool use_bj = prm->precond >= 1 && !no_bj && sys->n_tiles > 0 && sys->tile_rows == 128;
     if (use_bj) { FDB_DISPATCH_F(F, bj_supported(w, &use_bj)); }   // 16 real columns per row at most: F <= 16 real, F <= 8 complex
-    w->precond = use_bj ? 1 : 0;
+    bool use_modal = want_modal && use_bj;
+    if (want_modal) {
+        FDB_REQUIRE(real == w->real, "the modal correction needs the real-arithmetic kernels at 16 slots");
+        FDB_DISPATCH_F(F, modal_supported(w, &use_modal));
+        FDB_REQUIRE(use_modal && use_bj, "the modal correction is not available for this batch shape");
+    }
+    w->precond = use_modal ? 2 : (use_bj ? 1 : 0);
     if (use_bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
+    if (use_modal) {
+        modal_prepare(sys, w);
+        if (overlay) modal_build_adiag(sys);
+    }
+    const double modal_delta = prm->modal_delta_hz > 0.0 ? prm->modal_delta_hz : 300.0;
     w->n_rn = (int)rn_nodes.size();
     if (general_rhs) {
         w->rn_nodes.alloc(rn_nodes.size()); w->rn_ptr.alloc(rn_ptr.size()); w->rn_vec.alloc(rn_vec.size()); w->rn_val.alloc(rn_val.size());
@@ -2074,7 +1889,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     FDB_CUDA(cudaEventRecord(ev0, s));
     int64_t n_spmv = 0, n_kernels = 0;
-    int n_unconv = 0;
+    int n_unconv = 0, n_resumed = 0;
 
     Scalars h;
     memset(&h, 0, sizeof(h));
@@ -2085,6 +1900,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     std::vector<double> mu_f((size_t)std::max(1, ng) * 2);
     std::vector<int64_t> slot_freq(F, -1);
     std::vector<char> slot_used(F, 0);   // has the slot held a frequency before (its x is a usable starting guess)
+    std::vector<int> slot_resumes(kMaxF, 0);   // times the slot's system was restarted from its true residual
+    std::vector<double> slot_best(kMaxF, 1e300);   // modal path: best ||r||^2 / ||b||^2 the slot's recurrence has shown, and when
+    std::vector<int> slot_best_it(kMaxF, 0);
+    constexpr int kMaxResumes = 8, kStallWindow = 96;
     std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
     int64_t next = 0;
     int n_busy = 0;
@@ -2114,10 +1933,22 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             rcoef[(size_t)k * F + slot] = make_double2(rhs_coef[((size_t)k * nf + fi) * 2], rhs_coef[((size_t)k * nf + fi) * 2 + 1]);
         slot_freq[slot] = si;
         h.reset[slot] = 1;
+        h.keepx[slot] = 0;
         h.active[slot] = 0;
         h.iters[slot] = 0;
+        slot_resumes[slot] = 0;
+        slot_best[slot] = 1e300;
+        slot_best_it[slot] = 0;
         ++n_busy;
         return true;
+    };
+    // modes the coarse correction applies in the next launches: all below sqrt(f_max^2 + delta^2) of the busy slots
+    auto set_modes_use = [&]() {
+        if (!use_modal) { h.modes_use = 0; return; }
+        double w2max = 0.0;
+        for (int f = 0; f < F; ++f)
+            if (slot_freq[f] >= 0) w2max = std::max(w2max, h.w2[f]);
+        h.modes_use = modal_modes_for(sys, w2max, modal_delta);
     };
 
     // empty slots still need finite constants
@@ -2130,30 +1961,57 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         if (any_reset) {
             // slots that held a solution before can start from it (warm start from the slot's previous frequency)
             bool keep_x = prm->warm_start != 0 && !general_rhs;   // ||b|| of a general right-hand side comes from r0 = b
-            for (int f = 0; f < F; ++f)
+            bool any_keep = false;
+            for (int f = 0; f < F; ++f) {
                 if (h.reset[f] && !slot_used[f]) keep_x = false;
+                if (h.reset[f] && h.keepx[f]) any_keep = true;
+            }
+            set_modes_use();
             upload_scalars(sys, w, h, coef, &rcoef);
             int nk = 0;
-            FDB_DISPATCH_F(F, reload(sys, w, overlay, keep_x, d_src_nodes.p, d_src_q.p, n_src, &nk));
+            FDB_DISPATCH_F(F, reload(sys, w, overlay, keep_x, any_keep, d_src_nodes.p, d_src_q.p, n_src, &nk));
             n_kernels += nk;
-            if (keep_x) ++n_spmv;
+            if (keep_x || any_keep) ++n_spmv;
             for (int f = 0; f < F; ++f)
-                if (h.reset[f]) slot_used[f] = 1;
+                if (h.reset[f]) { slot_used[f] = 1; h.reset[f] = 0; h.keepx[f] = 0; }   // the device copy clears them as it loads the slots
             any_reset = false;
         } else {
+            set_modes_use();
             upload_scalars(sys, w, h, coef, &rcoef);
         }
         FDB_CUDA(cudaGraphLaunch(w->graph, s));
         n_spmv += check_every;
-        n_kernels += 3 * (int64_t)check_every;
+        n_kernels += (use_modal ? 6 : 3) * (int64_t)check_every;
         FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         FDB_CUDA(cudaStreamSynchronize(s));
         FDB_CUDA(cudaGetLastError());
 
+        // The modal correction makes the preconditioner indefinite (it inverts G on the modes below the drive frequency too): the
+        // recurrence then converges like CG on a definite system, but an (unlucky) near-breakdown is possible.  A slot that has
+        // not improved its residual for a long stretch, or has blown it up, is restarted from its true residual.
+        if (use_modal) {
+            for (int f = 0; f < F; ++f) {
+                if (slot_freq[f] < 0 || !h.active[f]) continue;
+                const double rrel = h.bb[f] > 0 ? h.rr[f] / h.bb[f] : 0.0;
+                if (rrel < 0.25 * slot_best[f]) { slot_best[f] = rrel; slot_best_it[f] = h.iters[f]; continue; }
+                const bool stalled = h.iters[f] - slot_best_it[f] >= kStallWindow || rrel > 1e8 * slot_best[f] || rrel != rrel;
+                if (stalled && slot_resumes[f] < kMaxResumes && h.iters[f] < prm->max_iter) {
+                    ++slot_resumes[f];
+                    ++n_resumed;
+                    h.reset[f] = 1;
+                    h.keepx[f] = 1;
+                    h.active[f] = 0;
+                    slot_best[f] = 1e300;
+                    slot_best_it[f] = h.iters[f];
+                    any_reset = true;
+                }
+            }
+        }
         bool finished_any = false;
         std::vector<char> done(kMaxF, 0);
         for (int f = 0; f < F; ++f) {
             if (slot_freq[f] < 0) continue;
+            if (h.reset[f]) continue;   // being restarted (above)
             if (!h.active[f] || h.iters[f] >= prm->max_iter) { done[f] = 1; finished_any = true; }
         }
         if (!finished_any) continue;
@@ -2182,9 +2040,19 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             if (!done[f]) continue;
             const int64_t fi = slot_freq[f];
             const double rel = (hf.bb[f] > 0) ? sqrt(hf.rt[f] / hf.bb[f]) : 0.0;
+            // Accepted on the TRUE residual only.  The recurrence stopped the slot but ||b - G x|| is still above tol: restart
+            // it from x with r = b - G x (the iteration count keeps running) instead of returning it.
+            if (!h.active[f] && !(rel <= prm->tol) && rel == rel && h.iters[f] < prm->max_iter && slot_resumes[f] < kMaxResumes) {
+                ++slot_resumes[f];
+                ++n_resumed;
+                h.reset[f] = 1;
+                h.keepx[f] = 1;
+                any_reset = true;
+                continue;
+            }
             if (res->iters) res->iters[fi] = h.iters[f];
             if (res->relres) res->relres[fi] = rel;
-            if (h.active[f] || !(rel <= 10 * prm->tol)) ++n_unconv;
+            if (!(rel <= prm->tol)) ++n_unconv;
             if (n_rcv && res->pR)
                 FDB_CUDA(cudaMemcpy(res->pR + ((size_t)fi * n_rcv) * 2, rcv_host.data() + (size_t)f * n_rcv,
                                     (size_t)n_rcv * sizeof(double2), cudaMemcpyDefault));
@@ -2194,8 +2062,13 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
 
         // Tail of the sweep: the queue is empty and slots fall idle, but the fused SpMV costs the same whatever the
         // number of live slots.  Move the live slots into a narrower batch as soon as they fit one.
-        static const bool no_narrow = getenv("FDB_NO_NARROW") != nullptr;   // debugging aid
-        if (next >= n_sys && n_busy > 0 && !any_reset && !no_narrow) {
+#ifdef FDB_TUNING
+        static const bool no_narrow = getenv("FDB_NO_NARROW") != nullptr;   // debugging aid (tuning builds only)
+#else
+        constexpr bool no_narrow = false;
+#endif
+        // (the modal correction's tensor-core kernels are built for 16 real columns: its batches stay as they are)
+        if (next >= n_sys && n_busy > 0 && !any_reset && !no_narrow && !use_modal) {
             int F2 = F;
             while (F2 / 2 >= 1 && F2 / 2 >= n_busy) F2 /= 2;
             if (F2 < F) {
@@ -2276,6 +2149,60 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     res->n_spmv = n_spmv;
     res->n_kernels = n_kernels;
     res->n_unconverged = n_unconv;
+    res->n_resumed = n_resumed;
+    res->precond_used = w->precond;
+}
+
+// ---- the fused SpMV for the modal set-up (modal.cu): 16 real columns, one w2 for all of them ----
+__global__ void k_set_w2(Scalars* sc, double w2) {
+    if (threadIdx.x < kMaxF) sc->w2[threadIdx.x] = w2;
+}
+SweepWork* modal_spmv_begin(fdb_system* sys) {
+    SweepWork* w = get_work(sys, kModalCols);
+    bool ok = false;
+    w->real = false;
+    FDB_DISPATCH_F(kModalCols, query_real(sys, w, &ok));
+    FDB_REQUIRE(ok, "the real-arithmetic SpMV is not available on this mesh");
+    w->real = true;
+    invalidate_graph(sys);
+    return w;
+}
+void modal_spmv_w2(fdb_system* sys, SweepWork* w, double w2) { k_set_w2<<<1, kMaxF, 0, sys->stream>>>(w->sc.p, w2); }
+void modal_spmv(fdb_system* sys, SweepWork* w, const double* x, double* y) { FDB_DISPATCH_F(kModalCols, spmv(sys, w, x, y, false, false)); }
+
+// z = V diag(1 / (lam - w_f^2)) V^T r on caller data, through the solver's own kernels (parity tests of the tensor-core path)
+__global__ void k_z32_to_f64(const float* __restrict__ z, int64_t n, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)z[i];
+}
+void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const double* r, double* z) {
+    FDB_REQUIRE(sys->have_modes, "no modes");
+    SweepWork* w = modal_spmv_begin(sys);
+    w->precond = 2;
+    { bool okb = false; FDB_DISPATCH_F(kModalCols, bj_supported(w, &okb)); (void)okb; }
+    w->z32.alloc((size_t)w->N * kModalCols);
+    modal_prepare(sys, w);
+    std::vector<double> om(kModalCols);
+    FDB_CUDA(cudaMemcpy(om.data(), omega, om.size() * sizeof(double), cudaMemcpyDefault));
+    Scalars h;
+    memset(&h, 0, sizeof(h));
+    std::vector<double2> coef((size_t)std::max(1, w->n_groups) * kModalCols, make_double2(0.0, 0.0));
+    for (int f = 0; f < kModalCols; ++f) fill_slot(h, coef, kModalCols, w->n_groups, f, om[f], nullptr, 0.0);
+    h.tol2 = 1.0;
+    h.modes_use = std::min(((std::max(n_use, 1) + 15) / 16) * 16, sys->mode_chunks * 128);
+    upload_scalars(sys, w, h, coef);
+    const size_t n = (size_t)w->N * kModalCols;
+    const int pg = (int)std::min<int64_t>(grid_for((int64_t)n, kBlock), w->grid);
+    double* tmp = (double*)w->tmp.p;
+    FDB_CUDA(cudaMemcpyAsync(tmp, r, n * sizeof(double), cudaMemcpyDefault, sys->stream));
+    k_permute_rows<double><<<pg, kBlock, 0, sys->stream>>>(tmp, (double*)w->r.p, sys->perm.p, kModalCols, w->N, true);
+    FDB_CUDA(cudaMemsetAsync(w->z32.p, 0, n * sizeof(float), sys->stream));
+    modal_apply(sys, w, false, false);
+    k_z32_to_f64<<<pg, kBlock, 0, sys->stream>>>(w->z32.p, (int64_t)n, (double*)w->q.p);
+    k_permute_rows<double><<<pg, kBlock, 0, sys->stream>>>((const double*)w->q.p, tmp, sys->perm.p, kModalCols, w->N, false);
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaMemcpyAsync(z, tmp, n * sizeof(double), cudaMemcpyDefault, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
+    w->precond = 0;
 }
 
 // one-batch constants for the stand-alone SpMV entry points

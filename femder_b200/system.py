@@ -15,6 +15,8 @@ from . import _lib
 from ._lib import SweepParams, SweepResult, check, ptr
 
 VALID_BATCH = (1, 2, 4, 8, 16, 32, 64)
+PRECOND_CODES = {"jacobi": 0, "block": 1, "modal": 2}
+PRECOND_NAMES = {v: k for k, v in PRECOND_CODES.items()}
 SMALL_MESH_NODES = 200_000  # below this the kernels are launch-bound: use wider batches
 
 
@@ -36,20 +38,22 @@ def _c128(a):
 
 
 class SweepStats:
-    def __init__(self, iters, relres, seconds, n_spmv, n_kernels, n_unconverged):
+    def __init__(self, iters, relres, seconds, n_spmv, n_kernels, n_unconverged, n_resumed=0, precond_used=0):
         self.iters = iters
         self.relres = relres
         self.seconds = seconds
         self.n_spmv = n_spmv
         self.n_kernels = n_kernels
         self.n_unconverged = n_unconverged
+        self.n_resumed = n_resumed          # restarts from the true residual (a slot the recurrence stopped above tol)
+        self.precond_used = PRECOND_NAMES.get(precond_used, str(precond_used))
 
     def __repr__(self):
         it = self.iters
         return (f"SweepStats(n_freq={len(it)}, iters[min/mean/max]={it.min() if len(it) else 0}/"
                 f"{it.mean() if len(it) else 0:.0f}/{it.max() if len(it) else 0}, max_relres="
                 f"{self.relres.max() if len(it) else 0:.2e}, seconds={self.seconds:.3f}, "
-                f"n_unconverged={self.n_unconverged})")
+                f"n_unconverged={self.n_unconverged}, n_resumed={self.n_resumed}, precond={self.precond_used})")
 
 
 class System:
@@ -240,6 +244,50 @@ class System:
         check(self._lib.fdb_set_surface(self._h, ng, len(ix), ptr(ip), ptr(ix), ptr(vals)))
         self.n_groups = ng
 
+    # ---- room modes ---------------------------------------------------------------------------
+    def modal_compute(self, f_cut, n_hint=0, tol=0.0, max_outer=12, f_acc=0.0):
+        """All modes ``H v = lambda Q v`` below ``f_cut`` Hz, on the GPU (``FEM3D.eigenfrequency``'s job,
+        ``FEM_3D.py:1699-1768``).  ``n_hint``: expected number of modes (sizes the block); ``tol``: relative residual of the
+        modes below ``f_acc`` (default: all; the rest may be 10 x coarser).  Returns the number kept."""
+        n = C.c_int(0)
+        check(self._lib.fdb_modal_compute(self._h, float(f_cut), float(f_acc), int(n_hint), float(tol), int(max_outer), C.byref(n)))
+        return n.value
+
+    def modal_info(self):
+        """dict(outer, block, mass_order, worst_residual, residuals) of the stored modes."""
+        o, b, t, wr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0.0)
+        res = np.empty(self.modal_count(), dtype=np.float64)
+        check(self._lib.fdb_modal_info(self._h, C.byref(o), C.byref(b), C.byref(t), C.byref(wr), ptr(res)))
+        return dict(outer=o.value, block=b.value, mass_order=t.value, worst_residual=wr.value, residuals=res)
+
+    def modal_set(self, lam, V):
+        """Modes computed elsewhere: ``lam`` (m,) ascending, ``V`` (m, N) Q-orthonormal rows."""
+        lam, V = _f64(lam), _f64(V)
+        if V.shape != (len(lam), self.n_nodes):
+            raise ValueError("V must be (n_modes, n_nodes)")
+        check(self._lib.fdb_modal_set(self._h, len(lam), ptr(lam), ptr(V)))
+
+    def modal_count(self):
+        n = C.c_int(0)
+        check(self._lib.fdb_modal_count(self._h, C.byref(n)))
+        return n.value
+
+    def modal_get(self, vectors=True):
+        m = self.modal_count()
+        lam = np.empty(m, dtype=np.float64)
+        V = np.empty((m, self.n_nodes), dtype=np.float64) if vectors else None
+        check(self._lib.fdb_modal_get(self._h, ptr(lam), ptr(V)))
+        return lam, V
+
+    def modal_apply(self, omega, n_use, r):
+        """``z = V diag(1 / (lam - omega_f^2)) V^T r`` through the solver's tensor-core kernels; r is (N, 16) real."""
+        omega, r = _f64(omega), _f64(r)
+        if r.shape != (self.n_nodes, 16) or len(omega) != 16:
+            raise ValueError("r must be (N, 16) and omega (16,)")
+        z = np.empty_like(r)
+        check(self._lib.fdb_modal_apply(self._h, ptr(omega), int(n_use), ptr(r), ptr(z)))
+        return z
+
     # ---- receivers ----------------------------------------------------------------------------
     def locate_points(self, coords, tol=1e-3):
         """(nodes (P, 4) int32, weights (P, 4)) with p(coord) = sum_j w_j p[node_j] for every point, on the GPU."""
@@ -251,8 +299,8 @@ class System:
 
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
-              max_iter=20000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,
-              rhs_coef=None, src_sets=None, precond="block"):
+              max_iter=200000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,
+              rhs_coef=None, src_sets=None, precond="block", modal_delta=0.0):
         """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
 
         mu: (n_groups, n_freq) complex.  ``rhs_vecs`` (list of real length-N vectors, dense or scipy sparse) with
@@ -260,7 +308,9 @@ class System:
         (velocity boundary conditions).  ``src_sets`` = list of ``(nodes, q)`` pairs solves several right-hand sides
         per frequency in the same batches (source candidate loops); outputs then carry a leading set axis.
         ``precond``: "block" = block-Jacobi over the 128-row tiles of the sweep's internal order where implemented
-        (batches of up to 16 real or 8 complex slots), point Jacobi elsewhere; "jacobi" = point Jacobi everywhere.
+        (batches of up to 16 real or 8 complex slots), point Jacobi elsewhere; "jacobi" = point Jacobi everywhere;
+        "modal" = block-Jacobi plus the coarse correction over the room modes (``modal_compute`` / ``modal_set`` first; the
+        batch is then 16 real or 8 complex slots; a batch applies the modes below sqrt(f_max^2 + modal_delta^2), default 300 Hz).
         Returns (pN or None, pR or None, SweepStats)."""
         omega = _f64(np.atleast_1d(omega))
         nf = len(omega)
@@ -281,7 +331,9 @@ class System:
             # frequencies fill the 128-byte gather line that 8 complex ones do
             real = (mu is None or not mu.any()) and not src_q.imag.any() and not force_complex and n_vec == 0
             batch = 16 if real else 8
-            if self.n_nodes <= SMALL_MESH_NODES:
+            if precond == "modal":
+                pass    # the tensor-core kernels of the modal correction fix the batch: 16 real or 8 complex slots
+            elif self.n_nodes <= SMALL_MESH_NODES:
                 # small meshes: the kernels are latency-bound, wide batches amortise the fixed cost per launch.  (The
                 # block-Jacobi kernels cover batches up to 16 only; on the coarse config-1 mesh, k h up to 1, 64 slots with point
                 # Jacobi sweep 20-500 Hz in 1.39 s against 2.18 s for 16 slots with block-Jacobi.)
@@ -304,9 +356,10 @@ class System:
         prm.batch = int(batch)
         prm.check_every = int(check_every)
         prm.warm_start = int(bool(warm_start))
-        if precond not in ("block", "jacobi"):
-            raise ValueError("precond must be 'block' or 'jacobi'")
-        prm.precond = 1 if precond == "block" else 0
+        if precond not in PRECOND_CODES:
+            raise ValueError("precond must be 'modal', 'block' or 'jacobi'")
+        prm.precond = PRECOND_CODES[precond]
+        prm.modal_delta_hz = float(modal_delta)
         prm.arithmetic = 1 if force_complex else 0
         prm.n_rhs_vec = n_vec
         if n_vec:
@@ -353,7 +406,7 @@ class System:
             if pR is not None:
                 pR = pR.reshape(n_sets, nf, n_rcv)
             iters, relres = iters.reshape(n_sets, nf), relres.reshape(n_sets, nf)
-        st = SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged)
+        st = SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged, res.n_resumed, res.precond_used)
         st.real_arithmetic = bool(res.real_arithmetic)
         return pN, pR, st
 

@@ -27,7 +27,7 @@ typedef struct fdb_system fdb_system;
 
 /* ---- library / device ------------------------------------------------------------------------- */
 const char* fdb_last_error(void);
-int fdb_abi_version(void);
+int fdb_abi_version(void);   /* 2 */
 int fdb_device_count(int* count);
 
 /* One system = one mesh on one GPU.  `stream` is a cudaStream_t (0 = library-owned non-blocking stream);
@@ -101,13 +101,17 @@ typedef struct fdb_sweep_params {
      * FEM_3D.py:1633-1648).  0 = one set.  Outputs are then [n_src_sets][n_freq][...]. */
     int64_t n_src_sets;
     const int32_t* src_set_ptr; /* [n_src_sets+1] set k = sources src_set_ptr[k] .. src_set_ptr[k+1] */
-    double tol;               /* relative residual ||b - G x|| / ||b|| to reach */
+    double tol;               /* relative residual to reach: every returned solution satisfies ||b - G x|| / ||b|| <= tol on the TRUE
+                               * residual (a slot the recurrence stopped early is restarted from its true residual), or is
+                               * counted in n_unconverged */
     int32_t max_iter;
     int32_t batch;            /* solver slots = frequencies per fused SpMV: 1, 2, 4, 8, 16, 32 or 64 */
     int32_t check_every;      /* iterations between host convergence checks (one CUDA graph launch) */
     int32_t warm_start;       /* 1: start each batch from the previous batch's last solution */
-    int32_t precond;          /* 0: point Jacobi; 1: block-Jacobi (FP32 inverses of the 128-row diagonal blocks of H) where it is
-                               * implemented - batches of up to 16 real or 8 complex slots - and point Jacobi elsewhere */
+    int32_t precond;          /* 0: point Jacobi; 1: block-Jacobi (FP32 inverses of the 128-row diagonal blocks of H + s Q, s = (2 pi 50 Hz)^2)
+                               * where it is implemented - batches of up to 16 real or 8 complex slots - and point Jacobi elsewhere;
+                               * 2: block-Jacobi plus the modal coarse correction V diag(d) V^T over the low room modes
+                               * (fdb_modal_compute / fdb_modal_set must have been called; the batch is then 16 real or 8 complex slots) */
     int32_t arithmetic;       /* 0: automatic (real arithmetic for rigid-wall sweeps with real sources), 1: always complex */
     /* extra right-hand-side terms (velocity boundary conditions, FEM_3D.py:1320-1347): b_n += sum_k rhs_coef[k][n] * vec_k */
     int64_t n_rhs_vec;
@@ -118,6 +122,7 @@ typedef struct fdb_sweep_params {
     int64_t n_rcv;            /* receivers: pR[n][i] = sum_j rcv_w[i][j] * p[n][rcv_nodes[i][j]] */
     const int32_t* rcv_nodes; /* [n_rcv][4] (unused slots: weight 0, any valid node) */
     const double* rcv_w;      /* [n_rcv][4] */
+    double modal_delta_hz;    /* precond 2: a batch applies the modes below sqrt(f_max^2 + modal_delta_hz^2); 0 = default (300 Hz) */
 } fdb_sweep_params;
 /* Multi-GPU: frequencies are independent, so each rank creates its own system on its own
  * GPU and passes only the frequencies it owns; there is no collective on this path. */
@@ -130,14 +135,39 @@ typedef struct fdb_sweep_result {
     double seconds;   /* device time of the sweep (CUDA events on the system's stream) */
     int64_t n_spmv;   /* fused SpMV launches */
     int64_t n_kernels;/* all kernel launches of the sweep */
-    int32_t n_unconverged;
+    int32_t n_unconverged;    /* systems returned with ||b - G x|| / ||b|| > tol (max_iter reached, breakdown, NaN) */
     int32_t real_arithmetic;  /* 1 if the sweep ran in real arithmetic (G real, b imaginary: p = 1j*u) */
+    int32_t n_resumed;        /* restarts from the true residual (see tol) */
+    int32_t precond_used;     /* the preconditioner the sweep actually ran: 0, 1 or 2 as in fdb_sweep_params.precond */
 } fdb_sweep_result;
 
 int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);
 /* sizeof(fdb_sweep_params) / sizeof(fdb_sweep_result) as compiled, so a binding can verify its struct layout. */
 int fdb_sizeof_sweep_params(void);
 int fdb_sizeof_sweep_result(void);
+
+/* ---- room modes (modal analysis; coarse correction of the sweep) --------------------------------------------------- *
+ * The eigenpairs H v = lambda Q v (lambda = (2 pi f)^2) that the reference computes in FEM3D.eigenfrequency
+ * (femder/FEM_3D.py:1699-1768: spsolve(Q, H) + scipy eigs, F_n = sqrt(lambda) / 2 pi, Vc = eigenvectors) and uses for modal
+ * superposition (1842-1934).  fdb_modal_compute finds all modes below f_cut_hz on the GPU (Chebyshev-filtered subspace
+ * iteration with a polynomial approximation of the inverse mass matrix, Rayleigh-Ritz with the consistent H, Q; csrc/modal.cu);
+ * fdb_modal_set takes modes computed elsewhere.  Either makes precond = 2 available to fdb_sweep.  V is [n_modes][n_nodes],
+ * Q-orthonormal, eigenvalues ascending.  At most 1024 modes are kept.
+ *   f_acc_hz   the modes below it must meet `tol` (0 = all of them); those between f_acc_hz and f_cut_hz may be 10 x coarser
+ *   tol        relative residual ||H v - lambda Q v|| / (lambda ||Q v||) to aim for (0 = default 2e-2: what the sweep's coarse
+ *              correction needs; eigenvalues are then good to ~tol^2).  The polynomial mass approximation bounds what can be
+ *              reached on coarse meshes; fdb_modal_info reports what was.
+ *   n_modes_hint  expected number of modes below f_cut_hz (sizes the block; 0 = find out by widening) */
+int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found);
+/* Diagnostics of the stored modes: outer iterations / block width / order of the mass approximation of the last fdb_modal_compute,
+ * its worst relative residual, and per mode ||H v - lambda Q v|| / ||Q v|| (what fdb_sweep bounds 1 / (lambda - w^2) with).  Any pointer may be NULL. */
+int fdb_modal_info(fdb_system* sys, int* outer_iterations, int* block_columns, int* mass_order, double* worst_residual, double* residuals /* [n_modes] */);
+int fdb_modal_set(fdb_system* sys, int n_modes, const double* lam /* [n_modes] */, const double* V /* [n_modes][n_nodes] */);
+int fdb_modal_count(fdb_system* sys, int* n_modes);
+int fdb_modal_get(fdb_system* sys, double* lam /* [n_modes] or NULL */, double* V /* [n_modes][n_nodes] or NULL */);
+/* The modal correction alone on caller data, for parity tests: z = V diag(1 / (lam - omega[f]^2)) V^T r in the kernels'
+ * arithmetic (bf16 V, (hi, lo) bf16 operands, FP32 accumulation); r, z are [n_nodes][16] real. */
+int fdb_modal_apply(fdb_system* sys, const double* omega /* [16] */, int n_modes_use, const double* r, double* z);
 
 /* y = G_f x for a batch of frequencies on caller data: x, y are [n_nodes][batch] complex. (K5 alone; parity) */
 int fdb_spmv(fdb_system* sys, int batch, const double* omega, const double* mu /* [n_groups][batch] complex */,
