@@ -59,6 +59,10 @@ class BC:
         for i in idx:
             self.mu[i] = np.ones_like(self.AC.freq) * normalized_admittance / (self.AP.c0 * self.AP.rho0)
 
+    def velocity(self, domain_index, velocity):
+        """Normal velocity on a surface group (``BoundaryConditions.py:98-116``): fills ``v`` only, never ``mu``."""
+        self.v[domain_index] = np.ones_like(self.AC.freq) * velocity
+
     def impedance(self, domain_index, impedance):
         idx = domain_index if isinstance(domain_index, (list, tuple)) else [domain_index]
         for i in idx:

@@ -850,7 +850,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     SweepWork* w = modal_spmv_begin(sys);
     const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr;   // progress lines on stderr; changes nothing that is computed
     std::vector<double> theta, res;
-    int wanted = 0, outer = 0, order_t = 0;
+    int wanted = 0, wanted_prev = -1, outer = 0, order_t = 0;
     const int max_order = tol < 1e-2 ? 4 : 1;
     double worst = 0.0, worst_prev = 1e300;
     DevBuf<double> X, Y, U, V1, T, big_x, big_hx, big_qx, big_new, Hs, Qs, W;
@@ -954,14 +954,19 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
                 const double rel = res[i] / std::max(std::fabs(theta[i]), th_ref);
                 if (theta[i] <= lam_acc) worst = std::max(worst, rel); else worst_hi = std::max(worst_hi, rel);
             }
-            a_low = std::max(lam_cut * 1.05, theta[nb - 1]);   // next filter: damp everything above the block's own upper edge
+            // next filter: damp everything above the guard band.  (The block's own upper Ritz value is the textbook choice, but it
+            // starts far above the cut and comes down slowly; the columns between the cut and it need no protection.)
+            a_low = lam_cut * 1.1;
             if (verbose)
                 fprintf(stderr, "[fdb modal] outer %d: block %d, wanted %d, mass order %d, degree %d, worst rel residual %.3e (below f_acc) %.3e (above), top Ritz f %.1f Hz\n",
                         outer, nb, wanted, order_t, deg, worst, worst_hi, std::sqrt(std::max(theta[nb - 1], 0.0)) / two_pi);
-            if (worst <= tol && worst_hi <= std::max(10.0 * tol, 0.1)) { converged = true; break; }
-            // the mass approximation of the filter limits what the subspace can reach: raise its order when progress stalls,
-            // stop when the highest order stalls too (the residuals are reported, the sweep does not depend on them being small)
-            if (outer >= 2 && worst > 0.5 * worst_prev) {
+            const bool stable = wanted == wanted_prev;   // the set of modes below the cut has stopped changing
+            wanted_prev = wanted;
+            if (stable && worst <= tol && worst_hi <= std::max(10.0 * tol, 0.1)) { converged = true; break; }
+            // Once the subspace is in its asymptotic regime the mass approximation of the filter limits what it can reach: raise its
+            // order when progress stalls, stop when the highest order stalls too (the residuals are reported; the sweep does not need
+            // them small, see k_modal_coef).
+            if (stable && worst < 0.2 && worst > 0.5 * worst_prev) {
                 if (order_t < max_order) ++order_t; else { converged = true; break; }
             }
             worst_prev = worst;

@@ -1903,6 +1903,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     std::vector<int> slot_resumes(kMaxF, 0);   // times the slot's system was restarted from its true residual
     std::vector<double> slot_best(kMaxF, 1e300);   // modal path: best ||r||^2 / ||b||^2 the slot's recurrence has shown, and when
     std::vector<int> slot_best_it(kMaxF, 0);
+    std::vector<char> slot_gave_up(kMaxF, 0);
     constexpr int kMaxResumes = 8, kStallWindow = 96;
     std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
     int64_t next = 0;
@@ -1939,6 +1940,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         slot_resumes[slot] = 0;
         slot_best[slot] = 1e300;
         slot_best_it[slot] = 0;
+        slot_gave_up[slot] = 0;
         ++n_busy;
         return true;
     };
@@ -1995,7 +1997,11 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 const double rrel = h.bb[f] > 0 ? h.rr[f] / h.bb[f] : 0.0;
                 if (rrel < 0.25 * slot_best[f]) { slot_best[f] = rrel; slot_best_it[f] = h.iters[f]; continue; }
                 const bool stalled = h.iters[f] - slot_best_it[f] >= kStallWindow || rrel > 1e8 * slot_best[f] || rrel != rrel;
-                if (stalled && slot_resumes[f] < kMaxResumes && h.iters[f] < prm->max_iter) {
+                if (stalled && slot_resumes[f] >= kMaxResumes) {
+                    // restarts exhausted: hand the slot back as it is (counted as unconverged below) instead of running to max_iter
+                    h.active[f] = 0;
+                    slot_gave_up[f] = 1;
+                } else if (stalled && h.iters[f] < prm->max_iter) {
                     ++slot_resumes[f];
                     ++n_resumed;
                     h.reset[f] = 1;
@@ -2042,7 +2048,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
             const double rel = (hf.bb[f] > 0) ? sqrt(hf.rt[f] / hf.bb[f]) : 0.0;
             // Accepted on the TRUE residual only.  The recurrence stopped the slot but ||b - G x|| is still above tol: restart
             // it from x with r = b - G x (the iteration count keeps running) instead of returning it.
-            if (!h.active[f] && !(rel <= prm->tol) && rel == rel && h.iters[f] < prm->max_iter && slot_resumes[f] < kMaxResumes) {
+            if (!h.active[f] && !(rel <= prm->tol) && rel == rel && h.iters[f] < prm->max_iter && slot_resumes[f] < kMaxResumes && !slot_gave_up[f]) {
                 ++slot_resumes[f];
                 ++n_resumed;
                 h.reset[f] = 1;

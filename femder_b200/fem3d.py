@@ -7,8 +7,10 @@ through ``libfemder_b200.so``.  There is no CPU fallback.
 Differences from the reference, all deliberate:
 * Tet4 ``H, Q`` are float64 csc; the reference rounds them to complex64 (``fem_numerical.py:307-312``).
   ``compat_complex64=True`` reproduces that rounding (values rounded to float32 before the solve).
-* every frequency is solved by preconditioned COCG (block-Jacobi, point Jacobi in the wide batches of small meshes) to
-  ``tol`` instead of a PARDISO factorisation.
+* every frequency is solved by preconditioned COCG to ``tol`` (true residual) instead of a PARDISO factorisation.  The
+  preconditioner is block-Jacobi plus a coarse correction over the low room modes (``precond="modal"``, the default
+  whenever it pays: the modes are what ``eigenfrequency`` computes, found once per assembly on the GPU), plain
+  block-Jacobi (``"block"``) or point Jacobi (``"jacobi"``).
 * a surface group without a boundary condition raises ``KeyError`` as in the reference (``FEM_3D.py:1310``);
   ``mu`` keys are paired with their own group instead of by position.
 * the velocity-BC branch (``FEM_3D.py:1320-1347``) is supported: ``b = -1j*w*sum_i v_i V_i 1`` (the reference's
@@ -78,7 +80,7 @@ def receiver_stencil(nos, elem_vol, coord, interpolation_tolerance=1e-3):
 
 class FEM3D:
     def __init__(self, Grid, S, R, AP, AC, BC=None, device=None, stream=None, tol=1e-8, max_iter=200000, batch="auto",
-                 check_every=32, warm_start=False, compat_complex64=False, shard=True, precond="block"):
+                 check_every=16, warm_start=False, compat_complex64=False, shard=True, precond="auto", modal_delta=300.0):
         self.BC = BC
         if BC is not None:
             self.mu = BC.mu
@@ -127,7 +129,9 @@ class FEM3D:
         self.max_iter = max_iter
         self.batch = batch
         self.check_every = check_every
-        self.precond = precond
+        self.precond = precond          # "auto" | "modal" | "block" | "jacobi"
+        self.modal_delta = modal_delta  # Hz: a frequency f is solved with the modes below sqrt(f^2 + modal_delta^2)
+        self._modes_key = None
         self.warm_start = warm_start
         self.compat_complex64 = compat_complex64
         self.shard = shard  # under torch.distributed: split the frequencies over the ranks and gather the rows at the end
@@ -224,15 +228,19 @@ class FEM3D:
         q = np.zeros([N, 1], dtype=np.complex128)
 
         group_ids = np.sort([*self.mu]) if self.BC is not None else np.array([], dtype=np.int64)
-        if self.BC is not None:
+        if self.BC is not None and len(self.v) == 0:
             for bl in self.number_ID_faces:
                 if bl not in self.mu:
-                    raise KeyError(bl)  # FEM_3D.py:1310 indexes self.mu[bl] for every surface group
+                    raise KeyError(bl)  # FEM_3D.py:1310 indexes self.mu[bl] for every surface group (admittance branch only:
+                                        # the velocity branch, 1330, walks np.sort([*self.mu]) and never touches the other groups)
         sys.set_surface_mesh(self.elem_surf, self.domain_index_surf, group_ids)
         self.areas = sys.heron_areas().astype(np.complex128)  # compute_areas returns complex128 (FEM_3D.py:743)
 
         if not self._assembled or new_mesh:
+            if not new_mesh:
+                sys.set_volume_mesh(self.nos, self.elem_vol)   # "H = None" re-assembles from the CURRENT nodes (in-place edits included)
             sys.assemble_volume(self.rho0, self.c0)
+            self._modes_key = None
             if self.compat_complex64:
                 H, Q = sys.get_HQ_values()
                 sys.set_HQ_values(H.astype(np.float32).astype(np.float64), Q.astype(np.float32).astype(np.float64))
@@ -280,12 +288,13 @@ class FEM3D:
         if self.R is not None and not keep_pN:
             rcv_nodes, rcv_w = sys.locate_points(np.atleast_2d(self.R.coord), 1e-3)   # batched on the GPU
 
+        precond = self._prepare_preconditioner(sys, nf)
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
         owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
-                                  tol=self.tol, max_iter=self.max_iter, batch=self.batch,
-                                  check_every=self.check_every, warm_start=self.warm_start, precond=self.precond, rhs_vecs=rhs_vecs,
-                                  rhs_coef=None if rhs_coef is None else rhs_coef[:, owned])
+                                  tol=self.tol, max_iter=self.max_iter, batch=self.batch if precond != "modal" else "auto",
+                                  check_every=self.check_every, warm_start=self.warm_start, precond=precond, rhs_vecs=rhs_vecs,
+                                  rhs_coef=None if rhs_coef is None else rhs_coef[:, owned], modal_delta=self.modal_delta)
         self.stats = stats
         if world > 1:
             pN = sharding.gather_rows(pN, owned, nf) if keep_pN else None
@@ -298,12 +307,84 @@ class FEM3D:
         self.pN = pN
         if pR is not None:
             self.pR = pR
+        # The reference's direct solver cannot "not converge"; an iterative one can (max_iter, breakdown): never hand back such
+        # a sweep silently.  relres is the TRUE residual ||b - G p|| / ||b|| of every returned system.
+        bad = np.flatnonzero(~(np.asarray(self.relres) <= self.tol))
+        self.n_unconverged = int(len(bad))
+        if len(bad):
+            import warnings
+            fr = np.asarray(self.freq)[bad]
+            warnings.warn(f"femder_b200: {len(bad)} of {nf} frequencies did not reach tol={self.tol:g} "
+                          f"(worst relative residual {np.nanmax(np.asarray(self.relres)[bad]):.2e} at "
+                          f"{fr[np.nanargmax(np.asarray(self.relres)[bad])]:g} Hz; first: {fr[:8]})", RuntimeWarning, stacklevel=2)
         self.t = time.time() - then
         if timeit:
             if self.t <= 60:
                 print(f"Time taken: {self.t} s")
             else:
                 print(f"Time taken: {self.t / 60} min")
+
+    # ---- room modes (FEM_3D.py:1699-1768) and the preconditioner that uses them ----------------
+    def _mode_count_estimate(self, f):
+        """Weyl's estimate of the number of room modes below ``f`` from the mesh's volume and boundary area (sizes the block
+        of the subspace iteration; the solver widens the block by itself when this is short)."""
+        nos = np.asarray(self.nos, dtype=np.float64)
+        ev = np.asarray(self.elem_vol)[:, :4].astype(np.int64)
+        a = nos[ev[:, 1]] - nos[ev[:, 0]]
+        b = nos[ev[:, 2]] - nos[ev[:, 0]]
+        c = nos[ev[:, 3]] - nos[ev[:, 0]]
+        vol = float(np.abs(np.einsum("ij,ij->i", a, np.cross(b, c))).sum() / 6.0)
+        area = float(np.real(self.areas).sum()) if getattr(self, "areas", None) is not None and len(self.areas) else 6.0 * vol ** (2.0 / 3.0)
+        x = f / float(np.real(self.c0))
+        return int(4.0 * np.pi / 3.0 * vol * x ** 3 + np.pi / 4.0 * area * x ** 2 + 1.5 * vol ** (1.0 / 3.0) * x) + 1
+
+    def _prepare_preconditioner(self, sys, nf):
+        """Resolve ``precond="auto"`` and make sure the modes the modal correction needs are on the device."""
+        precond = self.precond
+        if precond == "auto":
+            # the modes cost a few sweeps' worth of SpMVs once per assembly: worth it for anything but tiny problems
+            precond = "modal" if (self.NumNosC >= 2000 and nf >= 4) else "block"
+        if precond != "modal":
+            return precond
+        f_hi = float(np.max(np.asarray(self.freq, dtype=np.float64)))
+        delta = float(self.modal_delta)
+        f_cut = float(np.hypot(f_hi, delta))
+        # at most ~1000 modes are kept: shrink the margin above the sweep, then the cut itself, until the estimate fits
+        while self._mode_count_estimate(f_cut) > 960 and f_cut > 1.02 * f_hi:
+            f_cut = max(1.02 * f_hi, 0.97 * f_cut)
+        while self._mode_count_estimate(f_cut) > 960:
+            f_cut *= 0.97
+        key = (f_cut,)
+        if self._modes_key is None or self._modes_key[0] < f_cut:
+            sys.modal_compute(f_cut, n_hint=self._mode_count_estimate(f_cut), f_acc=min(f_hi, f_cut))
+            self._modes_key = key
+        return precond
+
+    def eigenfrequency(self, neigs=12, near_freq=None, optimize=False):
+        """The reference's modal analysis (``FEM_3D.py:1699-1768``): the ``neigs`` lowest room modes.  Leaves ``F_n`` (Hz,
+        ascending) and ``Vc`` (N, neigs) like the reference, returns ``F_n``.  Computed on the GPU by Chebyshev-filtered subspace
+        iteration + Rayleigh-Ritz on (H, Q); the reference runs ``spsolve(Q, H)`` + ARPACK."""
+        sys = self._system()
+        if not self._assembled:
+            self._ensure_volume(sys)
+            sys.assemble_volume(self.rho0, self.c0)
+            self._assembled = True
+            self._modes_key = None
+        c0 = float(np.real(self.c0))
+        # frequency below which Weyl's estimate predicts a few more than neigs modes
+        f = 20.0
+        while self._mode_count_estimate(f) < neigs + 4:
+            f *= 1.1
+        for _ in range(8):
+            sys.modal_compute(f, n_hint=self._mode_count_estimate(f), tol=1e-4, max_outer=30)
+            self._modes_key = (f,)
+            if sys.modal_count() >= neigs:
+                break
+            f *= 1.15
+        lam, V = sys.modal_get()
+        self.F_n = np.sqrt(np.maximum(lam[:neigs], 0.0)) / (2.0 * np.pi)
+        self.Vc = V[:neigs].T.copy()
+        return self.F_n
 
     # ---- evaluate (FEM_3D.py:2042-2090) ------------------------------------------------------
     def evaluate(self, R, interpolation_tolerance=0.001, plot=False):

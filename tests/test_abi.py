@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/femder_b200.h but not exported"
     assert set(declared_symbols()) == set(_lib.SIGNATURES), "ctypes signatures and header disagree"
-    assert lib.fdb_abi_version() == 1
+    assert lib.fdb_abi_version() == 2
     assert lib.fdb_sizeof_sweep_params() == ctypes.sizeof(_lib.SweepParams)
     assert lib.fdb_sizeof_sweep_result() == ctypes.sizeof(_lib.SweepResult)
 
