@@ -8,14 +8,13 @@ Workload: synthetic shoebox 3.0 x 4.0 x 2.5 m, 99 x 133 x 74 cells -> 1 005 000 
 point source q = 1e-4 near (1.0, 1.0, 1.2), receiver near (2.0, 3.0, 1.25), sweep 20..500 Hz at 1 Hz (481
 frequencies), every frequency converged to 1e-8 relative residual.
 
-A "step" is one call of the hot path on one batch of synthetic input: 96 (97 for the first) frequencies taken
-every `--stride` (5) Hz across the sweep, f = 20 + s + 5 j Hz for step s, so every step samples the whole 20..500 Hz
-range and 5 consecutive steps are exactly the 481-frequency sweep (a user's call solves all 481 at once; a fifth of
-it keeps the default run within minutes while the tail of a call - the last, hardest systems running in a
-narrowing batch - weighs about what it does in the full sweep).  Inside the call the frequencies run through
-`--batch` (16) solver slots of the fused multi-frequency SpMV; a slot whose frequency converged is reloaded with
-the next one.  With N ranks, rank r takes steps r, r+N, ... (frequency sharding, no collective on the solve
-path; weak scaling: per-GPU work per step is fixed whatever N is).
+A "step" is one call of the hot path on the whole workload: the 481-frequency sweep (`--stride 1`; `--stride s` takes every
+s-th frequency instead).  Inside the call the frequencies run through 16 solver slots of the fused multi-frequency SpMV
+(real arithmetic: rigid walls); a slot whose frequency converged is reloaded with the next one.  The preconditioner is
+block-Jacobi plus the modal coarse correction (tcgen05 kernels over the room's ~750 modes below 583 Hz, computed on the GPU
+once per assembly: part of the e2e leg, resident for `value`).
+With N ranks the SAME sweep is split: rank r solves frequencies r, r+N, ... of it (no collective on the solve path, receiver
+pressures gathered at the end) and the time is the slowest rank's - STRONG scaling: total work is fixed whatever N is.
 
 Timing: W >= 3 untimed warm-up steps, then exactly K steps bracketed by a barrier + torch.cuda.synchronize() on
 both sides and by CUDA events on the stream the library launches on; the reported time is the MAX over ranks.
@@ -45,12 +44,18 @@ WORKLOAD = ("synthetic shoebox 3.0x4.0x2.5 m, 99x133x74 cells, 1005000 DOF Tet4,
             "20-500 Hz at 1 Hz, tol 1e-8")
 
 
-STEP_STRIDE = 5  # Hz between the frequencies of one step (--stride); STEP_STRIDE steps tile the sweep
+STEP_STRIDE = 1  # Hz between the frequencies of one step (--stride): 1 = the whole 481-frequency sweep per step
 
 
 def step_frequencies(i):
     """Frequencies of step i: every STEP_STRIDE-th frequency of the sweep starting at 20 + (i mod STEP_STRIDE) Hz."""
     return np.arange(F_LO, F_HI + 1.0, 1.0)[(i % STEP_STRIDE)::STEP_STRIDE]
+
+
+def mode_count_estimate(f):
+    """Weyl's estimate for the benchmark room (3.0 x 4.0 x 2.5 m): sizes the block of the modal set-up."""
+    x = f / C0
+    return int(4 * np.pi / 3 * 30.0 * x ** 3 + np.pi / 4 * 59.0 * x ** 2 + 1.5 * 30.0 ** (1 / 3) * x) + 1
 
 
 def measured_peaks():
@@ -107,10 +112,10 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's algorithm (assembly + sparse direct solve per frequency)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, shape=(26, 34, 22), cores=None):
+def cpu_reference_run(steps, warmup, sizes, cores=None):
     from oracle import cpu_baseline
     workload_dof = (SHAPE[0] + 1) * (SHAPE[1] + 1) * (SHAPE[2] + 1)
-    return cpu_baseline.run(steps, warmup, shape=shape, cores=cores, f_lo=F_LO, f_hi=F_HI, src=SRC, rcv=RCV, c0=C0, rho0=RHO0,
+    return cpu_baseline.run(steps, warmup, sizes=sizes, cores=cores, f_lo=F_LO, f_hi=F_HI, src=SRC, rcv=RCV, c0=C0, rho0=RHO0,
                             workload_dof=workload_dof)
 
 
@@ -124,14 +129,16 @@ def run_reference(args):
         # count is read when numpy loads, so restart this process with the environment set.
         env = dict(os.environ, FDB_REF_BLAS1="1", OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
         os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
-    r = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup, args.cpu_sizes)
+    cb = {"value": r["value"], "unit": "frequencies/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+          "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"], "measured_points": r["points"], "fit": r["fit"],
+          "extrapolated": True}
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frequencies/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reference_sample": r["sample"]},
-            "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"],
-            "cpu_baseline": {"value": r["value"], "unit": "frequencies/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
-                             "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"]},
+            "measured_at_sample": r["measured_at_sample"], "sample_dof": r["N"], "measured_points": r["points"], "fit": r["fit"],
+            "cpu_baseline": cb,
             "e2e": {"value": r["value"], "unit": "frequencies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -146,7 +153,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import femder_b200 as fd
-    from femder_b200 import _lib
+    from femder_b200 import _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,9 +165,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.Stream(device=local_rank)
+    dev = f"cuda:{local_rank}"
 
     shape = tuple(int(t) for t in args.shape.split(","))
-    F = args.batch
 
     # ---- inputs: host mesh arrays in pinned memory (the e2e leg copies them every step) ----
     grid = fd.shoebox_tet4(*shape)
@@ -177,8 +184,10 @@ def run_ours(args):
     src_node = grid.closest_node(SRC)
     rcv_node = grid.closest_node(RCV)
     group_ids = np.arange(2, 8)
+    delta = args.modal_delta
+    f_cut = float(np.hypot(F_HI, delta))
 
-    # ---- resident system: assemble once on the GPU ----
+    # ---- resident system: assemble once on the GPU, room modes once ----
     sysm = fd.System(local_rank, stream.cuda_stream)
     t_setup = time.perf_counter()
     sysm.set_volume_mesh(nos, ev)
@@ -187,16 +196,24 @@ def run_ours(args):
     sysm.assemble_surface()
     sysm.synchronize()
     t_setup = time.perf_counter() - t_setup
-    mu_zero = np.zeros((len(group_ids), 512), dtype=np.complex128)
+    t_modes = time.perf_counter()
+    n_modes = sysm.modal_compute(f_cut, n_hint=mode_count_estimate(f_cut), f_acc=F_HI) if args.precond == "modal" else 0
+    sysm.synchronize()
+    t_modes = time.perf_counter() - t_modes
+    modal_info = {k: v for k, v in sysm.modal_info().items() if k != "residuals"} if n_modes else None
     rcv_nodes = np.array([[rcv_node] * 4], dtype=np.int32)
     rcv_w = np.array([[1.0, 0.0, 0.0, 0.0]])
 
-    batch_freqs = step_frequencies
+    def my_share(f):
+        """Strong scaling: this rank's frequencies of the step (dealt singly round-robin: every rank gets the same mix)."""
+        return f[sharding.owned_frequencies(len(f), 1, rank, world)]
 
     def step_resident(i):
-        f = batch_freqs(i)
-        _, pR, st = sysm.sweep(2 * np.pi * f, mu_zero[:, :len(f)], [src_node], [1e-4], rcv_nodes, rcv_w, want_pN=False,
-                               tol=args.tol, max_iter=args.max_iter, batch=F, check_every=args.check_every)
+        f = my_share(step_frequencies(i))
+        _, pR, st = sysm.sweep(2 * np.pi * f, np.zeros((len(group_ids), len(f)), dtype=np.complex128), [src_node], [1e-4],
+                               rcv_nodes, rcv_w, want_pN=False, tol=args.tol, max_iter=args.max_iter,
+                               batch="auto" if args.precond == "modal" else args.batch, check_every=args.check_every,
+                               precond=args.precond, modal_delta=delta)
         return len(f), st, pR
 
     def barrier():
@@ -208,29 +225,37 @@ def run_ours(args):
         """K steps of fn bracketed by barrier+sync and CUDA events on the library's stream; MAX over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nfreq, nk, its, unconv, extra = 0, 0, [], 0, []
+        nfreq, nk, its, unconv, relres, resumed = 0, 0, [], 0, 0.0, 0
         with torch.cuda.stream(stream):
             e0.record(stream)
             for s in range(args.steps):
-                n, st, x = fn(idx0 + s * world + rank)
-                nfreq += n; nk += st.n_kernels; its.extend(st.iters.tolist()); unconv += st.n_unconverged; extra.append(x)
+                n, st, _ = fn(idx0 + s)
+                nfreq += n; nk += st.n_kernels; its.extend(np.asarray(st.iters).ravel().tolist()); unconv += st.n_unconverged
+                relres = max(relres, float(np.max(st.relres)) if len(st.relres) else 0.0)
+                resumed += getattr(st, "n_resumed", 0)
             e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local_rank}")
-        tot = torch.tensor([float(nfreq), float(nk), float(unconv), float(np.sum(its))], dtype=torch.float64, device=f"cuda:{local_rank}")
+        my_ms = e0.elapsed_time(e1)
+        ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(nfreq), float(nk), float(unconv), float(np.sum(its)), float(resumed)], dtype=torch.float64, device=dev)
+        mx = torch.tensor([relres], dtype=torch.float64, device=dev)
+        per_rank = [None] * world
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        return float(ms.item()), tot.tolist(), its
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_gather_object(per_rank, {"rank": rank, "seconds": my_ms * 1e-3, "frequencies": nfreq, "iterations": int(np.sum(its))})
+        else:
+            per_rank = [{"rank": 0, "seconds": my_ms * 1e-3, "frequencies": nfreq, "iterations": int(np.sum(its))}]
+        return float(ms.item()), tot.tolist(), its, float(mx.item()), per_rank
 
     # ---- warm-up (untimed) then the timed region ----
-    idx_w = args.steps * world  # warm-up uses batches after the timed ones in the visiting order
     for s in range(args.warmup):
-        step_resident(idx_w + s * world + rank)
+        step_resident(args.steps + s)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, tot, its = timed(step_resident, 0)
+    ms, tot, its, max_relres, per_rank = timed(step_resident, 0)
     clocks = sampler.stop() if rank == 0 else None
     value = tot[0] / (ms * 1e-3)
 
@@ -238,38 +263,60 @@ def run_ours(args):
     AP = fd.AirProperties(c0=C0, rho0=RHO0)
     S = fd.Source(coord=grid.nos[src_node], q=[1e-4])
     R = fd.Receiver(coord=grid.nos[rcv_node])
-    h2d = nos.nbytes + ev.nbytes + es.nbytes + 4 * len(es) + 16 * (481 // STEP_STRIDE + 1) * (1 + len(group_ids))
+    n_step = len(step_frequencies(0))
+    h2d = nos.nbytes + ev.nbytes + es.nbytes + 4 * len(es) + 16 * n_step * (1 + len(group_ids))
     d2h_holder = [0]
 
-    def step_e2e(i):
-        f = batch_freqs(i)
+    def make_obj(f, **kw):
         AC = fd.AlgControls(AP, freq_vec=f)
         BC = fd.BC(AC, AP)
         for g in group_ids:
             BC.rigid(int(g))
-        obj = fd.FEM3D(grid, S, R, AP, AC, BC, device=local_rank, stream=stream.cuda_stream, tol=args.tol,
-                       max_iter=args.max_iter, batch=F, check_every=args.check_every, shard=False)  # every rank runs its own step
+        return fd.FEM3D(grid, S, R, AP, AC, BC, device=local_rank, stream=stream.cuda_stream, tol=args.tol, max_iter=args.max_iter,
+                        check_every=args.check_every, shard=(world > 1), precond=args.precond if args.precond != "modal" else "auto",
+                        modal_delta=delta, **kw)
+
+    def step_e2e(i, keep_pN=False, pN_out=None):
+        obj = make_obj(step_frequencies(i))
         obj._sys = sysm            # reuse the device allocation; everything below is recomputed from the host buffers
-        obj._sys_key = None        # force mesh upload + pattern build + assembly (a fresh object is not assembled)
-        obj.compute(timeit=False, keep_pN=False)
+        obj._sys_key = None        # force mesh upload + pattern build + assembly + modal set-up (a fresh object has none of them)
+        obj.pN_out = pN_out
+        obj.compute(timeit=False, keep_pN=keep_pN)
         # read back: Heron areas, receiver pressures, iteration counts, residuals (H, Q, A stay on the GPU until asked for)
-        d2h_holder[0] = obj.areas.nbytes // 2 + obj.pR.nbytes + obj.iters.nbytes + obj.relres.nbytes
-        return len(f), obj.stats, obj.pR
+        d2h_holder[0] = obj.areas.nbytes // 2 + obj.pR.nbytes + obj.iters.nbytes + obj.relres.nbytes + (obj.pN.nbytes if keep_pN else 0)
+        st = obj.stats
+        return (len(obj.freq) if world == 1 else len(my_share(obj.freq))), st, obj.pR
 
     e2e = None
+    e2e_pN = None
     if not args.no_e2e:
-        step_e2e(idx_w + rank)  # one warm-up of the e2e path
-        ms_e, tot_e, _ = timed(step_e2e, 0)
+        step_e2e(args.steps)  # one warm-up of the e2e path
+        ms_e, tot_e, _, relres_e, per_rank_e = timed(step_e2e, 0)
         e2e = {"value": tot_e[0] / (ms_e * 1e-3), "unit": "frequencies/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h_holder[0]), "ms_per_step": ms_e / args.steps,
-               "call": "FEM3D.compute(keep_pN=False): mesh upload, pattern + assembly, receiver location, sweep, receiver read-back"}
+               "d2h_bytes_per_step": int(d2h_holder[0]), "ms_per_step": ms_e / args.steps, "max_relres": relres_e,
+               "per_rank": per_rank_e if world > 1 else None,
+               "call": "FEM3D.compute(keep_pN=False) with all solver defaults: mesh upload, pattern + assembly, room modes "
+                       "(Chebyshev-filtered subspace iteration), receiver location, sweep, receiver read-back"}
+        if world == 1 and not args.no_pn:
+            # the reference's actual output contract once: pN (n_f, N) complex128 on the host (pinned destination)
+            f0 = step_frequencies(0)
+            buf = torch.empty((len(f0), grid.NumNosC, 2), dtype=torch.float64).pin_memory()
+            pN_host = buf.numpy().view(np.complex128).reshape(len(f0), grid.NumNosC)
+            barrier()
+            tp = time.perf_counter()
+            step_e2e(0, keep_pN=True, pN_out=pN_host)
+            torch.cuda.synchronize()
+            tp = time.perf_counter() - tp
+            e2e_pN = {"value": len(f0) / tp, "unit": "frequencies/s", "seconds": tp, "d2h_bytes_per_step": int(d2h_holder[0]),
+                      "call": "FEM3D.compute(keep_pN=True): as e2e plus the (n_f, N) complex128 pressure array copied to pinned host memory"}
+            del buf, pN_host
 
-    # ---- rooflines of the three kernels of a solver iteration, each measured live with CUDA events on the launching
-    #      stream (50 back-to-back launches on resident vectors, working set > L2); `roofline` = the dominant one ----
+    # ---- rooflines of the kernels of a solver iteration, each measured live with CUDA events on the launching
+    #      stream (back-to-back launches on resident vectors, working set > L2); `roofline` = the dominant one ----
     peaks, peak_src = measured_peaks()
-    reps = 50
-    real = F >= 4  # the rigid workload runs in real arithmetic whenever the batch width allows it
-    bj = real and F <= 16
+    reps = 40
+    F = 16
+    modal = args.precond == "modal"
     traffic_file = {}
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.isfile(tp):
@@ -277,34 +324,58 @@ def run_ours(args):
             traffic_file = json.load(open(tp))
         except Exception:
             traffic_file = {}
-    names = {0: ("K5", "k_spmv_blob (fused multi-frequency SpMV, shared-memory x tiles)"),
-             1: ("K6a", "k_update_bj (residual update + block-Jacobi z = B r out of shared memory + rho, ||r||^2)" if bj
-                 else "k_update (residual update + Jacobi + rho, ||r||^2)"),
-             2: ("K6b", "k_pupdate_bj (x += alpha p, p = z + beta p)" if bj else "k_pupdate (x += alpha p, p = z + beta p)")}
+    names = [(0, "K5", "k_spmv_blob (fused multi-frequency SpMV, shared-memory x tiles)"),
+             (1, "K6a", "k_update_bj (residual update + block-Jacobi z = B r out of shared memory)"),
+             (2, "K6b", "k_pupdate_bj (x += alpha p, p = z + beta p)")]
+    if modal:
+        names += [(3, "K8a", "k_modal_project (c = V^T r: tcgen05.mma over bf16 mode tiles, partial sums in TMEM)"),
+                  (5, "K8b", "k_modal_coef (block partials -> e = d c as the bf16 operand image)"),
+                  (4, "K8c", "k_modal_expand (z += V e on tcgen05, then rho' = r^T z, ||r||^2 and the iteration's scalars)")]
     kernels = []
-    for which in (0, 1, 2):
-        sysm.iteration_enqueue(F, 1, -1, real=real, block_jacobi=bj)      # fresh vectors and scalars, every slot active
-        sysm.iteration_enqueue(F, 5, which, real=real, block_jacobi=bj)   # warm-up
+    for which, kid, label in names:
+        sysm.iteration_enqueue(F, 1, -1, real=True, block_jacobi=True, modal=modal)      # fresh vectors and scalars, every slot active
+        sysm.iteration_enqueue(F, 5, which, real=True, block_jacobi=True, modal=modal)   # warm-up
         barrier()
         with torch.cuda.stream(stream):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record(stream)
-            nbytes = sysm.iteration_enqueue(F, reps, which, real=real, block_jacobi=bj)
+            nbytes = sysm.iteration_enqueue(F, reps, which, real=True, block_jacobi=True, modal=modal)
             a1.record(stream)
         torch.cuda.synchronize()
         us = a0.elapsed_time(a1) / reps * 1e3
         achieved = nbytes / (us * 1e-6) / 1e9
-        kernels.append({"id": names[which][0], "kernel": names[which][1] + ", batch %d, %s arithmetic" % (F, "real" if real else "complex"),
+        kernels.append({"id": kid, "kernel": label + f", batch {F}, real arithmetic" + (f", {n_modes} modes" if which >= 3 else ""),
                         "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                        "traffic": traffic_file.get(names[which][0]), "algorithmic_bytes_per_launch": int(nbytes), "us_per_launch": us})
+                        "traffic": traffic_file.get(kid), "algorithmic_bytes_per_launch": int(nbytes), "us_per_launch": us})
     dom = max(kernels, key=lambda k: k["us_per_launch"])
     roofline = dict(dom)
+    it_us = sum(k["us_per_launch"] for k in kernels)
+    it_b = sum(k["algorithmic_bytes_per_launch"] for k in kernels)
     roofline.update({"peak_source": peak_src,
-                     "how": f"{reps} back-to-back launches on resident vectors (matrix + vectors > L2), torch CUDA events on the launching stream",
+                     "how": f"{reps} back-to-back launches on resident vectors (matrix + vectors + mode tiles > L2), torch CUDA events on the "
+                            "launching stream; the modal kernels with ALL stored modes applied (a batch at f applies those below sqrt(f^2 + delta^2))",
                      "iteration_kernels": kernels,
-                     "iteration": {"us": sum(k["us_per_launch"] for k in kernels),
-                                   "algorithmic_bytes": sum(k["algorithmic_bytes_per_launch"] for k in kernels),
-                                   "frac": sum(k["algorithmic_bytes_per_launch"] for k in kernels) / (sum(k["us_per_launch"] for k in kernels) * 1e-6) / 1e9 / peaks["hbm_gbs"]}})
+                     "iteration": {"us": it_us, "algorithmic_bytes": it_b, "frac": it_b / (it_us * 1e-6) / 1e9 / peaks["hbm_gbs"]}})
+
+    # ---- a second workload on the same mesh: one wall with normalized admittance 0.02 -> complex arithmetic, 8 slots ----
+    extra = None
+    if rank == 0 and not args.no_extra:
+        fx = np.arange(F_LO, F_HI + 1.0, 1.0)[::5]
+        mu = np.zeros((len(group_ids), len(fx)), dtype=np.complex128)
+        mu[5] = 0.02 / (RHO0 * C0)
+        sysm.sweep(2 * np.pi * fx[:16], mu[:, :16], [src_node], [1e-4], rcv_nodes, rcv_w, want_pN=False, tol=args.tol, precond=args.precond,
+                   batch="auto", check_every=args.check_every, modal_delta=delta)       # warm-up (graphs, boundary damping of the modes)
+        torch.cuda.synchronize()
+        tx = time.perf_counter()
+        _, _, stx = sysm.sweep(2 * np.pi * fx, mu, [src_node], [1e-4], rcv_nodes, rcv_w, want_pN=False, tol=args.tol, precond=args.precond,
+                               batch="auto", check_every=args.check_every, modal_delta=delta)
+        torch.cuda.synchronize()
+        tx = time.perf_counter() - tx
+        extra = {"workload": "same mesh, wall z = 2.5 m with normalized admittance 0.02 (SURVEY 8d), every 5th frequency of 20-500 Hz: complex "
+                             "arithmetic, 8 solver slots, boundary overlay in the SpMV, modes damped by v^T A v",
+                 "value": len(fx) / tx, "unit": "frequencies/s", "seconds": tx, "frequencies": int(len(fx)),
+                 "iters_mean": float(np.mean(stx.iters)), "iters_max": int(np.max(stx.iters)), "unconverged": int(stx.n_unconverged),
+                 "max_relres": float(np.max(stx.relres)), "precond": stx.precond_used}
 
     # ---- the CPU baseline's own mesh (config 1, 21 735 DOF) through the same public call: the two arms' `value`s are on
     #      different problem sizes (the reference cannot factorise 1M DOF), this one is the like-for-like comparison
@@ -318,37 +389,39 @@ def run_ours(args):
             BC1.rigid(int(g))
         S1 = fd.Source(coord=g1.nos[g1.closest_node(SRC)], q=[1e-4])
         R1 = fd.Receiver(coord=g1.nos[g1.closest_node(RCV)])
-        o1 = fd.FEM3D(g1, S1, R1, AP, AC1, BC1, device=local_rank, tol=args.tol, max_iter=args.max_iter, check_every=args.check_every,
-                      shard=False)
+        o1 = fd.FEM3D(g1, S1, R1, AP, AC1, BC1, device=local_rank, tol=args.tol, max_iter=args.max_iter, shard=False)
         o1.compute(timeit=False, keep_pN=False)      # warm-up (graphs, allocations)
         o1.H = None
         t1 = time.perf_counter()
         o1.compute(timeit=False, keep_pN=False)
         t1 = time.perf_counter() - t1
         same_mesh = {"value": len(f1) / t1, "unit": "frequencies/s", "N": int(g1.NumNosC), "frequencies": int(len(f1)), "seconds": t1,
-                     "iters_mean": float(np.mean(o1.iters)), "unconverged": int(o1.stats.n_unconverged),
-                     "what": "FEM3D.compute(keep_pN=False) on the cpu_baseline mesh (config-1 shoebox 26x34x22, rigid), whole 20-500 Hz sweep, "
-                             "host wall clock incl. upload, pattern, assembly, sweep"}
+                     "iters_mean": float(np.mean(o1.iters)), "unconverged": int(o1.stats.n_unconverged), "precond": o1.stats.precond_used,
+                     "what": "FEM3D.compute(keep_pN=False), all defaults, on the cpu_baseline's smallest mesh (config-1 shoebox 26x34x22, rigid), "
+                             "whole 20-500 Hz sweep, host wall clock incl. upload, pattern, assembly, room modes, sweep"}
 
     line = None
     if rank == 0:
         its_a = np.asarray(its)
         line = {"metric": METRIC, "value": value, "unit": "frequencies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "step": f"one sweep call over the {481 // STEP_STRIDE}-{481 // STEP_STRIDE + 1} frequencies 20+s+{STEP_STRIDE}j Hz (COCG to {args.tol:g}, {F} solver slots, "
-                           f"continuous refill); {STEP_STRIDE} steps = the whole sweep", "batch": F, "parallelism": f"frequency-sharded x{world}",
-                           "l2": "working set per step 0.9 GB > 126 MB L2 (no flush needed)", "N": int(grid.NumNosC), "nnz": int(sysm.nnz),
-                           "setup_seconds_once": t_setup},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1]),
+                "config": {"workload": WORKLOAD,
+                           "step": f"one sweep call over the {n_step} frequencies 20..500 Hz every {STEP_STRIDE} Hz (COCG to a TRUE relative residual of "
+                                   f"{args.tol:g}, 16 real solver slots with continuous refill, preconditioner {args.precond})",
+                           "parallelism": f"frequency-sharded x{world}: the same sweep split over the ranks, no collective on the solve path",
+                           "l2": "working set per step (matrix 0.3 GB + 5 vectors x 128 MB + mode tiles 1.5 GB) > 126 MB L2 (no flush needed)",
+                           "N": int(grid.NumNosC), "nnz": int(sysm.nnz), "assembly_seconds_once": t_setup,
+                           "modes": int(n_modes), "modes_seconds_once": t_modes, "modal_delta_hz": delta, "modal_setup": modal_info},
+                "clocks": clocks, "e2e": e2e, "e2e_pN": e2e_pN, "gpu_launches": int(tot[1]),
                 "solver": {"iters_mean": float(its_a.mean()), "iters_min": int(its_a.min()), "iters_max": int(its_a.max()),
-                           "unconverged": int(tot[2]), "frequencies": int(tot[0])},
-                "roofline": roofline, "same_mesh_as_cpu_baseline": same_mesh}
+                           "unconverged": int(tot[2]), "resumed": int(tot[4]), "max_relres": max_relres, "frequencies": int(tot[0])},
+                "per_rank": per_rank, "roofline": roofline, "extra": extra, "same_mesh_as_cpu_baseline": same_mesh}
         if world == 1 and not args.no_cpu:
             # CUDA-free child process: the CPU baseline forks worker processes, which must not inherit a CUDA context
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps),
-                                      "--warmup", "1"], capture_output=True, text=True, timeout=900)
+                                      "--warmup", "1", "--cpu-sizes", "2"], capture_output=True, text=True, timeout=1200)
                 ref = json.loads(out.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = ref["cpu_baseline"]
             except Exception as e:  # the bench line must still be printed
@@ -369,13 +442,18 @@ def main():
     ap.add_argument("--stride", type=int, default=STEP_STRIDE, help="Hz between the frequencies of one step: 481/stride frequencies per step")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="solver slots (16: real arithmetic for the rigid workload)")
+    ap.add_argument("--precond", default="modal", choices=["modal", "block", "jacobi"])
+    ap.add_argument("--modal-delta", type=float, default=300.0, help="Hz: a batch at f applies the modes below sqrt(f^2 + delta^2)")
+    ap.add_argument("--batch", type=int, default=16, help="solver slots for --precond block/jacobi (the modal path always runs 16 real slots)")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iter", type=int, default=200000)
-    ap.add_argument("--check-every", type=int, default=64)
+    ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--shape", default=",".join(str(s) for s in SHAPE))
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-sizes", type=int, default=3, help="rungs of the CPU ladder the reference arm measures (21 735 / 47 250 / 94 424 DOF)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pn", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     STEP_STRIDE = max(1, args.stride)

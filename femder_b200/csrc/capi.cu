@@ -440,7 +440,7 @@ int fdb_iteration_enqueue(fdb_system* sys, int batch, int reps, int flags, int w
     FDB_API_BEGIN
     FDB_SYS(sys);
     FDB_REQUIRE(which < 0 || reps > 0, "reps must be positive");
-    FDB_REQUIRE(which >= -1 && which <= 2, "which must be -1 (prepare), 0 (K5), 1 (K6a) or 2 (K6b)");
+    FDB_REQUIRE(which >= -1 && which <= 5, "which must be -1 (prepare), 0 (K5), 1 (K6a), 2 (K6b), 3 / 4 / 5 (modal projection / expansion / coefficients)");
     fdb::run_iteration_enqueue(sys, batch, reps, flags, which, algorithmic_bytes);
     FDB_API_END
 }

@@ -498,17 +498,21 @@ int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz) {
 }
 
 // the three launches between K6a and K6b: c = V^T r, e = d c, z += V e (+ rho', ||r||^2, finalisation)
-void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start) {
+// parts: 1 = projection, 2 = coefficients, 4 = expansion (bench.py times them one at a time)
+void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts) {
     const int G = modal_grid(sys);
     const double* r = (const double*)w->r.p;
-    k_modal_project<<<G, kModalThreads, project_smem(), sys->stream>>>(r, sys->modal_v.p, sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
+    if (parts & 1)
+        k_modal_project<<<G, kModalThreads, project_smem(), sys->stream>>>(r, sys->modal_v.p, sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
     const int cg = grid_for((int64_t)sys->mode_chunks * kMC * 16, 256);
-    if (w->real)
+    if (!(parts & 2)) {
+    } else if (w->real)
         k_modal_coef<false><<<cg, 256, 0, sys->stream>>>(w->c_part.p, G, sys->modal_lam.p, sys->modal_res.p, sys->n_modes, nullptr, w->coef.p, 0, w->F,
                                                         w->sc.p, w->e_img.p);
     else
         k_modal_coef<true><<<cg, 256, 0, sys->stream>>>(w->c_part.p, G, sys->modal_lam.p, sys->modal_res.p, sys->n_modes, sys->modal_adiag.p, w->coef.p,
                                                        overlay ? sys->n_groups : 0, w->F, w->sc.p, w->e_img.p);
+    if (!(parts & 4)) return;
     double* part = (double*)w->partial.p;
     auto go = [&](auto kern) {
         kern<<<G, kModalThreads, expand_smem(), sys->stream>>>(r, w->z32.p, (double*)w->p.p, sys->modal_v.p, sys->mode_chunks, w->e_img.p, w->N,
@@ -516,6 +520,17 @@ void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start) {
     };
     if (w->real) { if (start) go(k_modal_expand<false, true>); else go(k_modal_expand<false, false>); }
     else { if (start) go(k_modal_expand<true, true>); else go(k_modal_expand<true, false>); }
+}
+
+// Algorithmic bytes of one launch at `modes_use` modes: 2 bytes per node and mode (the bf16 tile stream, whole 8-mode blocks) plus the
+// FP64 residual tile (projection) or the residual, the FP32 z tile read and written and the coefficient image (expansion).
+int64_t modal_bytes(fdb_system* sys, SweepWork* w, int modes_use, int part) {
+    const int64_t rows_pad = sys->n_tiles * 128;
+    const int64_t v = rows_pad * (int64_t)(((modes_use + 7) / 8) * 8) * 2;
+    const int64_t vec = (int64_t)w->N * kModalCols;
+    if (part == 1) return v + 8 * vec;
+    if (part == 4) return v + 8 * vec + 2 * 4 * vec + (int64_t)modes_use * 64;
+    return (int64_t)modal_grid(sys) * modes_use * 64 + (int64_t)modes_use * 64;   // coefficients: the block partials in, the image out
 }
 
 // boundary damping of the modes, once per surface assembly

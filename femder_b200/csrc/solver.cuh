@@ -233,7 +233,8 @@ __device__ __forceinline__ void fin_start(Scalars* __restrict__ sc, int ff, cons
 constexpr int kModalCols = 16;   // real columns per row the tensor-core kernels are built for (16 real or 8 complex slots)
 void modal_prepare(fdb_system* sys, SweepWork* w);
 int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz);
-void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start);   // c = V^T r ; e = d c ; z += V e, rho', ||r||^2, finalisation
+void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts = 7);   // c = V^T r ; e = d c ; z += V e, rho', ||r||^2, finalisation
+int64_t modal_bytes(fdb_system* sys, SweepWork* w, int modes_use, int part);
 void modal_build_adiag(fdb_system* sys);
 void modal_set(fdb_system* sys, int n_modes, const double* lam, const double* V);
 void modal_get(fdb_system* sys, double* lam, double* V);

@@ -2241,7 +2241,7 @@ static bool bench_real(fdb_system* sys, SweepWork* w, int F, int flags) {
 int64_t spmv_algorithmic_bytes(fdb_system* sys, int F, bool with_boundary, bool real) {
     // indptr + (indices + H + Q) once + overlay + x read and y write per frequency
     const int64_t N = sys->n_nodes, Z = sys->vol.nnz;
-    const bool has_overlay = sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;
+    const bool has_overlay = with_boundary && sys->have_overlay && sys->n_ov > 0 && sys->n_groups > 0;   // a rigid launch never reads the overlay
     // counted on the CSR sizes (the algorithm's bytes); the SELL-8 copy the kernel streams adds padding on top
     return 4 * (N + 1) + Z * 20 + (has_overlay ? 4 * (N + 1) + sys->n_ov * 16 : 0) + (real ? 16 : 32) * N * F;
 }
@@ -2294,9 +2294,13 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
     FDB_REQUIRE(!(flags & 1), "the iteration bench covers rigid-wall sweeps");
     SweepWork* w = get_work(sys, F);
     w->real = bench_real(sys, w, F, flags);
-    const bool bj = (flags & 4) && w->real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;   // the bench covers real sweeps
-    w->precond = bj ? 1 : 0;
+    const bool modal = (flags & 8) != 0;
+    if (modal) FDB_REQUIRE(sys->have_modes && w->real && F == kModalCols, "the modal iteration bench needs the modes and 16 real slots");
+    const bool bj = ((flags & 4) || modal) && w->real && F <= 16 && sys->n_tiles > 0 && sys->tile_rows == 128;   // the bench covers real sweeps
+    w->precond = modal ? 2 : (bj ? 1 : 0);
     if (bj) { FDB_DISPATCH_F(F, bj_prepare(sys, w)); }
+    if (modal) modal_prepare(sys, w);
+    const int modes_all = modal ? std::min(((sys->n_modes + 15) / 16) * 16, sys->mode_chunks * 128) : 0;
     const int64_t N = w->N, ne = N * F;
     const int64_t vb = (w->real ? 8 : 16) * ne;   // bytes of one vector pass
     if (which < 0) {
@@ -2311,6 +2315,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
             h.bb[f] = 0.0;   // never "converged": rr > tol2 * 0
         }
         h.tol2 = 1.0;
+        h.modes_use = modes_all;
         upload_scalars(sys, w, h, coef);
         const int64_t n2 = w->real ? (ne + 1) / 2 : ne;   // buffers are sized in double2
         k_fill_pattern<<<kNumSMs * 4, 256, 0, sys->stream>>>(w->p.p, n2);
@@ -2323,11 +2328,17 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
     }
     for (int i = 0; i < reps; ++i) {
         if (which == 0) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, false)); }
+        else if (which == 3) modal_apply(sys, w, false, false, 1);
+        else if (which == 4) modal_apply(sys, w, false, false, 4);
+        else if (which == 5) modal_apply(sys, w, false, false, 2);
         else { FDB_DISPATCH_F(F, vec_kernel(sys, w, false, which)); }
     }
     FDB_CUDA(cudaGetLastError());
     if (bytes) {
         if (which == 0) *bytes = spmv_algorithmic_bytes(sys, F, false, w->real);
+        else if (which == 3) *bytes = modal_bytes(sys, w, modes_all, 1);
+        else if (which == 4) *bytes = modal_bytes(sys, w, modes_all, 4);
+        else if (which == 5) *bytes = modal_bytes(sys, w, modes_all, 2);
         else if (which == 1) *bytes = bj ? 3 * vb + 4 * ne + sys->n_tiles * (int64_t)kBjPacked * 4 : 3 * vb + 16 * N;
         else *bytes = bj ? 4 * vb + 4 * ne : 5 * vb + 16 * N;
     }

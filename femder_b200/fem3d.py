@@ -132,6 +132,7 @@ class FEM3D:
         self.precond = precond          # "auto" | "modal" | "block" | "jacobi"
         self.modal_delta = modal_delta  # Hz: a frequency f is solved with the modes below sqrt(f^2 + modal_delta^2)
         self._modes_key = None
+        self.pN_out = None              # optional caller-owned (n_freq, N) complex128 destination for pN (e.g. pinned host memory)
         self.warm_start = warm_start
         self.compat_complex64 = compat_complex64
         self.shard = shard  # under torch.distributed: split the frequencies over the ranks and gather the rows at the end
@@ -291,7 +292,8 @@ class FEM3D:
         precond = self._prepare_preconditioner(sys, nf)
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
         owned = sharding.owned_frequencies(nf, 1, rank, world)
-        pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN,
+        pN_out = self.pN_out if (keep_pN and self.pN_out is not None and world == 1) else None
+        pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN, pN_out=pN_out,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch if precond != "modal" else "auto",
                                   check_every=self.check_every, warm_start=self.warm_start, precond=precond, rhs_vecs=rhs_vecs,
                                   rhs_coef=None if rhs_coef is None else rhs_coef[:, owned], modal_delta=self.modal_delta)

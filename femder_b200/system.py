@@ -427,11 +427,12 @@ class System:
         check(self._lib.fdb_spmv_bench(self._h, int(batch), int(reps), flags, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
 
-    def iteration_enqueue(self, batch, reps, which, real=True, block_jacobi=True):
-        """Enqueue ``reps`` launches of one kernel of a solver iteration (which: -1 prepare, 0 K5, 1 K6a, 2 K6b) on the
-        system's stream without synchronising; returns that kernel's algorithmic bytes per launch."""
+    def iteration_enqueue(self, batch, reps, which, real=True, block_jacobi=True, modal=False):
+        """Enqueue ``reps`` launches of one kernel of a solver iteration (which: -1 prepare, 0 K5, 1 K6a, 2 K6b, with ``modal``
+        3 projection, 4 expansion, 5 coefficients) on the system's stream without synchronising; returns that kernel's algorithmic
+        bytes per launch."""
         nbytes = C.c_int64()
-        flags = (2 if real else 0) | (4 if block_jacobi else 0)
+        flags = (2 if real else 0) | (4 if block_jacobi else 0) | (8 if modal else 0)
         check(self._lib.fdb_iteration_enqueue(self._h, int(batch), int(reps), flags, int(which), C.byref(nbytes)))
         return nbytes.value
 

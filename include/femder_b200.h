@@ -185,9 +185,11 @@ int fdb_spmv_enqueue(fdb_system* sys, int batch, int reps, int flags, int64_t* a
 /* The three kernels of one solver iteration, one at a time, for per-kernel rooflines (bench.py): enqueue `reps` launches
  * of kernel `which` on resident synthetic vectors without synchronising.  which = -1 prepares the vectors (call it first),
  * 0 = K5 (fused SpMV with its dot-product epilogue), 1 = K6a (residual update + preconditioner + reductions),
- * 2 = K6b (solution and search-direction update).  flags: FDB_SPMV_REAL, FDB_ITER_BLOCK_JACOBI (rigid-wall systems only).
- * algorithmic_bytes = what one launch of that kernel has to move. */
+ * 2 = K6b (solution and search-direction update); with FDB_ITER_MODAL also 3 = modal projection c = V^T r, 4 = modal expansion
+ * z += V e (+ rho', ||r||^2), 5 = modal coefficients.  flags: FDB_SPMV_REAL, FDB_ITER_BLOCK_JACOBI, FDB_ITER_MODAL (all stored
+ * modes applied; 16 real slots; rigid-wall systems only).  algorithmic_bytes = what one launch of that kernel has to move. */
 #define FDB_ITER_BLOCK_JACOBI 4
+#define FDB_ITER_MODAL 8
 int fdb_iteration_enqueue(fdb_system* sys, int batch, int reps, int flags, int which, int64_t* algorithmic_bytes);
 
 #ifdef __cplusplus

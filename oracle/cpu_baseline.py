@@ -3,11 +3,13 @@ and its ``--impl reference`` arm.
 
 One frequency is solved exactly as the reference does it (``femder/FEM_3D.py:1312-1318``): build
 ``G = H - w^2 Q`` (rigid walls), factorise it from scratch, solve, discard the factors.  scipy SuperLU stands in
-for MKL PARDISO (``pyMKL`` is un-vendored and not installable here).  SuperLU is single-threaded, so to use every
-host core a step solves ``cores`` frequencies at once, one per worker process; the reference's PARDISO would
+for MKL PARDISO (``pyMKL`` is un-vendored and not installable here).  SuperLU is single-threaded, so to use the
+host's cores a step solves several frequencies at once, one per worker process; the reference's PARDISO would
 instead thread one factorisation.
 
-The 1M-DOF factorisation does not fit host memory (3-D fill), so the sample mesh is config 1's 21 735-DOF shoebox.
+The 1M-DOF factorisation does not fit host memory (3-D fill), so the path is MEASURED on a ladder of smaller shoebox
+meshes of the same room (``measure_sizes``) and the throughput at the benchmark's size is an extrapolation of the
+fitted power law ``frequencies/s = a * DOF^-p`` - labelled as such wherever it is printed.
 """
 from __future__ import annotations
 
@@ -43,16 +45,16 @@ def _solve(freq):
     return complex(p[_STATE["rcv"]])
 
 
-def run(steps, warmup, shape=(26, 34, 22), cores=None, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0, 1.2), rcv=(2.0, 3.0, 1.25),
-        c0=343.0, rho0=1.21, workload_dof=None):
-    cores = cores or os.cpu_count() or 1
+def measure(shape, steps, warmup, workers, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0, 1.2), rcv=(2.0, 3.0, 1.25), c0=343.0, rho0=1.21):
+    """``steps`` timed steps of ``workers`` concurrent factorise-and-solve calls on the shoebox ``shape``; returns
+    dict(N, frequencies_per_s, seconds, workers, steps)."""
     total_steps = steps + warmup
     rng = np.random.default_rng(0)
-    freqs = rng.permutation(np.linspace(f_lo, f_hi, total_steps * cores)).reshape(total_steps, cores)
+    freqs = rng.permutation(np.linspace(f_lo, f_hi, total_steps * workers)).reshape(total_steps, workers)
     ctx = mp.get_context("fork")   # callers must not hold a CUDA context (bench.py runs this in a CUDA-free subprocess)
     times = []
-    with ctx.Pool(cores, initializer=_setup, initargs=(shape, list(src), list(rcv), c0, rho0)) as pool:
-        n_dof = pool.map(_ready, range(cores), chunksize=1)[0]  # workers have assembled (untimed)
+    with ctx.Pool(workers, initializer=_setup, initargs=(shape, list(src), list(rcv), c0, rho0)) as pool:
+        n_dof = pool.map(_ready, range(workers), chunksize=1)[0]  # workers have assembled (untimed)
         for s in range(total_steps):
             t = time.perf_counter()
             pool.map(_solve, list(freqs[s]), chunksize=1)
@@ -60,13 +62,47 @@ def run(steps, warmup, shape=(26, 34, 22), cores=None, f_lo=20.0, f_hi=500.0, sr
             if s >= warmup:
                 times.append(dt)
     total = float(np.sum(times))
-    measured = steps * cores / total
-    scale = (n_dof / workload_dof) if workload_dof else 1.0
+    return {"N": int(n_dof), "shape": list(shape), "frequencies_per_s": steps * workers / total, "seconds": total, "workers": int(workers),
+            "steps": int(steps)}
+
+
+# the room of the benchmark (3.0 x 4.0 x 2.5 m) at growing resolution: 21 735, 47 250 and 94 424 DOF
+LADDER = ((26, 34, 22), (34, 44, 29), (43, 57, 36))
+
+
+def fit_power_law(points):
+    """Least-squares fit of log(frequencies/s) = log a - p log N; returns (a, p)."""
+    n = np.log([p["N"] for p in points])
+    y = np.log([p["frequencies_per_s"] for p in points])
+    if len(points) == 1:
+        return float(np.exp(y[0]) * np.exp(n[0])), 1.0          # one size only: linear in DOF (favours the reference)
+    A = np.vstack([np.ones_like(n), -n]).T
+    (la, p), *_ = np.linalg.lstsq(A, y, rcond=None)
+    return float(np.exp(la)), float(p)
+
+
+def run(steps, warmup, sizes=2, cores=None, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0, 1.2), rcv=(2.0, 3.0, 1.25),
+        c0=343.0, rho0=1.21, workload_dof=None):
+    """Measure the first ``sizes`` rungs of the ladder (every host core busy, fewer workers on the largest meshes whose factors
+    are gigabytes each), fit the power law, and report the throughput extrapolated to ``workload_dof``."""
+    cores = cores or os.cpu_count() or 1
+    points = []
+    for i, shape in enumerate(LADDER[:max(1, sizes)]):
+        workers = max(1, min(cores, (cores, max(3, cores // 2), max(3, cores // 4))[i]))
+        st = steps if i == 0 else 1
+        wu = warmup if i == 0 else 0
+        points.append(measure(shape, st, wu, workers, f_lo, f_hi, src, rcv, c0, rho0))
+    a, p = fit_power_law(points)
+    measured = points[0]["frequencies_per_s"]
+    value = a * float(workload_dof) ** (-p) if workload_dof else measured
+    pts = "; ".join(f"{q['N']} DOF: {q['frequencies_per_s']:.4g} frequencies/s ({q['workers']} concurrent factorisations, "
+                    f"{q['steps'] * q['workers']} frequencies in {q['seconds']:.1f} s)" for q in points)
     sample = (f"oracle port of the reference algorithm (FP64 assembly, then per frequency: build G, scipy SuperLU factorise + solve, "
-              f"PARDISO stand-in) on the config-1 shoebox {shape[0]}x{shape[1]}x{shape[2]} cells = {n_dof} DOF; {steps} steps x {cores} "
-              f"frequencies (one per core) drawn from {f_lo:g}-{f_hi:g} Hz: MEASURED {measured:.4g} frequencies/s at {n_dof} DOF. "
+              f"PARDISO stand-in), rigid shoebox 3.0x4.0x2.5 m, frequencies drawn from {f_lo:g}-{f_hi:g} Hz, MEASURED at {pts}. "
               f"A 1M-DOF sparse LU does not fit this host's RAM, so the reference's direct solve cannot run the workload at all")
     if workload_dof:
-        sample += (f"; `value` is that measurement scaled LINEARLY in DOF to the {workload_dof}-DOF workload (x {scale:.5f}), an "
-                   f"extrapolation that favours the reference (sparse LU cost grows faster than linearly, ~N^2 in 3-D)")
-    return {"value": measured * scale, "measured_at_sample": measured, "seconds": total, "cores": cores, "N": n_dof, "sample": sample}
+        how = (f"fitted power law frequencies/s = {a:.4g} * DOF^-{p:.3f} over the measured sizes" if len(points) > 1
+               else "ONE measured size scaled linearly in DOF (favours the reference: sparse LU cost grows ~DOF^2 in 3-D)")
+        sample += f"; `value` is an EXTRAPOLATION to the {workload_dof}-DOF workload: {how}"
+    return {"value": value, "measured_at_sample": measured, "seconds": float(sum(q["seconds"] for q in points)), "cores": cores,
+            "N": points[0]["N"], "points": points, "fit": {"a": a, "p": p}, "sample": sample}

@@ -69,7 +69,7 @@ def test_volume_values_golden(gpu_lib, golden):
     # north star: assembled values within 1e-12 relative of the FP64 restatement
     assert _rel(H.data, Ho.data) < 1e-12 and _rel(Q.data, Qo.data) < 1e-12
     # against the reference's own arrays: float32 eps for Tet4 (complex64 storage), 1e-12 for Tet10
-    tol = 2.5e-7 if g.order == 1 else 1e-12
+    tol = 4e-7 if g.order == 1 else 1e-12   # float32 storage and accumulation in the reference (up to ~30 contributions per entry)
     assert _rel(H.data, g.H.data) < tol and _rel(Q.data, g.Q.data) < tol
     # element matrices before the scatter
     He, Qe = s.element_matrices()
@@ -175,7 +175,7 @@ def test_function_level_drop_ins(gpu_lib, golden):
         A = fn.assemble_surface_matrices(grid.elem_surf, grid.nos, areas, grid.domain_index_surf, g.group_ids, 1)
         with pytest.raises(ValueError):
             fn.assemble_volume_matrices(grid.elem_vol, grid.nos, fluid_c, fluid_rho, 2, grid.domain_index_vol, 0)
-        tol = 2.5e-7
+        tol = 4e-7
     else:
         H, Q = fn.assemble_Q_H_4_FAST_2order(grid.NumElemC, grid.NumNosC, grid.elem_vol, grid.nos, g.c0, g.rho0)
         A = fn.assemble_A10_3_FAST(grid.domain_index_surf, g.group_ids, grid.NumElemC, grid.NumNosC, grid.elem_surf,

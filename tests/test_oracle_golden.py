@@ -20,7 +20,7 @@ def test_oracle_assembly_matches_reference(golden):
     if g.order == 1:
         H, Q = O.assemble_tet4(g.grid.elem_vol, g.grid.nos, g.c0, g.rho0)
         assert g.H.dtype == np.complex64  # the reference rounds Tet4 H/Q to single precision
-        tol = 2.5e-7
+        tol = 4e-7   # float32 storage AND float32 accumulation of up to ~30 element contributions per entry (unstructured meshes)
     else:
         H, Q = O.assemble_tet10(g.grid.elem_vol, g.grid.nos, g.c0, g.rho0)
         assert g.H.dtype == np.float64
