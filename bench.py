@@ -282,6 +282,8 @@ def run_ours(args):
         obj._sys_key = None        # force mesh upload + pattern build + assembly + modal set-up (a fresh object has none of them)
         obj.pN_out = pN_out
         obj.compute(timeit=False, keep_pN=keep_pN)
+        if keep_pN:
+            obj.evaluate(R)        # the reference's flow: compute() leaves pN, evaluate() reads the receivers out of it
         # read back: Heron areas, receiver pressures, iteration counts, residuals (H, Q, A stay on the GPU until asked for)
         d2h_holder[0] = obj.areas.nbytes // 2 + obj.pR.nbytes + obj.iters.nbytes + obj.relres.nbytes + (obj.pN.nbytes if keep_pN else 0)
         st = obj.stats

@@ -298,6 +298,24 @@ class FEM3D:
                                   check_every=self.check_every, warm_start=self.warm_start, precond=precond, rhs_vecs=rhs_vecs,
                                   rhs_coef=None if rhs_coef is None else rhs_coef[:, owned], modal_delta=self.modal_delta)
         self.stats = stats
+        if precond == "modal" and stats.n_unconverged:
+            # Safety net: what the modal path handed back above tol (a mesh too coarse for its modes near the top of the sweep, an
+            # unlucky breakdown) is solved again with plain block-Jacobi, from scratch.
+            bad = np.flatnonzero(~(stats.relres <= self.tol))
+            ob = owned[bad]
+            pN2, pR2, st2 = sys.sweep(w[ob], mu[:, ob], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN, tol=self.tol,
+                                      max_iter=self.max_iter, batch=self.batch, check_every=max(self.check_every, 32),
+                                      warm_start=False, precond="block", rhs_vecs=rhs_vecs, rhs_coef=None if rhs_coef is None else rhs_coef[:, ob])
+            if keep_pN:
+                pN[bad] = pN2
+            if pR is not None:
+                pR[bad] = pR2
+            stats.iters[bad] += st2.iters
+            stats.relres[bad] = st2.relres
+            stats.n_unconverged = int(st2.n_unconverged)
+            stats.n_resolved_block = int(len(bad))
+            stats.seconds += st2.seconds
+            stats.n_kernels += st2.n_kernels
         if world > 1:
             pN = sharding.gather_rows(pN, owned, nf) if keep_pN else None
             pR = sharding.gather_rows(pR, owned, nf) if pR is not None else None
@@ -330,13 +348,17 @@ class FEM3D:
     def _mode_count_estimate(self, f):
         """Weyl's estimate of the number of room modes below ``f`` from the mesh's volume and boundary area (sizes the block
         of the subspace iteration; the solver widens the block by itself when this is short)."""
-        nos = np.asarray(self.nos, dtype=np.float64)
-        ev = np.asarray(self.elem_vol)[:, :4].astype(np.int64)
-        a = nos[ev[:, 1]] - nos[ev[:, 0]]
-        b = nos[ev[:, 2]] - nos[ev[:, 0]]
-        c = nos[ev[:, 3]] - nos[ev[:, 0]]
-        vol = float(np.abs(np.einsum("ij,ij->i", a, np.cross(b, c))).sum() / 6.0)
-        area = float(np.real(self.areas).sum()) if getattr(self, "areas", None) is not None and len(self.areas) else 6.0 * vol ** (2.0 / 3.0)
+        if getattr(self, "_room_size", None) is None or self._room_size[0] is not self.nos:
+            nos = np.asarray(self.nos, dtype=np.float64)
+            # bounding box x filling factor would do; the mesh volume is exact and one pass over the corner nodes
+            ev = np.asarray(self.elem_vol)[:, :4]
+            a = nos[ev[:, 1]] - nos[ev[:, 0]]
+            b = nos[ev[:, 2]] - nos[ev[:, 0]]
+            c = nos[ev[:, 3]] - nos[ev[:, 0]]
+            vol = float(np.abs(np.einsum("ij,ij->i", a, np.cross(b, c))).sum() / 6.0)
+            area = float(np.real(self.areas).sum()) if getattr(self, "areas", None) is not None and len(self.areas) else 6.0 * vol ** (2.0 / 3.0)
+            self._room_size = (self.nos, vol, area)
+        _, vol, area = self._room_size
         x = f / float(np.real(self.c0))
         return int(4.0 * np.pi / 3.0 * vol * x ** 3 + np.pi / 4.0 * area * x ** 2 + 1.5 * vol ** (1.0 / 3.0) * x) + 1
 

@@ -154,7 +154,7 @@ int fdb_sizeof_sweep_result(void);
  * fdb_modal_set takes modes computed elsewhere.  Either makes precond = 2 available to fdb_sweep.  V is [n_modes][n_nodes],
  * Q-orthonormal, eigenvalues ascending.  At most 1024 modes are kept.
  *   f_acc_hz   the modes below it must meet `tol` (0 = all of them); those between f_acc_hz and f_cut_hz may be 10 x coarser
- *   tol        relative residual ||H v - lambda Q v|| / (lambda ||Q v||) to aim for (0 = default 2e-2: what the sweep's coarse
+ *   tol        relative residual ||H v - lambda Q v|| / (lambda ||Q v||) to aim for (0 = default 4e-2: what the sweep's coarse
  *              correction needs; eigenvalues are then good to ~tol^2).  The polynomial mass approximation bounds what can be
  *              reached on coarse meshes; fdb_modal_info reports what was.
  *   n_modes_hint  expected number of modes below f_cut_hz (sizes the block; 0 = find out by widening) */

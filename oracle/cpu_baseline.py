@@ -8,8 +8,8 @@ host's cores a step solves several frequencies at once, one per worker process; 
 instead thread one factorisation.
 
 The 1M-DOF factorisation does not fit host memory (3-D fill), so the path is MEASURED on a ladder of smaller shoebox
-meshes of the same room (``measure_sizes``) and the throughput at the benchmark's size is an extrapolation of the
-fitted power law ``frequencies/s = a * DOF^-p`` - labelled as such wherever it is printed.
+meshes of the same room (``LADDER``) and the throughput at the benchmark's size is an extrapolation of the fitted power
+law ``seconds per factorise-and-solve = a * DOF^p`` - labelled as such wherever it is printed.
 """
 from __future__ import annotations
 
@@ -63,7 +63,7 @@ def measure(shape, steps, warmup, workers, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0,
                 times.append(dt)
     total = float(np.sum(times))
     return {"N": int(n_dof), "shape": list(shape), "frequencies_per_s": steps * workers / total, "seconds": total, "workers": int(workers),
-            "steps": int(steps)}
+            "steps": int(steps), "seconds_per_solve": total / steps}
 
 
 # the room of the benchmark (3.0 x 4.0 x 2.5 m) at growing resolution: 21 735, 47 250 and 94 424 DOF
@@ -71,12 +71,12 @@ LADDER = ((26, 34, 22), (34, 44, 29), (43, 57, 36))
 
 
 def fit_power_law(points):
-    """Least-squares fit of log(frequencies/s) = log a - p log N; returns (a, p)."""
+    """Least-squares fit of log(seconds per factorise-and-solve) = log a + p log N; returns (a, p)."""
     n = np.log([p["N"] for p in points])
-    y = np.log([p["frequencies_per_s"] for p in points])
+    y = np.log([p["seconds_per_solve"] for p in points])
     if len(points) == 1:
-        return float(np.exp(y[0]) * np.exp(n[0])), 1.0          # one size only: linear in DOF (favours the reference)
-    A = np.vstack([np.ones_like(n), -n]).T
+        return float(np.exp(y[0]) / np.exp(n[0])), 1.0          # one size only: linear in DOF (favours the reference)
+    A = np.vstack([np.ones_like(n), n]).T
     (la, p), *_ = np.linalg.lstsq(A, y, rcond=None)
     return float(np.exp(la)), float(p)
 
@@ -94,14 +94,16 @@ def run(steps, warmup, sizes=2, cores=None, f_lo=20.0, f_hi=500.0, src=(1.0, 1.0
         points.append(measure(shape, st, wu, workers, f_lo, f_hi, src, rcv, c0, rho0))
     a, p = fit_power_law(points)
     measured = points[0]["frequencies_per_s"]
-    value = a * float(workload_dof) ** (-p) if workload_dof else measured
+    # one factorisation per core, as on the smallest mesh - at the workload's size not even one fits in memory: favours the reference
+    value = cores / (a * float(workload_dof) ** p) if workload_dof else measured
     pts = "; ".join(f"{q['N']} DOF: {q['frequencies_per_s']:.4g} frequencies/s ({q['workers']} concurrent factorisations, "
                     f"{q['steps'] * q['workers']} frequencies in {q['seconds']:.1f} s)" for q in points)
     sample = (f"oracle port of the reference algorithm (FP64 assembly, then per frequency: build G, scipy SuperLU factorise + solve, "
               f"PARDISO stand-in), rigid shoebox 3.0x4.0x2.5 m, frequencies drawn from {f_lo:g}-{f_hi:g} Hz, MEASURED at {pts}. "
               f"A 1M-DOF sparse LU does not fit this host's RAM, so the reference's direct solve cannot run the workload at all")
     if workload_dof:
-        how = (f"fitted power law frequencies/s = {a:.4g} * DOF^-{p:.3f} over the measured sizes" if len(points) > 1
+        how = (f"{cores} cores / (fitted seconds per factorise-and-solve = {a:.4g} * DOF^{p:.3f} over the measured sizes), i.e. as if every "
+               f"core could hold a factorisation of that size (the larger measured meshes already cannot: fewer concurrent ones)" if len(points) > 1
                else "ONE measured size scaled linearly in DOF (favours the reference: sparse LU cost grows ~DOF^2 in 3-D)")
         sample += f"; `value` is an EXTRAPOLATION to the {workload_dof}-DOF workload: {how}"
     return {"value": value, "measured_at_sample": measured, "seconds": float(sum(q["seconds"] for q in points)), "cores": cores,
