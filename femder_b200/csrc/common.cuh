@@ -126,6 +126,7 @@ struct fdb_system {
     fdb::DevBuf<uint16_t> sell_lidx;   // [sell_entries]
     // block-Jacobi preconditioner: FP32 inverse of the tile's diagonal block of H (128 x 128, symmetric), per re-assembly
     fdb::DevBuf<float> blk_inv;        // [n_tiles][8256] packed lower triangles
+    fdb::DevBuf<uint16_t> blk_inv16;   // [n_tiles][128 x 128] the same blocks in bf16, as 8 x 8 core matrices (tensor-core operand, modal.cu)
     bool have_blk = false;
 
     // surface

@@ -250,6 +250,244 @@ k_modal_project(const double* __restrict__ r, const uint16_t* __restrict__ V, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6a of the modal path, fused with the projection: per 128-row tile
+//     r <- r - alpha q (FP64, stored)          z_bj = B_t r  (tcgen05: B_t = bf16 inverse of the tile's diagonal block)
+//     c += V_t^T r      (tcgen05, partial sums of the block's tiles in TMEM as in k_modal_project)
+// One pass over r, q and the tile's block inverse instead of k_update_bj's CUDA-core product (the dominant, issue-bound kernel
+// of round 1) plus a second read of r by the projection.  The residual tile's bf16 (hi, lo) image is the B operand of BOTH
+// products.  Everything arrives by bulk copies - [r | q] into two 32 KB buffers, B_t and the V chunks into a ring of 32 KB slots - and
+// the updated residual leaves by a bulk store out of the buffer it arrived in.
+// START: slot load - r as it stands (no q), only the columns flagged in sc.reset carry data.
+// ------------------------------------------------------------------------------------------------
+struct FusedSmem {
+    uint64_t s_full[kStages], s_empty[kStages];   // ring of B_t and V chunks: filled by the producer, consumed IN ORDER by the MMA thread
+    uint64_t rq_full[2], rq_empty[2];             // [r | q] tiles: consumed by the converter warps.  (A consumer that skipped phases of a
+                                                  // shared ring could not tell them apart by parity: each consumer has its own barriers.)
+    uint64_t b_full[2], b_empty[2];
+    uint64_t z_full[2], z_empty[2];
+    uint64_t done;
+    uint32_t tmem_base;
+    double2 alpha[16];
+    int act[16];
+};
+
+template <bool START, bool CPX>
+__global__ void __launch_bounds__(kModalThreads, 1)
+k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint16_t* __restrict__ binv16, float* __restrict__ z32,
+                const uint16_t* __restrict__ V, int n_chunks, int64_t n_rows, int64_t n_tiles, const Scalars* __restrict__ sc,
+                float* __restrict__ c_part) {
+    constexpr int F = CPX ? 8 : 16;
+    constexpr uint32_t kZCol = 32 * kModalMaxChunks;   // TMEM columns: [0, 256) projection accumulators, [256, 320) two z_bj accumulators
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;                                      // [kStages][32 KB]
+    unsigned char* rqbuf = smem_raw + (size_t)kStages * kChunkBytes;     // [2][32 KB]: r (16 KB) | q (16 KB)
+    unsigned char* bimg = rqbuf + 2 * (size_t)kChunkBytes;               // [2][8 KB]
+    FusedSmem* sm = reinterpret_cast<FusedSmem*>(bimg + 2 * 8192);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n_use, ksteps_last;
+    uint32_t bytes_last;
+    modal_shape(sc->modes_use, n_use, bytes_last, ksteps_last);
+    const uint32_t items = 1u + (uint32_t)n_use;   // ring items per tile: B_t, then the V chunks
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm->s_full[i], 1); mbar_init(&sm->s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm->rq_full[i], 1); mbar_init(&sm->rq_empty[i], 1);
+            mbar_init(&sm->b_full[i], 128); mbar_init(&sm->b_empty[i], 1);
+            mbar_init(&sm->z_full[i], 1); mbar_init(&sm->z_empty[i], 128);
+        }
+        mbar_init(&sm->done, 1);
+        mbar_fence_init();
+    }
+    if (tid < F) {
+        const bool a = START ? (sc->reset[tid] != 0) : (sc->active[tid] != 0);
+        double2 al = make_double2(0.0, 0.0);
+        if (!START && a) {
+            const double2 pq = sc->pq[tid];
+            if (pq.x != 0.0 || pq.y != 0.0) al = cdiv(sc->rho[tid], pq);
+        }
+        sm->act[tid] = a ? 1 : 0;
+        sm->alpha[tid] = al;
+    }
+    if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, ti = 0;
+            auto slot_for = [&](uint32_t i) { mbar_wait_bounded(&sm->s_empty[i % kStages], ((i / kStages) & 1u) ^ 1u); return (int)(i % kStages); };
+            auto load_rq = [&](int64_t t, uint32_t k) {   // [r | q] of tile t into buffer k & 1
+                const int bb = k & 1;
+                const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
+                mbar_wait_bounded(&sm->rq_empty[bb], ((k >> 1) & 1u) ^ 1u);
+                unsigned char* dst = rqbuf + (size_t)bb * kChunkBytes;
+                mbar_expect_tx(&sm->rq_full[bb], rows * 128u * (START ? 1u : 2u));
+                bulk_g2s(dst, r + t * 128 * 16, rows * 128u, &sm->rq_full[bb]);
+                if (!START) bulk_g2s(dst + 16384, q + t * 128 * 16, rows * 128u, &sm->rq_full[bb]);
+            };
+            if ((int64_t)blockIdx.x < n_tiles) load_rq(blockIdx.x, 0);
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+                if (t + gridDim.x < n_tiles) load_rq(t + gridDim.x, ti + 1);   // the next tile's vectors ahead of this tile's mode chunks
+                {   // B_t
+                    const int st = slot_for(it++);
+                    mbar_expect_tx(&sm->s_full[st], (uint32_t)kChunkBytes);
+                    bulk_g2s(ring + (size_t)st * kChunkBytes, binv16 + t * (kChunkBytes / 2), (uint32_t)kChunkBytes, &sm->s_full[st]);
+                }
+                for (int j = 0; j < n_use; ++j) {
+                    const int st = slot_for(it++);
+                    const uint32_t bytes = (j == n_use - 1) ? bytes_last : (uint32_t)kChunkBytes;
+                    mbar_expect_tx(&sm->s_full[st], bytes);
+                    bulk_g2s(ring + (size_t)st * kChunkBytes, V + ((int64_t)t * n_chunks + j) * (kChunkBytes / 2), bytes, &sm->s_full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_p = tc_idesc_bf16(128, 32, 1, 1);   // projection: A = V^T chunk (MN-major), B = residual image (MN-major)
+            constexpr uint32_t idesc_z = tc_idesc_bf16(128, 32, 0, 1);   // block product: A = B_t (K-major), same B
+            uint32_t ti = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+                const int bb = ti & 1;
+                const uint32_t it0 = ti * items;
+                mbar_wait_bounded(&sm->b_full[bb], (ti >> 1) & 1u);
+                const uint32_t b_addr = smem_u32(bimg + bb * 8192);
+                {   // z_bj = B_t r
+                    const uint32_t it = it0;
+                    const int st = it % kStages;
+                    mbar_wait_bounded(&sm->s_full[st], (it / kStages) & 1u);
+                    mbar_wait_bounded(&sm->z_empty[bb], ((ti >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        tc_mma_bf16(tmem + kZCol + 32 * bb, tc_desc(a_addr + ks * 2 * kSm, kSm, kSn), tc_desc(b_addr + ks * 256, 128, 2048), idesc_z, ks > 0);
+                    tc_commit(&sm->s_empty[st]);
+                    tc_commit(&sm->z_full[bb]);
+                }
+                for (int j = 0; j < n_use; ++j) {
+                    const uint32_t it = it0 + 1 + j;
+                    const int st = it % kStages;
+                    mbar_wait_bounded(&sm->s_full[st], (it / kStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        tc_mma_bf16(tmem + 32 * j, tc_desc(a_addr + ks * 2 * kSn, kSn, kSm), tc_desc(b_addr + ks * 256, 128, 2048), idesc_p, ti > 0 || ks > 0);
+                    tc_commit(&sm->s_empty[st]);
+                }
+                tc_commit(&sm->b_empty[bb]);
+            }
+            tc_commit(&sm->done);
+        }
+    } else {
+        const int i = tid - 64;            // node row of the tile this thread converts
+        const int qd = warp & 3;           // TMEM lanes this warp may read
+        const int zrow = qd * 32 + lane;   // ... = the row whose z_bj it stores
+        auto epilogue = [&](int64_t t, uint32_t ti) {
+            const int bb = ti & 1;
+            mbar_wait_bounded(&sm->z_full[bb], (ti >> 1) & 1u);
+            tc_fence_after();
+            float acc[32];
+            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + kZCol + 32 * bb, acc);
+            tc_fence_before();
+            mbar_arrive(&sm->z_empty[bb]);
+            const int64_t row = t * 128 + zrow;
+            if (row < n_rows) {
+                float4* zd = reinterpret_cast<float4*>(z32 + row * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    zd[k] = make_float4(acc[4 * k] + acc[16 + 4 * k], acc[4 * k + 1] + acc[17 + 4 * k], acc[4 * k + 2] + acc[18 + 4 * k],
+                                        acc[4 * k + 3] + acc[19 + 4 * k]);
+            }
+        };
+        uint32_t ti = 0;
+        int64_t t_prev = -1;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int bb = ti & 1;
+            const int64_t row = t * 128 + i;
+            const bool valid = row < n_rows;
+            mbar_wait_bounded(&sm->rq_full[bb], (ti >> 1) & 1u);
+            double* rs = reinterpret_cast<double*>(rqbuf + (size_t)bb * kChunkBytes) + i * 16;
+            const double* qs = rs + 2048;
+            double v[16];
+            // 16-byte chunks of the row, rotated by the row index: the 8 threads of a quarter-warp phase hit 8 different bank groups
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int ch = (jj + i) & 7;
+                double2 rv = make_double2(0.0, 0.0), qv = make_double2(0.0, 0.0);
+                if (valid) {
+                    rv = *reinterpret_cast<const double2*>(rs + 2 * ch);
+                    if (!START) qv = *reinterpret_cast<const double2*>(qs + 2 * ch);
+                }
+                double2 rn;
+                if constexpr (CPX) {
+                    const double2 al = sm->alpha[ch];
+                    rn = make_double2(rv.x - (al.x * qv.x - al.y * qv.y), rv.y - (al.x * qv.y + al.y * qv.x));
+                } else {
+                    rn = make_double2(rv.x - sm->alpha[2 * ch].x * qv.x, rv.y - sm->alpha[2 * ch + 1].x * qv.y);
+                }
+                if (!START && valid) *reinterpret_cast<double2*>(rs + 2 * ch) = rn;
+                const bool a0 = sm->act[CPX ? ch : 2 * ch] != 0, a1 = sm->act[CPX ? ch : 2 * ch + 1] != 0;
+                // registers are indexed statically: select the chunk's place with predicated moves
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c == ch) { v[2 * c] = a0 ? rn.x : 0.0; v[2 * c + 1] = a1 ? rn.y : 0.0; }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t h0, l0, h1, l1;
+                bf16_split((float)v[2 * k], h0, l0);
+                bf16_split((float)v[2 * k + 1], h1, l1);
+                hi[k] = h0 | (h1 << 16);
+                lo[k] = l0 | (l1 << 16);
+            }
+            mbar_wait_bounded(&sm->b_empty[bb], ((ti >> 1) & 1u) ^ 1u);
+            unsigned char* img = bimg + bb * 8192 + i * 16;
+            *reinterpret_cast<uint4*>(img) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(img + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(img + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(img + 6144) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            fence_proxy_async();
+            mbar_arrive(&sm->b_full[bb]);
+            // the updated residual leaves from the slot it arrived in; the slot goes back to the producer when the store has read it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (i == 0) {
+                if (!START) {
+                    const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
+                    bulk_s2g(r + t * 128 * 16, rqbuf + (size_t)bb * kChunkBytes, rows * 128u);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                mbar_arrive(&sm->rq_empty[bb]);
+            }
+            if (t_prev >= 0) epilogue(t_prev, ti - 1);
+            t_prev = t;
+        }
+        if (t_prev >= 0) epilogue(t_prev, ti - 1);
+        if (i == 0 && !START) bulk_wait<0>();
+        // ---- this block's partial projections ----
+        mbar_wait_bounded(&sm->done, 0);
+        tc_fence_after();
+        float* out = c_part + (int64_t)blockIdx.x * kModalMaxModes * 16;
+        for (int j = 0; j < n_use; ++j) {
+            float acc[32];
+            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + 32 * j, acc);
+            float4* o = reinterpret_cast<float4*>(out + (int64_t)(j * kMC + qd * 32 + lane) * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o[k] = make_float4(acc[4 * k] + acc[16 + 4 * k], acc[4 * k + 1] + acc[17 + 4 * k], acc[4 * k + 2] + acc[18 + 4 * k],
+                                   acc[4 * k + 3] + acc[19 + 4 * k]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // coefficients  e = d * c :  fixed-order sum of the block partials, d from lambda, w^2 and the modes' boundary damping;
 // written as the bf16 (hi, lo) MN-major operand image of the expansion: chunk j, column block cb, mode k at
 // j * 8192 + cb * 2048 + k * 16 (+ 2 bytes per column)
@@ -465,6 +703,7 @@ k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static size_t fused_smem() { return (size_t)(kStages + 2) * kChunkBytes + 2 * 8192 + sizeof(FusedSmem) + 64; }
 static size_t project_smem() { return (size_t)kStages * kChunkBytes + 2 * 8192 + sizeof(ModalSmem) + 64; }
 static size_t expand_smem() { return (size_t)kStages * kChunkBytes + (size_t)kModalMaxChunks * 8192 + sizeof(ModalSmem) + 64; }
 
@@ -479,6 +718,10 @@ void modal_prepare(fdb_system* sys, SweepWork* w) {
     FDB_REQUIRE(sys->device >= 0 && sys->device < 64, "device index out of range");
     if (!done[sys->device]) {
         FDB_CUDA(cudaFuncSetAttribute(k_modal_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)project_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem()));
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
@@ -499,6 +742,22 @@ int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz) {
 }
 
 // the three launches between K6a and K6b: c = V^T r, e = d c, z += V e (+ rho', ||r||^2, finalisation)
+// K6a of the modal path: residual update + block-Jacobi product + projection in one tensor-core kernel
+void modal_precond_fused(fdb_system* sys, SweepWork* w, bool start) {
+    FDB_REQUIRE(sys->blk_inv16.p != nullptr, "bf16 block inverses missing");
+    const int G = modal_grid(sys);
+    auto go = [&](auto kern) {
+        kern<<<G, kModalThreads, fused_smem(), sys->stream>>>((double*)w->r.p, (const double*)w->q.p, sys->blk_inv16.p, w->z32.p, sys->modal_v.p,
+                                                             sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
+    };
+    if (w->real) { if (start) go(k_precond_fused<true, false>); else go(k_precond_fused<false, false>); }
+    else { if (start) go(k_precond_fused<true, true>); else go(k_precond_fused<false, true>); }
+}
+int64_t modal_fused_bytes(fdb_system* sys, SweepWork* w, int modes_use) {
+    const int64_t vec = (int64_t)w->N * kModalCols;
+    return modal_bytes(sys, w, modes_use, 1) + 2 * 8 * vec /* q in, r out */ + 4 * vec /* z32 out */ + sys->n_tiles * (int64_t)kChunkBytes /* B_t */;
+}
+
 // parts: 1 = projection, 2 = coefficients, 4 = expansion (bench.py times them one at a time)
 void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts) {
     const int G = modal_grid(sys);

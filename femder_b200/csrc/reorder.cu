@@ -258,7 +258,8 @@ void build_sell(fdb_system* sys) {
 constexpr int kBlk = 128;
 constexpr int kBlkPacked = kBlk * (kBlk + 1) / 2;   // 8256 floats = 33 024 bytes per tile
 __global__ void __launch_bounds__(256) k_block_inverse(const int32_t* __restrict__ sell_off, const int32_t* __restrict__ sell_idx,
-                                                        const double2* __restrict__ sell_hq, int64_t n_rows, double shift, float* __restrict__ out) {
+                                                        const double2* __restrict__ sell_hq, int64_t n_rows, double shift, float* __restrict__ out,
+                                                        uint16_t* __restrict__ out16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* A = reinterpret_cast<double*>(smem_raw);          // [128][128]
     double* colk = A + kBlk * kBlk;                            // [128]
@@ -309,19 +310,30 @@ __global__ void __launch_bounds__(256) k_block_inverse(const int32_t* __restrict
         const int i = idx >> 7, j = idx & (kBlk - 1);
         if (j <= i) o[i * (i + 1) / 2 + j] = (float)(0.5 * (A[i * kBlk + j] + A[j * kBlk + i]));
     }
+    // the full (symmetric) block in bf16 for the tensor-core product of the modal path: 8 x 8 core matrices, entry (i, k) at byte
+    // (k / 8) * 2048 + (i / 8) * 128 + (i % 8) * 16 + (k % 8) * 2 - the layout of a tile of modes, rows = nodes, K = columns
+    uint16_t* o16 = out16 + (int64_t)blockIdx.x * (kBlk * kBlk);
+    for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
+        const int i = idx >> 7, k = idx & (kBlk - 1);
+        const float v = (float)(0.5 * (A[i * kBlk + k] + A[k * kBlk + i]));
+        uint32_t u = __float_as_uint(v);
+        u += 0x7fffu + ((u >> 16) & 1u);
+        o16[((k >> 3) * 2048 + (i >> 3) * 128 + (i & 7) * 16 + (k & 7) * 2) >> 1] = (uint16_t)(u >> 16);
+    }
 }
 
 void build_block_prec(fdb_system* sys) {
     if (sys->have_blk) return;
     FDB_REQUIRE(sys->have_order && sys->tile_rows == kBlk && sys->n_tiles > 0, "block-Jacobi needs the 128-row tiles of the internal order");
     sys->blk_inv.alloc((size_t)sys->n_tiles * kBlkPacked);
+    sys->blk_inv16.alloc((size_t)sys->n_tiles * kBlk * kBlk);
     const size_t smem = (size_t)(kBlk * kBlk + 2 * kBlk) * sizeof(double);
     FDB_CUDA(cudaFuncSetAttribute(k_block_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // H + shift Q with a small positive shift (w = 2 pi 50 Hz, far below a block's own eigenvalues): a tile that holds a whole
     // connected component (meshes of up to 128 nodes) has a singular H block, and H + shift Q is positive definite always
     const double shift = (2.0 * 3.14159265358979323846 * 50.0) * (2.0 * 3.14159265358979323846 * 50.0);
     k_block_inverse<<<(unsigned)sys->n_tiles, 256, smem, sys->stream>>>(sys->sell_off.p, sys->sell_idx.p, sys->sell_hq.p, sys->n_nodes,
-                                                                         shift, sys->blk_inv.p);
+                                                                         shift, sys->blk_inv.p, sys->blk_inv16.p);
     FDB_CUDA(cudaGetLastError());
     sys->have_blk = true;
 }

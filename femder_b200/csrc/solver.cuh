@@ -60,6 +60,7 @@ struct SweepWork {
     int graph_precond = 0;
     DevBuf<float> c_part;         // modal: per-block partial projections [grid][kModalMaxModes][16]
     DevBuf<uint16_t> e_img;       // modal: coefficients e = D V^T r as the bf16 (hi, lo) operand image of the expansion
+    bool fused_precond = true;    // modal: K6a + projection as one tensor-core kernel (k_precond_fused); false = k_update_bj + k_modal_project
     DevBuf<float> z32;            // [N][F] preconditioned residual of the block-Jacobi path
     bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
     int blob_dbg = 0;             // FDB_BLOB_DBG: timing experiments (1 no compute, 2 no x fill, 4 no matrix stream) - results are wrong
@@ -235,6 +236,8 @@ void modal_prepare(fdb_system* sys, SweepWork* w);
 int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz);
 void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts = 7);   // c = V^T r ; e = d c ; z += V e, rho', ||r||^2, finalisation
 int64_t modal_bytes(fdb_system* sys, SweepWork* w, int modes_use, int part);
+void modal_precond_fused(fdb_system* sys, SweepWork* w, bool start);   // r -= alpha q ; z = B r ; c = V^T r  (one tcgen05 kernel)
+int64_t modal_fused_bytes(fdb_system* sys, SweepWork* w, int modes_use);
 void modal_build_adiag(fdb_system* sys);
 void modal_set(fdb_system* sys, int n_modes, const double* lam, const double* V);
 void modal_get(fdb_system* sys, double* lam, double* V);

@@ -1481,8 +1481,13 @@ struct Launch {
     template <typename T>
     static void iteration_t(fdb_system* sys, SweepWork* w, bool overlay) {
         spmv(sys, w, w->p.p, w->q.p, true, overlay);
-        vec_kernel_t<T>(sys, w, overlay, 1);
-        if (w->precond == 2) modal_apply(sys, w, overlay, false);
+        if (w->precond == 2 && w->fused_precond) {
+            modal_precond_fused(sys, w, false);          // K6a + projection on the tensor cores
+            modal_apply(sys, w, overlay, false, 2 | 4);  // coefficients, expansion + scalars
+        } else {
+            vec_kernel_t<T>(sys, w, overlay, 1);
+            if (w->precond == 2) modal_apply(sys, w, overlay, false);
+        }
         vec_kernel_t<T>(sys, w, overlay, 2);
     }
     static void iteration(fdb_system* sys, SweepWork* w, bool overlay) {
@@ -1520,8 +1525,15 @@ struct Launch {
             nk += 2;
         }
         bool started = false;
-        if (w->precond >= 1) started = bj_update<T>(sys, w, true);
-        if (started && w->precond == 2) { modal_apply(sys, w, overlay, true); nk += 3; }
+        if (w->precond == 2 && w->fused_precond) {
+            modal_precond_fused(sys, w, true);
+            modal_apply(sys, w, overlay, true, 2 | 4);
+            nk += 2;
+            started = true;
+        } else {
+            if (w->precond >= 1) started = bj_update<T>(sys, w, true);
+            if (started && w->precond == 2) { modal_apply(sys, w, overlay, true); nk += 3; }
+        }
         if (started) {
         } else if (overlay) {
             if constexpr (std::is_same<T, double2>::value)
@@ -1610,6 +1622,7 @@ static SweepWork* new_work(fdb_system* sys, int F) {
         if (const char* e = getenv("FDB_BLOB_LPR")) w->blob_lpr = atoi(e) == 4 ? 4 : 2;
         if (const char* e = getenv("FDB_BLOB_DBG")) w->blob_dbg = atoi(e);
         if (getenv("FDB_NO_ROWS_KERNEL")) w->rows_kernel = false;
+        if (getenv("FDB_NO_FUSED_PRECOND")) w->fused_precond = false;   // A/B: k_update_bj + k_modal_project instead of k_precond_fused
 #endif
         const size_t n = (size_t)w->N * F;
         w->x.alloc(n); w->r.alloc(n); w->p.alloc(n); w->q.alloc(n); w->dinv.alloc(n); w->tmp.alloc(n);
@@ -1983,7 +1996,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         }
         FDB_CUDA(cudaGraphLaunch(w->graph, s));
         n_spmv += check_every;
-        n_kernels += (use_modal ? 6 : 3) * (int64_t)check_every;
+        n_kernels += (use_modal ? (w->fused_precond ? 5 : 6) : 3) * (int64_t)check_every;
         FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         FDB_CUDA(cudaStreamSynchronize(s));
         FDB_CUDA(cudaGetLastError());
@@ -2328,6 +2341,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
     }
     for (int i = 0; i < reps; ++i) {
         if (which == 0) { FDB_DISPATCH_F(F, spmv(sys, w, w->p.p, w->q.p, true, false)); }
+        else if (which == 1 && modal && w->fused_precond) modal_precond_fused(sys, w, false);
         else if (which == 3) modal_apply(sys, w, false, false, 1);
         else if (which == 4) modal_apply(sys, w, false, false, 4);
         else if (which == 5) modal_apply(sys, w, false, false, 2);
@@ -2336,6 +2350,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
     FDB_CUDA(cudaGetLastError());
     if (bytes) {
         if (which == 0) *bytes = spmv_algorithmic_bytes(sys, F, false, w->real);
+        else if (which == 1 && modal && w->fused_precond) *bytes = modal_fused_bytes(sys, w, modes_all);
         else if (which == 3) *bytes = modal_bytes(sys, w, modes_all, 1);
         else if (which == 4) *bytes = modal_bytes(sys, w, modes_all, 4);
         else if (which == 5) *bytes = modal_bytes(sys, w, modes_all, 2);
