@@ -9,10 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(OUT, exist_ok=True)
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
@@ -46,8 +46,9 @@ def launches():
         agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(OUT, f"{R}_launches.md"), "w") as f:
-        f.write(f"# {R}: kernel launch list of `bench.py --stride 15 --steps 1 --warmup 3 --no-e2e --no-cpu` (a step of 32 frequencies keeps the run under ncu short)\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 900` (cold-cache, serialised launches: compare SHARES).\n\n"
+        f.write(f"# {R}: kernel launch list of the sweep in `scripts/sweep_for_ncu.py` (33 frequencies of 20-500 Hz on the 1M-DOF mesh, modal path; "
+                "the NVTX range keeps the modal set-up's SpMVs out)\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include sweep/` (cold-cache, serialised launches: compare SHARES).\n\n"
                 "| kernel | launches | mean us | share of captured time |\n|---|---:|---:|---:|\n")
         for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"| `{n}` | {c} | {t / c / 1000:.1f} | {t / tot:.3f} |\n")
@@ -89,14 +90,14 @@ def to_bytes(v):
 launches()
 traffic = {}
 for name, kid, title in (("spmv_real16", "K5", "K5 fused multi-frequency SpMV k_spmv_blob, batch 16, real arithmetic (the variant the rigid benchmark sweep launches)"),
-                         ("update_bj_real16", "K6a", "K6a k_update_bj, batch 16 real: residual update + block-Jacobi z = B r out of shared memory + reductions"),
-                         ("pupdate_bj_real16", "K6b", "K6b k_pupdate_bj, batch 16 real: x += alpha p, p = z + beta p"),
-                         ("spmv_cpx8", None, "K5 fused multi-frequency SpMV, batch 8, complex arithmetic (admittance sweeps)")):
+                         ("precond_fused", "K6a", "K6a k_precond_fused, batch 16 real, 747 modes: r -= alpha q, z = B r (bf16 block inverse) and c = V^T r on tcgen05"),
+                         ("modal_expand", "K8c", "K8c k_modal_expand, batch 16 real, 747 modes: z += V e on tcgen05, rho' = r^T z, ||r||^2, iteration scalars"),
+                         ("pupdate_bj_real16", "K6b", "K6b k_pupdate_bj, batch 16 real: x += alpha p, p = z + beta p")):
     v = capture(name, title)
     if v and kid:
         traffic[kid] = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
 if traffic:
-    traffic["source"] = f"profiles/{R}_spmv_real16.md, {R}_update_bj_real16.md, {R}_pupdate_bj_real16.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    traffic["source"] = f"profiles/{R}_spmv_real16.md, {R}_precond_fused.md, {R}_modal_expand.md, {R}_pupdate_bj_real16.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     json.dump(traffic, open(os.path.join(OUT, "kernel_traffic.json"), "w"))
 for fn in ("bench_%s.json" % R,):
     src = os.path.join(GO, fn)
