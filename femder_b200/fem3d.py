@@ -225,8 +225,93 @@ class FEM3D:
         then = time.time()
         sys = self._system()
         N = self.NumNosC
-        new_mesh = self._ensure_volume(sys)
         q = np.zeros([N, 1], dtype=np.complex128)
+        group_ids, mu, rhs_vecs, rhs_coef = self._assemble(sys)
+
+        src_nodes, src_q = [], []
+        if self.S is not None:
+            for ii in range(len(self.S.coord)):
+                n = closest_node(self.nos, self.S.coord[ii, :])
+                q[n] = np.asarray(self.S.q[ii]).ravel()[0]
+                src_nodes.append(n)
+                src_q.append(complex(np.asarray(self.S.q[ii]).ravel()[0]))
+        self.q = csc_matrix(q)
+        if rhs_vecs is not None:
+            src_nodes, src_q = [], []   # FEM_3D.py:1341: b = -1j*w*Vn only
+
+        nf = len(self.freq)
+        w = np.asarray(self.w, dtype=np.float64)
+
+        rcv_nodes = rcv_w = None
+        if self.R is not None and not keep_pN:
+            rcv_nodes, rcv_w = sys.locate_points(np.atleast_2d(self.R.coord), 1e-3)   # batched on the GPU
+
+        self._sweep(sys, w, mu, src_nodes, src_q, rcv_nodes, rcv_w, keep_pN, rhs_vecs, rhs_coef)
+        self.t = time.time() - then
+        if timeit:
+            if self.t <= 60:
+                print(f"Time taken: {self.t} s")
+            else:
+                print(f"Time taken: {self.t / 60} min")
+
+    def compute_candidates(self, sources, receivers, timeit=False):
+        """The source / receiver candidate loop of the reference's optimizer (``FEM_3D.py:1633-1648``: per candidate pair
+        ``self.S, self.R = sC[i], rC[i]; self.compute(); self.pR = self.evaluate(self.R)``) as ONE sweep: every candidate's source
+        is a right-hand side of the same ``G(w)``, so the (candidate, frequency) systems fill the solver's batches together and the
+        matrices, block inverses and room modes are built once.  ``sources`` / ``receivers``: equally long lists of ``Source`` /
+        ``Receiver`` objects.  Returns the list of ``pR`` arrays, ``(n_freq, n_receivers_i)`` each - what the loop appends to
+        ``pOptim`` - and leaves them in ``self.pR_candidates``; ``self.S``, ``self.R``, ``self.pR`` end as after the loop's last pass."""
+        then = time.time()
+        if len(sources) != len(receivers) or len(sources) == 0:
+            raise ValueError("sources and receivers must be equally long, non-empty lists")
+        if self.BC is not None and len(self.v) > 0:
+            raise NotImplementedError("candidate batching covers the point-source branches (FEM_3D.py:1304-1319, 1348-1365)")
+        sys = self._system()
+        group_ids, mu, _, _ = self._assemble(sys)
+        w = np.asarray(self.w, dtype=np.float64)
+        nf = len(w)
+        sets, counts, coords = [], [], []
+        for S, R in zip(sources, receivers):
+            nodes = [closest_node(self.nos, c) for c in np.atleast_2d(S.coord)]
+            sets.append((nodes, [complex(np.asarray(v).ravel()[0]) for v in S.q]))
+            rc = np.atleast_2d(R.coord)
+            counts.append(len(rc))
+            coords.append(rc)
+        rcv_nodes, rcv_w = sys.locate_points(np.vstack(coords), 1e-3)
+        precond = self._prepare_preconditioner(sys, nf)
+        _, pR, stats = sys.sweep(w, mu, None, None, rcv_nodes, rcv_w, want_pN=False, tol=self.tol, max_iter=self.max_iter,
+                                 batch=self.batch if precond != "modal" else "auto", check_every=self.check_every, precond=precond,
+                                 src_sets=sets, modal_delta=self.modal_delta)
+        if precond == "modal" and stats.n_unconverged:
+            _, pB, sb = sys.sweep(w, mu, None, None, rcv_nodes, rcv_w, want_pN=False, tol=self.tol, max_iter=self.max_iter, batch=self.batch,
+                                  check_every=max(self.check_every, 32), precond="block", src_sets=sets)
+            bad = ~(stats.relres <= self.tol)
+            pR[bad] = pB[bad]
+            stats.relres[bad] = sb.relres[bad]
+            stats.iters[bad] += sb.iters[bad]
+            stats.n_unconverged = int((~(stats.relres <= self.tol)).sum())
+        self.stats = stats
+        self.iters, self.relres = stats.iters, stats.relres
+        self.n_unconverged = int((~(stats.relres <= self.tol)).sum())
+        if self.n_unconverged:
+            import warnings
+            warnings.warn(f"femder_b200: {self.n_unconverged} of {stats.relres.size} (candidate, frequency) systems did not reach "
+                          f"tol={self.tol:g} (worst relative residual {np.nanmax(stats.relres):.2e})", RuntimeWarning, stacklevel=2)
+        out, k = [], 0
+        for c in counts:
+            out.append(pR[len(out), :, k:k + c].copy())
+            k += c
+        self.pR_candidates = out
+        self.S, self.R, self.pR = sources[-1], receivers[-1], out[-1]
+        self.pN = None
+        self.t = time.time() - then
+        if timeit:
+            print(f"Time taken: {self.t} s")
+        return out
+
+    # ---- set-up shared by compute() and compute_candidates(): mesh, matrices, boundary conditions --------------
+    def _assemble(self, sys):
+        new_mesh = self._ensure_volume(sys)
 
         group_ids = np.sort([*self.mu]) if self.BC is not None else np.array([], dtype=np.int64)
         if self.BC is not None and len(self.v) == 0:
@@ -268,27 +353,15 @@ class FEM3D:
             wv = np.asarray(self.w, dtype=np.float64)
             rhs_coef = np.array([-1j * wv * np.asarray(self.v[k]).ravel()[:len(wv)] for k in vkeys])
 
-        src_nodes, src_q = [], []
-        if self.S is not None:
-            for ii in range(len(self.S.coord)):
-                n = closest_node(self.nos, self.S.coord[ii, :])
-                q[n] = np.asarray(self.S.q[ii]).ravel()[0]
-                src_nodes.append(n)
-                src_q.append(complex(np.asarray(self.S.q[ii]).ravel()[0]))
-        self.q = csc_matrix(q)
-        if rhs_vecs is not None:
-            src_nodes, src_q = [], []   # FEM_3D.py:1341: b = -1j*w*Vn only
-
         nf = len(self.freq)
-        w = np.asarray(self.w, dtype=np.float64)
         mu = np.zeros((len(group_ids), nf), dtype=np.complex128)
         for i, g in enumerate(group_ids):
             mu[i] = np.asarray(self.mu[g]).ravel()[:nf]
+        return group_ids, mu, rhs_vecs, rhs_coef
 
-        rcv_nodes = rcv_w = None
-        if self.R is not None and not keep_pN:
-            rcv_nodes, rcv_w = sys.locate_points(np.atleast_2d(self.R.coord), 1e-3)   # batched on the GPU
-
+    # ---- the sweep of compute(): preconditioner, frequency sharding, safety net, gather ---------------------------
+    def _sweep(self, sys, w, mu, src_nodes, src_q, rcv_nodes, rcv_w, keep_pN, rhs_vecs, rhs_coef):
+        nf = len(w)
         precond = self._prepare_preconditioner(sys, nf)
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
         owned = sharding.owned_frequencies(nf, 1, rank, world)
@@ -337,12 +410,6 @@ class FEM3D:
             warnings.warn(f"femder_b200: {len(bad)} of {nf} frequencies did not reach tol={self.tol:g} "
                           f"(worst relative residual {np.nanmax(np.asarray(self.relres)[bad]):.2e} at "
                           f"{fr[np.nanargmax(np.asarray(self.relres)[bad])]:g} Hz; first: {fr[:8]})", RuntimeWarning, stacklevel=2)
-        self.t = time.time() - then
-        if timeit:
-            if self.t <= 60:
-                print(f"Time taken: {self.t} s")
-            else:
-                print(f"Time taken: {self.t / 60} min")
 
     # ---- room modes (FEM_3D.py:1699-1768) and the preconditioner that uses them ----------------
     def _mode_count_estimate(self, f):

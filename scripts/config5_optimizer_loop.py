@@ -18,6 +18,8 @@ from femder_b200.mesh import scale_grid  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--geometries", type=int, default=64)
 ap.add_argument("--shape", default="26,34,22")
+ap.add_argument("--candidates", type=int, default=0, help="source / receiver candidate pairs per geometry (FEM_3D.py:1633-1648), batched as "
+                                                            "right-hand sides of one sweep with FEM3D.compute_candidates; 0 = one pair, compute()")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 dev = int(os.environ.get("LOCAL_RANK", "0"))
@@ -40,9 +42,17 @@ for gi in range(rank, a.geometries, world):
     if obj is not None:
         new._sys = obj._sys          # keep the device allocation; the new coordinates force re-assembly
     obj = new
-    obj.compute(timeit=False, keep_pN=False)
-    nfreq += len(AC.freq)
-    assert obj.stats.n_unconverged == 0
+    if a.candidates > 0:
+        crng = np.random.default_rng(gi)
+        lo, hi = grid.nos.min(axis=0) + 0.3, grid.nos.max(axis=0) - 0.3
+        sC = [fd.Source(coord=grid.nos[grid.closest_node(crng.uniform(lo, hi))], q=[1e-4]) for _ in range(a.candidates)]
+        rC = [fd.Receiver(coord=crng.uniform(lo, hi)) for _ in range(a.candidates)]
+        obj.compute_candidates(sC, rC)
+        nfreq += len(AC.freq) * a.candidates
+    else:
+        obj.compute(timeit=False, keep_pN=False)
+        nfreq += len(AC.freq)
+    assert obj.n_unconverged == 0
 dt = time.perf_counter() - t0
-print(f"rank {rank}/{world}: {a.geometries // world} geometries x {len(AC.freq)} frequencies in {dt:.2f} s = {nfreq / dt:.1f} frequencies/s "
-      f"(N = {base.NumNosC}), last receiver SPL at 100 Hz = {obj.spl[80, 0]:.2f} dB")
+print(f"rank {rank}/{world}: {a.geometries // world} geometries x {max(1, a.candidates)} candidates x {len(AC.freq)} frequencies in {dt:.2f} s = "
+      f"{nfreq / dt:.1f} systems/s (N = {base.NumNosC}), last receiver SPL at 100 Hz = {obj.spl[80, 0]:.2f} dB")

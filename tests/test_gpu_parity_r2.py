@@ -213,3 +213,71 @@ def test_eigenfrequency_matches_eigsh(gpu_lib):
     assert abs(F_n[1] - C0 / (2 * 4.0)) < 0.2       # mesh dispersion only
     G = obj.Vc.T @ (Q.real @ obj.Vc)
     assert np.abs(G - np.eye(12)).max() < 1e-8
+
+
+def test_compute_candidates_against_the_oracle(gpu_lib):
+    """The optimizer's source / receiver candidate loop (FEM_3D.py:1633-1648) as one multi-RHS sweep: every candidate's pR
+    against the oracle's compute() + evaluate() of that candidate alone."""
+    grid = fd.shoebox_tet4(10, 12, 8, jitter=0.2)
+    freq = np.array([35.0, 80.0, 125.0, 160.0, 200.0])
+    obj, S0, R0, AC, BC = _problem(grid, freq, rigid=range(2, 7), adm={7: 0.15})
+    srcs = [fd.Source(coord=grid.nos[grid.closest_node(c)], q=[qv]) for c, qv in
+            (([1.0, 1.0, 1.2], 1e-4), ([2.2, 0.7, 0.6], 2e-4), ([0.5, 3.2, 1.9], 1e-4))]
+    rcvs = [fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])]),
+            fd.Receiver(coord=[[1.93, 2.71, 1.33], list(grid.nos[grid.closest_node([0.4, 0.4, 0.4])])]),     # off-node + on-node
+            fd.Receiver(coord=[1.11, 1.77, 0.83])]
+    out = obj.compute_candidates(srcs, rcvs)
+    assert len(out) == 3 and [o.shape for o in out] == [(5, 1), (5, 2), (5, 1)] and obj.n_unconverged == 0
+    for S, R, pR in zip(srcs, rcvs, out):
+        r = O.compute(grid, freq, BC.mu, S.coord, S.q.ravel(), C0, RHO0)
+        ref = O.evaluate(grid.nos, grid.elem_vol, r["pN"], R.coord)
+        assert np.abs(pR - ref).max() / np.abs(ref).max() < 1e-6
+        assert np.abs(O.p2SPL(pR) - O.p2SPL(ref)).max() < 0.01
+    assert obj.pR is out[-1] and obj.S is srcs[-1]
+
+
+def test_config5_geometry_loop(gpu_lib):
+    """BASELINE config 5 in the small: perturbed geometries on ONE connectivity, re-assembly + sweep each on the same device
+    system (pattern, internal order and tile tables are reused; matrices, block inverses and room modes are rebuilt)."""
+    from femder_b200.mesh import scale_grid
+    base = fd.shoebox_tet4(12, 16, 10)
+    freq = np.array([40.0, 63.0, 100.0, 160.0, 200.0])
+    rng = np.random.default_rng(0)
+    prev = None
+    for fac in rng.uniform(0.95, 1.05, size=(3, 3)):
+        grid = scale_grid(base, fac)
+        obj, S, R, AC, BC = _problem(grid, freq, src=np.array([1.0, 1.0, 1.2]) * fac, rcv=np.array([2.0, 3.0, 1.25]) * fac)
+        if prev is not None:
+            obj._sys = prev._sys
+        obj.compute(timeit=False, keep_pN=False)
+        assert obj.stats.precond_used == "modal" and obj.n_unconverged == 0
+        r = O.compute(grid, freq, BC.mu, S.coord, S.q.ravel(), C0, RHO0)
+        ref = O.evaluate(grid.nos, grid.elem_vol, r["pN"], R.coord)
+        assert np.abs(O.p2SPL(obj.pR) - O.p2SPL(ref)).max() < 0.01
+        prev = obj
+
+
+def test_config2_full_size_tet10(gpu_lib):
+    """BASELINE config 2 at its size: ~21k-DOF Tet10 shoebox, normalized admittance 0.02 on one wall, 20-200 Hz at 1 Hz with all
+    defaults: every frequency converged on the true residual; the residual re-checked against the oracle's FP64 Tet10 matrices
+    and the solution against the oracle's direct solve at one frequency."""
+    grid = fd.to_tet10(fd.shoebox_tet4(13, 17, 11, jitter=0.1))
+    freq = np.arange(20.0, 201.0, 1.0)
+    obj, S, R, AC, BC = _problem(grid, freq, rigid=range(2, 7), adm={7: 0.02})
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        obj.compute(timeit=False)
+    assert obj.n_unconverged == 0 and obj.relres.max() <= 1e-8 and obj.pN.shape == (181, grid.NumNosC)
+    H, Q = O.assemble_tet10(grid.elem_vol, grid.nos, C0, RHO0)
+    A = O.assemble_surface(grid.elem_surf, grid.nos, grid.domain_index_surf, [7], 2)[0]
+    q = O.source_vector(grid.nos, S.coord, S.q.ravel())
+    Hr, Qr, Ar = H.tocsr(), Q.tocsr(), A.tocsr()
+    for i in (0, 90, 180):
+        w = 2 * np.pi * freq[i]
+        x = obj.pN[i]
+        r = -1j * w * q - (Hr @ x - w * w * (Qr @ x) + 1j * w * BC.mu[7][i] * (Ar @ x))
+        assert np.linalg.norm(r) / np.linalg.norm(w * q) <= 2e-8
+    w = 2 * np.pi * freq[120]
+    G = (H - w * w * Q + 1j * w * BC.mu[7][120] * A).tocsc().astype(np.complex128)
+    ref = splu(G).solve(-1j * w * q)
+    assert np.linalg.norm(obj.pN[120] - ref) / np.linalg.norm(ref) < 1e-6
