@@ -64,6 +64,7 @@ SIGNATURES = {
     "fdb_sizeof_sweep_params": (C.c_int, []),
     "fdb_sizeof_sweep_result": (C.c_int, []),
     "fdb_modal_compute": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int)]),
+    "fdb_modal_estimate": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_int)]),
     "fdb_modal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p, C.c_void_p]),
     "fdb_modal_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fdb_modal_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

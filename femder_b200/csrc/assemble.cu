@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(256) k_reduce_hq(const int32_t* __restrict__ c
 void assemble_volume(fdb_system* sys, double rho0, double c0) {
     FDB_REQUIRE(sys->have_pattern && sys->vol.n_elem > 0 && sys->vol.conn.p, "fdb_set_volume_mesh must be called first");
     FDB_REQUIRE(rho0 != 0.0 && c0 != 0.0, "rho0 and c0 must be non-zero");
+    sys->rho0 = rho0;   // kept for Weyl's mode-count estimate (modal.cu)
+    sys->c0 = c0;
     upload_constants();
     Pattern& P = sys->vol;
     const int nper = P.nper, n2 = nper * nper;

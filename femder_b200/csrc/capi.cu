@@ -81,6 +81,14 @@ int fdb_system_create(int device, void* stream, fdb_system** out) {
     cudaDeviceProp prop;
     FDB_CUDA(cudaGetDeviceProperties(&prop, device));
     FDB_REQUIRE(prop.major >= 10, "femder_b200 is built for sm_100a (Blackwell B200) only");
+    {   // keep freed device memory in the process (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     fdb_system* s = new fdb_system();
     s->device = device;
     s->num_sms = prop.multiProcessorCount;
@@ -367,6 +375,14 @@ int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_m
     FDB_API_BEGIN
     FDB_SYS_MUT(sys);
     fdb::modal_compute(sys, f_cut_hz, f_acc_hz, n_modes_hint, tol, max_outer, n_modes_found);
+    FDB_API_END
+}
+
+int fdb_modal_estimate(fdb_system* sys, double f_hz, int* n_modes) {
+    FDB_API_BEGIN
+    FDB_SYS(sys);
+    FDB_REQUIRE(n_modes != nullptr, "null argument");
+    *n_modes = fdb::modal_estimate(sys, f_hz);
     FDB_API_END
 }
 

@@ -44,15 +44,25 @@ struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
+    // Stream-ordered allocation out of the device's default memory pool (its release threshold is raised in fdb_system_create, so
+    // freed blocks stay with the process): a set-up that allocates and frees tens of gigabytes of temporaries per call - the modal
+    // set-up does - otherwise spends a noticeable part of its time mapping and unmapping device memory inside cudaMalloc / cudaFree.
+    // Semantics are those of cudaMalloc / cudaFree: the free waits for the device, the memory is usable on every stream at once.
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            cudaDeviceSynchronize();
+            cudaFreeAsync(p, (cudaStream_t)0);
+        }
         p = nullptr;
         n = 0;
     }
     void alloc(size_t count) {
         if (count == n && p) return;
         release();
-        if (count) FDB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (count) {
+            FDB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), (cudaStream_t)0));
+            FDB_CUDA(cudaStreamSynchronize((cudaStream_t)0));
+        }
         n = count;
     }
     void zero(cudaStream_t s) {
@@ -159,6 +169,7 @@ struct fdb_system {
     fdb::DevBuf<double> modal_x;       // FP64 modes [ceil(n_modes / 16)][n_nodes (internal order)][16], kept on request
     fdb::DevBuf<double> modal_adiag;   // [n_groups][n_modes] v_i^T A_g v_i (damping of mode i by group g), built on demand
     bool have_modes = false, have_adiag = false;
+    double rho0 = 0.0, c0 = 0.0;       // of the last fdb_assemble_volume (0: matrices given from outside)
     void* cublas = nullptr;            // cublasHandle_t / cusolverDnHandle_t of the modal set-up (dense Gram products, Rayleigh-Ritz)
     void* cusolver = nullptr;
     int modal_outer = 0, modal_block = 0, modal_order = 0;   // diagnostics of the last fdb_modal_compute: outer iterations, block width, mass order

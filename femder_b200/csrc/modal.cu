@@ -915,6 +915,10 @@ __global__ void __launch_bounds__(256) k_cheb_step_lumped(const double* __restri
         Ynew[i] = v;
     }
 }
+__global__ void __launch_bounds__(256) k_modal_dinv(const double2* __restrict__ diag_hq, double mass_scale, int64_t n, double* __restrict__ dinv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dinv[i] = 1.0 / (diag_hq[i].y * mass_scale);
+}
 __global__ void __launch_bounds__(256) k_modal_scale(double* __restrict__ x, double a, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
 }
@@ -999,7 +1003,7 @@ static void modal_residuals(fdb_system* sys, SweepWork* w, const double* X, cons
 }
 
 // upper bound of the spectrum of D^-1 H (Gershgorin) and the total-mass scale of D = mass_scale * diag(Q)
-static void modal_bounds(fdb_system* sys, double& mass_scale, double& b_up) {
+static void modal_bounds(fdb_system* sys, double& mass_scale, double& b_up, double* total_mass = nullptr) {
     const int64_t N = sys->n_nodes;
     cudaStream_t s = sys->stream;
     DevBuf<double> qrow;
@@ -1020,10 +1024,31 @@ static void modal_bounds(fdb_system* sys, double& mass_scale, double& b_up) {
     for (int64_t i = 0; i < N; ++i) { mass += h_qrow[i]; trq += h_diag[i].y; }
     FDB_REQUIRE(mass > 0.0 && trq > 0.0, "the mass matrix has no positive total mass");
     mass_scale = mass / trq;
+    if (total_mass) *total_mass = mass;
     double gersh;
     memcpy(&gersh, &h_g, sizeof(double));
     b_up = 1.01 * gersh / mass_scale;
     FDB_REQUIRE(b_up > 0.0 && std::isfinite(b_up), "could not bound the spectrum of D^-1 H");
+}
+
+// Weyl's estimate of the number of room modes below f: N(f) = 4 pi / 3 V (f / c)^3 + pi / 4 S (f / c)^2 + L / 8 (f / c), with the
+// room's volume from the total mass (1^T Q 1 = V / (rho c^2)), its surface from the boundary triangles' areas when they are on the
+// device (6 V^(2/3) otherwise) and the edge term from a cube of that volume.  0 when the matrices were given from outside (no c).
+int modal_estimate(fdb_system* sys, double f_hz) {
+    if (!(sys->c0 > 0.0) || !(sys->rho0 > 0.0) || !sys->have_hq) return 0;
+    double mass_scale, b_up, mass = 0.0;
+    modal_bounds(sys, mass_scale, b_up, &mass);
+    const double vol = mass * sys->rho0 * sys->c0 * sys->c0;
+    double area = 6.0 * std::pow(vol, 2.0 / 3.0);
+    if (sys->n_tri > 0 && sys->areas.p && sys->areas.n == (size_t)sys->n_tri) {
+        std::vector<double> a(sys->n_tri);
+        FDB_CUDA(cudaMemcpy(a.data(), sys->areas.p, a.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        double sa = 0.0;
+        for (double v : a) sa += v;
+        if (sa > 0.0) area = sa;
+    }
+    const double x = f_hz / sys->c0;
+    return (int)(4.0 * 3.14159265358979323846 / 3.0 * vol * x * x * x + 3.14159265358979323846 / 4.0 * area * x * x + 1.5 * std::cbrt(vol) * x) + 1;
 }
 
 // modal_x (FP64 batches) + modal_lam_host -> bf16 tiles, device eigenvalues, per-mode residuals of the consistent pencil
@@ -1129,6 +1154,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
 
     // block size: the caller's estimate of the mode count plus a guard band, in batches of 16 columns
     const int cap_cols = (int)std::min<int64_t>(kModalMaxModes + 128, std::max<int64_t>(16, (N / 3 / 16) * 16));
+    if (n_hint <= 0) n_hint = modal_estimate(sys, f_cut_hz);   // 0 if the room's size is unknown: start small and widen
     int nb = n_hint > 0 ? ((int)(1.12 * n_hint) + 24 + 15) / 16 * 16 : 64;
     nb = std::max(16, std::min(nb, cap_cols));
 
@@ -1142,7 +1168,10 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     DevBuf<int> dinfo;
     dinfo.alloc(1);
     const int fgrid = (int)std::min<int64_t>(grid_for(N * 16, 256), (int64_t)sys->num_sms * 8);
-    bool have_ritz = false;
+    bool have_ritz = false, fused_cheb = true;
+    DevBuf<double> dinv_mass;   // 1 / (mass_scale * Q_rr)
+    dinv_mass.alloc(N);
+    k_modal_dinv<<<grid_for(N, 256), 256, 0, s>>>(sys->diag_hq.p, mass_scale, N, dinv_mass.p);
     double a_low = lam_cut * 1.21;   // lower edge of the interval the filter damps (1.1 f_cut until the block's own upper edge is known)
     const size_t bsz = (size_t)N * 16;
     // u = Qt^-1 (H y) for one batch: order_t extra SpMVs with Q
@@ -1194,6 +1223,9 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
                 // one filter step: Ynew = c1 A Y + c2 Y + c3 Xold
                 auto step = [&](const double* y, const double* xold, double c1, double c2, double c3, double* out) {
                     if (order_t == 0) {
+                        // lumped mass: the whole step inside the SpMV's epilogue where the mesh's tiles allow it
+                        if (fused_cheb && modal_spmv_cheb(sys, w, y, xold, out, dinv_mass.p, c1, c2, c3)) return;
+                        fused_cheb = false;
                         modal_spmv(sys, w, y, T.p);
                         k_cheb_step_lumped<<<fgrid, 256, 0, s>>>(T.p, y, xold, sys->diag_hq.p, mass_scale, c1, c2, c3, (int64_t)bsz, out);
                     } else {
@@ -1278,7 +1310,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             // keeps a negative direction the correction knows nothing about).  The ones between f_acc and f_cut only ever see
             // lambda - w^2 > 0: whatever the block holds of them helps, none of them is needed.
             // ... but the block should have stopped collecting them: fewer modes between f_acc and f_cut cost the sweep iterations).
-            if (outer >= 2 && worst <= tol && wanted - prev_wanted <= std::max(1, wanted / 100)) { converged = true; break; }
+            if (outer >= 2 && worst <= tol && wanted - prev_wanted <= std::max(1, wanted / 20)) { converged = true; break; }
             // Once the subspace is in its asymptotic regime the mass approximation of the filter limits what it can reach: raise its
             // order when progress stalls, stop when the highest order stalls too (the residuals are reported; the sweep does not need
             // them small, see k_modal_coef).

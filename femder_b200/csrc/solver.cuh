@@ -32,6 +32,12 @@ struct __align__(16) Scalars {
     unsigned int ticket[4];
 };
 
+// Chebyshev-filter epilogue of k_spmv_blob (modal set-up): y[row] = c1 (G x)[row] d[row] + c2 x[row] + c3 xold[row]
+struct ChebEpilogue {
+    const double* d = nullptr;      // [n_rows] 1 / (lumped mass); nullptr = plain SpMV
+    const double* xold = nullptr;   // [n_rows][16] previous iterate (read by the owner of the row only; y may alias it)
+    double c1 = 0.0, c2 = 0.0, c3 = 0.0;
+};
 struct SweepWork {
     int F = 0;
     int64_t N = 0;
@@ -60,6 +66,7 @@ struct SweepWork {
     int graph_precond = 0;
     DevBuf<float> c_part;         // modal: per-block partial projections [grid][kModalMaxModes][16]
     DevBuf<uint16_t> e_img;       // modal: coefficients e = D V^T r as the bf16 (hi, lo) operand image of the expansion
+    ChebEpilogue cheb;            // modal set-up: the SpMV writes a Chebyshev filter step (see k_spmv_blob)
     bool fused_precond = true;    // modal: K6a + projection as one tensor-core kernel (k_precond_fused); false = k_update_bj + k_modal_project
     DevBuf<float> z32;            // [N][F] preconditioned residual of the block-Jacobi path
     bool rows_kernel = true;      // FDB_NO_ROWS_KERNEL: narrow real batches fall back to the older kernels (A/B aid)
@@ -242,11 +249,14 @@ void modal_build_adiag(fdb_system* sys);
 void modal_set(fdb_system* sys, int n_modes, const double* lam, const double* V);
 void modal_get(fdb_system* sys, double* lam, double* V);
 void modal_finish(fdb_system* sys, int n_modes);
+int modal_estimate(fdb_system* sys, double f_hz);
 void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint, double tol, int max_outer, int* n_found);
 // ---- sweep.cu: the fused SpMV on 16 real columns for the modal set-up (y = (H - w2 Q) x, one w2 for all columns) ----
 SweepWork* modal_spmv_begin(fdb_system* sys);
 void modal_spmv_w2(fdb_system* sys, SweepWork* w, double w2);
 void modal_spmv(fdb_system* sys, SweepWork* w, const double* x, double* y);
+bool modal_spmv_cheb(fdb_system* sys, SweepWork* w, const double* x, const double* xold, double* out, const double* dinv, double c1, double c2,
+                     double c3);
 void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const double* r, double* z);
 
 }  // namespace fdb

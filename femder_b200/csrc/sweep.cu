@@ -485,13 +485,18 @@ constexpr int kBlobHdr = 20;        // ints of a tile header (= kTileHdr of reor
 constexpr int blob_producers(int tile) { return tile / 32; }   // producer warps
 constexpr int blob_threads(int tile, int lpr) { return tile * lpr + blob_producers(tile) * 32; }
 
-template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE>
+// CHEB (modal set-up, modal.cu): instead of y = G x the epilogue writes one step of the Chebyshev filter recurrence,
+//     y[row] = c1 * (G x)[row] * cheb_d[row] + c2 * x[row] + c3 * cheb_xold[row]      (y may alias cheb_xold)
+// with the row's own x taken from the staged tile: the filter step costs one vector read more than the SpMV instead of a
+// second kernel with four vector passes.
+template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE, bool CHEB = false>
 __global__ void __launch_bounds__(blob_threads(TILE, LPR), TILE == 64 ? 2 : 1)
 k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
             const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_hdr,
             const int32_t* __restrict__ ov_ptr, const int2* __restrict__ ov_cg, const double* __restrict__ ov_val,
-            const double2* __restrict__ coef, const double* __restrict__ x, double* __restrict__ y, int64_t n_rows,
-            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial, int dbg) {
+            const double2* __restrict__ coef, const double* __restrict__ x, double* y, int64_t n_rows,
+            int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial, int dbg, ChebEpilogue cheb) {
+    static_assert(!(CHEB && (CPX || DOT || OVERLAY)), "the Chebyshev epilogue belongs to the real, dot-free SpMV of the modal set-up");
     constexpr int F = CPX ? 8 : 16;
     constexpr int kBlobTile = TILE;
     constexpr int NCONS = kBlobTile * LPR;            // consumer threads
@@ -634,8 +639,24 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                 }
             }
             if (valid) {
+                if constexpr (CHEB) {
+                    const double* xo = xb + (self0 + rin) * 16;
+                    const double sd = cheb.c1 * cheb.d[row];
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = make_double2(acc[j][0], acc[j][1]);
+                    for (int j = 0; j < NCH; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(xo + choff[j]);
+                        double2 o = make_double2(sd * acc[j][0] + cheb.c2 * v.x, sd * acc[j][1] + cheb.c2 * v.y);
+                        if (cheb.c3 != 0.0) {
+                            const double2 p = *reinterpret_cast<const double2*>(cheb.xold + row * 16 + choff[j]);
+                            o.x += cheb.c3 * p.x;
+                            o.y += cheb.c3 * p.y;
+                        }
+                        *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) *reinterpret_cast<double2*>(y + row * 16 + choff[j]) = make_double2(acc[j][0], acc[j][1]);
+                }
                 if (DOT) {
                     const double* xo = xb + (self0 + rin) * 16;
 #pragma unroll
@@ -1323,8 +1344,15 @@ struct Launch {
                 kern<<<grid, threads, smem, sys->stream>>>(sys->sell_lidx.p, sys->sell_hq.p, sys->tile_meta.p,
                                                              sys->tile_cols.p, sys->tile_hdr.p, sys->ov_ptr.p, sys->ov_cg.p, sys->ov_val.p,
                                                              w->coef.p, (const double*)x, (double*)y, w->N, sys->n_tiles,
-                                                             x_cap, se, w->sc.p, (double*)w->partial.p, w->blob_dbg);
+                                                             x_cap, se, w->sc.p, (double*)w->partial.p, w->blob_dbg, w->cheb);
             };
+            if constexpr (!CPX) {
+                if (w->cheb.d != nullptr) {   // modal set-up: one filter step instead of y = G x (128-row tiles, 2 lanes per row)
+                    if (tile != 128 || dot) return false;
+                    launch(k_spmv_blob<false, false, false, 2, 128, true>, blob_threads(128, 2));
+                    return true;
+                }
+            }
             auto pick = [&](auto lpr, auto tl) {
                 constexpr int L = decltype(lpr)::value, T = decltype(tl)::value;
                 constexpr int TH = blob_threads(T, L);
@@ -2170,6 +2198,15 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     res->n_unconverged = n_unconv;
     res->n_resumed = n_resumed;
     res->precond_used = w->precond;
+}
+
+// one Chebyshev filter step fused into the SpMV (false: this mesh's tiles do not run k_spmv_blob - use the separate kernels)
+bool modal_spmv_cheb(fdb_system* sys, SweepWork* w, const double* x, const double* xold, double* out, const double* dinv, double c1, double c2,
+                     double c3) {
+    w->cheb.d = dinv; w->cheb.xold = xold; w->cheb.c1 = c1; w->cheb.c2 = c2; w->cheb.c3 = c3;
+    const bool ok = Launch<kModalCols>::spmv_blob<false>(sys, w, x, out, false, false);
+    w->cheb = ChebEpilogue();
+    return ok;
 }
 
 // ---- the fused SpMV for the modal set-up (modal.cu): 16 real columns, one w2 for all of them ----

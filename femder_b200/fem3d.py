@@ -412,23 +412,6 @@ class FEM3D:
                           f"{fr[np.nanargmax(np.asarray(self.relres)[bad])]:g} Hz; first: {fr[:8]})", RuntimeWarning, stacklevel=2)
 
     # ---- room modes (FEM_3D.py:1699-1768) and the preconditioner that uses them ----------------
-    def _mode_count_estimate(self, f):
-        """Weyl's estimate of the number of room modes below ``f`` from the mesh's volume and boundary area (sizes the block
-        of the subspace iteration; the solver widens the block by itself when this is short)."""
-        if getattr(self, "_room_size", None) is None or self._room_size[0] is not self.nos:
-            nos = np.asarray(self.nos, dtype=np.float64)
-            # bounding box x filling factor would do; the mesh volume is exact and one pass over the corner nodes
-            ev = np.asarray(self.elem_vol)[:, :4]
-            a = nos[ev[:, 1]] - nos[ev[:, 0]]
-            b = nos[ev[:, 2]] - nos[ev[:, 0]]
-            c = nos[ev[:, 3]] - nos[ev[:, 0]]
-            vol = float(np.abs(np.einsum("ij,ij->i", a, np.cross(b, c))).sum() / 6.0)
-            area = float(np.real(self.areas).sum()) if getattr(self, "areas", None) is not None and len(self.areas) else 6.0 * vol ** (2.0 / 3.0)
-            self._room_size = (self.nos, vol, area)
-        _, vol, area = self._room_size
-        x = f / float(np.real(self.c0))
-        return int(4.0 * np.pi / 3.0 * vol * x ** 3 + np.pi / 4.0 * area * x ** 2 + 1.5 * vol ** (1.0 / 3.0) * x) + 1
-
     def _prepare_preconditioner(self, sys, nf):
         """Resolve ``precond="auto"`` and make sure the modes the modal correction needs are on the device."""
         precond = self.precond
@@ -441,13 +424,14 @@ class FEM3D:
         delta = float(self.modal_delta)
         f_cut = float(np.hypot(f_hi, delta))
         # at most ~1000 modes are kept: shrink the margin above the sweep, then the cut itself, until the estimate fits
-        while self._mode_count_estimate(f_cut) > 960 and f_cut > 1.02 * f_hi:
+        # (Weyl's estimate from the room's volume and boundary area, computed by the library from the assembled mass)
+        while sys.modal_estimate(f_cut) > 960 and f_cut > 1.02 * f_hi:
             f_cut = max(1.02 * f_hi, 0.97 * f_cut)
-        while self._mode_count_estimate(f_cut) > 960:
+        while sys.modal_estimate(f_cut) > 960:
             f_cut *= 0.97
         key = (f_cut,)
         if self._modes_key is None or self._modes_key[0] < f_cut:
-            sys.modal_compute(f_cut, n_hint=self._mode_count_estimate(f_cut), f_acc=min(f_hi, f_cut))
+            sys.modal_compute(f_cut, f_acc=min(f_hi, f_cut))
             self._modes_key = key
         return precond
 
@@ -464,10 +448,12 @@ class FEM3D:
         c0 = float(np.real(self.c0))
         # frequency below which Weyl's estimate predicts a few more than neigs modes
         f = 20.0
-        while self._mode_count_estimate(f) < neigs + 4:
+        for _ in range(200):
+            if sys.modal_estimate(f) >= neigs + 4:
+                break
             f *= 1.1
         for _ in range(8):
-            sys.modal_compute(f, n_hint=self._mode_count_estimate(f), tol=1e-4, max_outer=30)
+            sys.modal_compute(f, tol=1e-4, max_outer=30)
             self._modes_key = (f,)
             if sys.modal_count() >= neigs:
                 break

@@ -253,6 +253,12 @@ class System:
         check(self._lib.fdb_modal_compute(self._h, float(f_cut), float(f_acc), int(n_hint), float(tol), int(max_outer), C.byref(n)))
         return n.value
 
+    def modal_estimate(self, f):
+        """Weyl's estimate of the number of room modes below ``f`` Hz (0 if the room's size is unknown)."""
+        n = C.c_int(0)
+        check(self._lib.fdb_modal_estimate(self._h, float(f), C.byref(n)))
+        return n.value
+
     def modal_info(self):
         """dict(outer, block, mass_order, worst_residual, residuals) of the stored modes."""
         o, b, t, wr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0.0)

@@ -159,6 +159,9 @@ int fdb_sizeof_sweep_result(void);
  *              reached on coarse meshes; fdb_modal_info reports what was.
  *   n_modes_hint  expected number of modes below f_cut_hz (sizes the block; 0 = find out by widening) */
 int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found);
+/* Weyl's estimate of the number of room modes below f_hz from the assembled room's volume (total mass) and boundary area; 0 when the
+ * matrices were given from outside.  fdb_modal_compute uses it when n_modes_hint is 0. */
+int fdb_modal_estimate(fdb_system* sys, double f_hz, int* n_modes);
 /* Diagnostics of the stored modes: outer iterations / block width / order of the mass approximation of the last fdb_modal_compute,
  * its worst relative residual, and per mode ||H v - lambda Q v|| / ||Q v|| (what fdb_sweep bounds 1 / (lambda - w^2) with).  Any pointer may be NULL. */
 int fdb_modal_info(fdb_system* sys, int* outer_iterations, int* block_columns, int* mass_order, double* worst_residual, double* residuals /* [n_modes] */);
