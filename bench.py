@@ -204,9 +204,19 @@ def run_ours(args):
     rcv_nodes = np.array([[rcv_node] * 4], dtype=np.int32)
     rcv_w = np.array([[1.0, 0.0, 0.0, 0.0]])
 
+    lam_modes = sysm.modal_get(vectors=False)[0] if n_modes else None
+
     def my_share(f):
-        """Strong scaling: this rank's frequencies of the step (dealt singly round-robin: every rank gets the same mix)."""
-        return f[sharding.owned_frequencies(len(f), 1, rank, world)]
+        """Strong scaling: this rank's frequencies of the step, dealt one at a time - the ones next to a room resonance first (they
+        can take several times the usual iteration count), then by frequency - so every rank gets the same mix (what FEM3D does)."""
+        if world == 1:
+            return f
+        if lam_modes is None:
+            return f[sharding.owned_frequencies(len(f), 1, rank, world)]
+        w2 = (2 * np.pi * f) ** 2
+        k = np.clip(np.searchsorted(lam_modes, w2), 1, len(lam_modes) - 1)
+        near = np.minimum(np.abs(lam_modes[k] - w2), np.abs(lam_modes[k - 1] - w2)) / w2
+        return f[sharding.deal_by_cost(np.where(near < 1e-3, 10.0, 1.0) + f / f.max(), rank, world)]
 
     def step_resident(i):
         f = my_share(step_frequencies(i))

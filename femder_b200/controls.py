@@ -63,6 +63,11 @@ class BC:
         """Normal velocity on a surface group (``BoundaryConditions.py:98-116``): fills ``v`` only, never ``mu``."""
         self.v[domain_index] = np.ones_like(self.AC.freq) * velocity
 
+    def fluid(self, domain_index, cc, rhoc):
+        """Equivalent fluid in a VOLUME domain (``BoundaryConditions.py:140-160``): complex sound speed and density."""
+        self.rhoc[domain_index] = (np.ones_like(self.AC.freq, dtype=complex) * rhoc).ravel()
+        self.cc[domain_index] = (np.ones_like(self.AC.freq, dtype=complex) * cc).ravel()
+
     def impedance(self, domain_index, impedance):
         idx = domain_index if isinstance(domain_index, (list, tuple)) else [domain_index]
         for i in idx:

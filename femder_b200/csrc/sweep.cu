@@ -1946,15 +1946,35 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
     std::vector<int> slot_best_it(kMaxF, 0);
     std::vector<char> slot_gave_up(kMaxF, 0);
     constexpr int kMaxResumes = 8, kStallWindow = 96;
+    constexpr double kNearResonance = 1e-3;   // |lambda - w^2| / w^2 below which a system is dispatched ahead of the others
     std::vector<double2> rcv_host((size_t)F * std::max(1, n_rcv));
     int64_t next = 0;
     int n_busy = 0;
 
     // Frequencies are dispatched to the slots in descending order: the iteration count grows with frequency, and
     // starting the expensive systems first leaves the cheap ones for the tail where slots begin to idle.
+    // With the modal correction the iteration count no longer depends on the frequency - except next to a resonance, where the
+    // stored (approximate) mode cannot be deflated cleanly and a system may need several times the usual count: those go first,
+    // so the long ones never start when the queue is about to run dry.
     std::vector<int64_t> order(n_sys);
     for (int64_t i = 0; i < n_sys; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return omega[a % nf] > omega[b % nf]; });
+    std::vector<char> near_mode(nf, 0);
+    if (use_modal) {
+        const auto& lam = sys->modal_lam_host;
+        for (int64_t i = 0; i < nf; ++i) {
+            const double w2 = omega[i] * omega[i];
+            auto it = std::lower_bound(lam.begin(), lam.end(), w2);
+            double d = 1e300;
+            if (it != lam.end()) d = std::min(d, std::fabs(*it - w2));
+            if (it != lam.begin()) d = std::min(d, std::fabs(*(it - 1) - w2));
+            near_mode[i] = d < kNearResonance * w2;
+        }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        const int64_t fa = a % nf, fb = b % nf;
+        if (near_mode[fa] != near_mode[fb]) return near_mode[fa] > near_mode[fb];
+        return omega[fa] > omega[fb];
+    });
 
     auto assign = [&](int slot) {
         if (next >= n_sys) {

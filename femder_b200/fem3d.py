@@ -15,7 +15,12 @@ Differences from the reference, all deliberate:
   ``mu`` keys are paired with their own group instead of by position.
 * the velocity-BC branch (``FEM_3D.py:1320-1347``) is supported: ``b = -1j*w*sum_i v_i V_i 1`` (the reference's
   cumulative ``V[indx] = v`` assignment reduces to this because ``V_i`` only has columns on group i's nodes); as in
-  the reference, point sources are ignored in that branch.  Equivalent fluids (``1367-1421``) raise NotImplementedError.
+  the reference, point sources are ignored in that branch.
+* the equivalent-fluid branch (``FEM_3D.py:1367-1399``: complex ``rho(w), c(w)`` per volume domain, ``BC.fluid``) does not
+  re-assemble per frequency as the reference does: ``H, Q`` are assembled once for air, the fluid domains' own stiffness and
+  mass (``H_d, Q_d``) once more, and ``G(w) = H - w^2 Q + sum_d [(rho0/rho_d - 1) H_d - w^2 (rho0 c0^2 / (rho_d c_d^2) - 1) Q_d]
+  + 1j w sum_g mu_g A_g`` - the bracket rides in the SpMV's overlay with per-frequency complex coefficients.  ``obj.H, obj.Q``
+  are the air matrices (the reference leaves the last frequency's).
 """
 from __future__ import annotations
 
@@ -119,11 +124,18 @@ class FEM3D:
         self._H = self._Q = self._A = None
         self._assembled = False
         self._A_ready = False
+        # equivalent-fluid volume domains (FEM_3D.py:1203-1218): complex rho(w), c(w) per domain in BC.rhoc / BC.cc, air elsewhere
         self.rho = {}
         self.c = {}
         if BC is not None and (len(getattr(BC, "rhoc", {})) > 0 or len(getattr(BC, "cc", {})) > 0):
-            raise NotImplementedError("equivalent-fluid domains (BC.rhoc / BC.cc, FEM_3D.py:1367-1421) are outside "
-                                      "the B200 hot path")
+            if set(BC.rhoc) != set(BC.cc):
+                raise ValueError("BC.rhoc and BC.cc must name the same volume domains (BC.fluid sets both)")
+            for d in np.asarray(self.number_ID_vol).tolist():
+                if d not in BC.rhoc:
+                    self.rho[d] = np.ones_like(np.asarray(self.freq, dtype=np.float64)) * self.rho0
+                    self.c[d] = np.ones_like(np.asarray(self.freq, dtype=np.float64)) * self.c0
+            self.rho.update(BC.rhoc)
+            self.c.update(BC.cc)
         # solver controls (no counterpart in the reference, which uses a direct solver)
         self.tol = tol
         self.max_iter = max_iter
@@ -238,6 +250,11 @@ class FEM3D:
         self.q = csc_matrix(q)
         if rhs_vecs is not None:
             src_nodes, src_q = [], []   # FEM_3D.py:1341: b = -1j*w*Vn only
+        if len(self.rho) > 0:
+            if rhs_vecs is not None:
+                raise NotImplementedError("velocity boundary conditions together with equivalent-fluid domains (the reference's "
+                                          "fluid branch, FEM_3D.py:1367-1399, has no velocity term either)")
+            mu = self._fluid_overlay(sys, group_ids, mu)
 
         nf = len(self.freq)
         w = np.asarray(self.w, dtype=np.float64)
@@ -309,6 +326,39 @@ class FEM3D:
             print(f"Time taken: {self.t} s")
         return out
 
+    # ---- equivalent-fluid domains (FEM_3D.py:1367-1399) --------------------------------------------------------------
+    def _fluid_overlay(self, sys, group_ids, mu):
+        """Add the fluid domains' correction to the overlay the SpMV reads and return the admittance table extended by its
+        per-frequency coefficients.  The element matrices are those the volume assembly just left on the device (assembled with
+        rho0, c0): ``H_d, Q_d`` = their sum over domain d's elements."""
+        from scipy.sparse import csc_matrix as _csc
+        N = self.NumNosC
+        w = np.asarray(self.w, dtype=np.float64)
+        nf = len(w)
+        He, Qe = sys.element_matrices()                      # (nper, nper, E) as assembled for air
+        ev = np.asarray(self.elem_vol).astype(np.int64)
+        dom = np.asarray(self.domain_index_vol)
+        mats = list(sys.get_A(drop_zeros=(self.order == 2))) if len(group_ids) else []
+        rows_mu = [mu[i] for i in range(len(group_ids))]
+        rho0, c0 = complex(np.real(self.rho0)), complex(np.real(self.c0))
+        for d in sorted(self.BC.rhoc):
+            sel = np.flatnonzero(dom == d)
+            if len(sel) == 0:
+                continue
+            r = np.repeat(ev[sel][:, :, None], ev.shape[1], axis=2).ravel()
+            c = np.repeat(ev[sel][:, None, :], ev.shape[1], axis=1).ravel()
+            Hd = _csc((np.transpose(He[:, :, sel], (2, 0, 1)).ravel(), (r, c)), shape=(N, N))
+            Qd = _csc((np.transpose(Qe[:, :, sel], (2, 0, 1)).ravel(), (r, c)), shape=(N, N))
+            rho_d = np.asarray(self.rho[d], dtype=np.complex128).ravel()[:nf]
+            c_d = np.asarray(self.c[d], dtype=np.complex128).ravel()[:nf]
+            a_d = rho0 / rho_d - 1.0                               # multiplies H_d
+            b_d = rho0 * c0 ** 2 / (rho_d * c_d ** 2) - 1.0        # multiplies -w^2 Q_d
+            mats += [Hd, Qd]
+            # the overlay applies 1j * w * mu_g to group g
+            rows_mu += [a_d / (1j * w), 1j * w * b_d]
+        sys.set_surface_matrices(mats)
+        return np.array(rows_mu, dtype=np.complex128).reshape(len(mats), nf)
+
     # ---- set-up shared by compute() and compute_candidates(): mesh, matrices, boundary conditions --------------
     def _assemble(self, sys):
         new_mesh = self._ensure_volume(sys)
@@ -364,7 +414,16 @@ class FEM3D:
         nf = len(w)
         precond = self._prepare_preconditioner(sys, nf)
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
-        owned = sharding.owned_frequencies(nf, 1, rank, world)
+        if world > 1 and precond == "modal":
+            # iterations are flat in frequency with the modal correction, except next to a resonance (up to several times the usual
+            # count): deal those first so every rank gets its share of them, then the rest by frequency
+            lam, _ = sys.modal_get(vectors=False)
+            w2 = w * w
+            k = np.clip(np.searchsorted(lam, w2), 1, len(lam) - 1)
+            near = np.minimum(np.abs(lam[k] - w2), np.abs(lam[k - 1] - w2)) / w2
+            owned = sharding.deal_by_cost(np.where(near < 1e-3, 10.0, 1.0) + w / w.max(), rank, world)
+        else:
+            owned = sharding.owned_frequencies(nf, 1, rank, world)
         pN_out = self.pN_out if (keep_pN and self.pN_out is not None and world == 1) else None
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN, pN_out=pN_out,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch if precond != "modal" else "auto",

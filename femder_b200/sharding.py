@@ -21,6 +21,16 @@ def owned_frequencies(n_freq, batch, rank, world):
     return idx[idx < n_freq]
 
 
+def deal_by_cost(cost, rank, world):
+    """Indices (ascending) of the items rank ``rank`` takes when they are dealt one at a time in order of decreasing ``cost``:
+    every rank gets the same share of the expensive ones."""
+    cost = np.asarray(cost, dtype=np.float64)
+    if world <= 1:
+        return np.arange(len(cost), dtype=np.int64)
+    order = np.argsort(-cost, kind="stable")
+    return np.sort(order[rank::world]).astype(np.int64)
+
+
 def dist_info():
     """(rank, world, local_rank) from torch.distributed if initialised, else from the torchrun environment
     only when a process group exists; a plain single process is (0, 1, 0)."""

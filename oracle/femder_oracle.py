@@ -271,6 +271,92 @@ def compute(grid, freq, mu_by_group, src_coord, src_q, c0=343.0, rho0=1.21, comp
     return dict(H=H, Q=Q, A=A, q=q, pN=pN, group_ids=group_ids, V=V)
 
 
+# --------------------------------------------------------------------------------------------------
+# Equivalent-fluid branch: FEM_3D.py:1367-1421 with int_tetra_4gauss (773-805), assemble_Q_H_4_FAST_equifluid (353-374),
+# int_tri_impedance_3gauss (953-990) and assemble_A_3_FAST (525-539).  Per frequency H and Q are re-assembled with the
+# complex rho(w), c(w) of each element's volume domain.
+# --------------------------------------------------------------------------------------------------
+def tet4_fluid_geometry(elem_vol, nos, float32_shape=True):
+    """K_e = B^T B det / 6 and M_e = sum_g N N^T det / 24 per element (4, 4, E): H_e = K_e / rho, Q_e = M_e / (rho c^2).
+    ``float32_shape``: ``int_tetra_4gauss`` builds the shape-function vector ``Ni`` as complex64 (FEM_3D.py:800), so ``N N^T`` is
+    evaluated in single precision before it meets the complex128 material factor; False gives the FP64 restatement."""
+    det_ja, arg_stiff = tet4_precompute(elem_vol, nos)
+    ptx = np.array([GAUSS_A, GAUSS_B, GAUSS_B, GAUSS_B])
+    pty = np.array([GAUSS_B, GAUSS_A, GAUSS_B, GAUSS_B])
+    ptz = np.array([GAUSS_B, GAUSS_B, GAUSS_A, GAUSS_B])
+    Ng = np.stack([1 - ptx - pty - ptz, ptx, pty, ptz], axis=1)      # (gauss, node)
+    if float32_shape:
+        Ng32 = Ng.astype(np.float32)
+        S = np.zeros((4, 4), dtype=np.float64)
+        for gp in range(4):
+            S = S + np.outer(Ng32[gp], Ng32[gp]).astype(np.float64)   # each N N^T rounded to float32, summed after the cast
+        # (the reference adds weight * (1 / (rho c^2)) * (N N^T) * det per Gauss point in complex128: the float32 products are exact
+        #  inputs to that sum)
+    else:
+        S = np.einsum("ga,gb->ab", Ng, Ng)
+    return arg_stiff / 6.0, S[:, :, None] * det_ja / 24.0
+
+
+def assemble_fluid(elem_vol, nos, c_by_domain, rho_by_domain, domain_index_vol, fi, float32_shape=True):
+    """``assemble_Q_H_4_FAST_equifluid`` for frequency index ``fi``: H, Q csc complex128."""
+    Ke, Me = tet4_fluid_geometry(elem_vol, nos, float32_shape)
+    dom = np.asarray(domain_index_vol)
+    rho = np.array([complex(np.asarray(rho_by_domain[d]).ravel()[fi]) for d in dom])
+    c = np.array([complex(np.asarray(c_by_domain[d]).ravel()[fi]) for d in dom])
+    He = Ke * (1.0 / rho)[None, None, :]
+    Qe = Me * (1.0 / (rho * c ** 2))[None, None, :]
+    N = len(nos)
+    return scatter_csc(He, elem_vol, N), scatter_csc(Qe, elem_vol, N)
+
+
+def tri3_impedance_unit_matrix():
+    """``int_tri_impedance_3gauss`` without the area: sum over the 3 x 3 tensor rule of w_i w_j N N^T with
+    N = [qsi1, qsi2, 1 - qsi1 - qsi2] (FEM_3D.py:969-988)."""
+    ptx = np.array([1 / 6, 1 / 6, 2 / 3])
+    pty = np.array([1 / 6, 2 / 3, 1 / 6])
+    wt = np.array([1 / 6, 1 / 6, 1 / 6]) * 2
+    D = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            Ni = np.array([ptx[i], pty[j], 1 - ptx[i] - pty[j]])
+            D = D + wt[i] * wt[j] * np.outer(Ni, Ni)
+    return D
+
+
+def assemble_surface_fluid_branch(elem_surf, nos, domain_index_surf, number_ID_faces):
+    """``assemble_A_3_FAST``: one csc per entry of ``number_ID_faces`` (in that order), built through a dense N x N scratch, so
+    exact zeros are dropped."""
+    f = np.asarray(elem_surf, dtype=np.int64)
+    N = len(nos)
+    areas = heron_areas(nos, f)
+    D = tri3_impedance_unit_matrix()
+    out = []
+    for bl in number_ID_faces:
+        idx = np.argwhere(np.asarray(domain_index_surf) == bl).ravel()
+        A = scatter_csc(D[:, :, None] * areas[idx][None, None, :], f[idx], N)
+        A.eliminate_zeros()
+        out.append(A)
+    return out
+
+
+def compute_fluid(grid, freq, mu_by_group, c_by_domain, rho_by_domain, src_coord, src_q, float32_shape=True):
+    """The equivalent-fluid branch of ``FEM3D.compute()`` (FEM_3D.py:1367-1399, Tet4): returns dict(pN, A, q)."""
+    freq = np.asarray(freq, dtype=np.float64)
+    w = 2.0 * np.pi * freq
+    ids = np.asarray(grid.number_ID_faces)
+    A = assemble_surface_fluid_branch(grid.elem_surf, grid.nos, grid.domain_index_surf, ids)
+    q = source_vector(grid.nos, src_coord, src_q)
+    pN = np.empty((len(freq), len(grid.nos)), dtype=np.complex128)
+    for n in range(len(freq)):
+        H, Q = assemble_fluid(grid.elem_vol, grid.nos, c_by_domain, rho_by_domain, grid.domain_index_vol, n, float32_shape)
+        Ag = 0
+        for Ai, bl in zip(A, ids):
+            Ag = Ag + Ai * np.asarray(mu_by_group[bl]).ravel()[n]
+        G = (H + 1j * w[n] * Ag - (w[n] ** 2) * Q).tocsc().astype(np.complex128)
+        pN[n] = splu(G).solve(-1j * w[n] * q)
+    return dict(pN=pN, A=A, q=q)
+
+
 def tet4_interpolate(nos, elem_vol, coord, pN):
     """``coord_interpolation`` (FEM_3D.py:173-218): candidate tets contain the closest node; pick by the
     barycentric test of ``which_tetra`` (last hit wins); linear shape functions."""

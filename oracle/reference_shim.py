@@ -106,6 +106,7 @@ def load_reference(disable_jit=False):
         os.environ["NUMBA_DISABLE_JIT"] = "1"
     if not hasattr(np, "cfloat"):
         np.cfloat = np.complex128
+    np.sctypeDict.setdefault("cfloat", np.complex128)   # int_tetra_4gauss asks for dtype='cfloat' (FEM_3D.py:775-776): a NumPy 1 alias
     import numpy.matlib  # noqa: F401  (FEM_3D.py uses np.matlib.repmat without importing it)
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.ticker", "matplotlib.colors", "seaborn",
                  "plotly", "plotly.io", "plotly.graph_objs", "plotly.graph_objects", "plotly.figure_factory",
@@ -153,8 +154,9 @@ class PlainReceiver:
         self.coord = np.atleast_2d(np.asarray(coord, dtype=np.float64))
 
 
-def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, c0=343.0, rho0=1.21, v_by_group=None):
-    """Run the reference's own ``FEM3D.compute()`` + ``evaluate()`` on ``grid``.  Returns the FEM3D object."""
+def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, c0=343.0, rho0=1.21, v_by_group=None, fluid=None):
+    """Run the reference's own ``FEM3D.compute()`` + ``evaluate()`` on ``grid``.  Returns the FEM3D object.
+    ``fluid``: {volume domain: (cc, rhoc)} -> ``BC.fluid`` (the equivalent-fluid branch, FEM_3D.py:1367-1421)."""
     ref = load_reference()
     AP = ref.controlsair.AirProperties(c0=c0, rho0=rho0)
     AC = ref.controlsair.AlgControls(AP, freq_vec=np.asarray(freq, dtype=np.float64))
@@ -163,6 +165,8 @@ def run_reference_compute(grid, freq, mu_by_group, src_coord, src_q, rcv_coord, 
         BC.mu[g] = np.asarray(mu)
     for g, v in (v_by_group or {}).items():
         BC.v[g] = np.asarray(v)
+    for d, (cc, rhoc) in (fluid or {}).items():
+        BC.fluid(d, cc, rhoc)
     S = PlainSource(src_coord, src_q)
     R = PlainReceiver(rcv_coord)
     obj = ref.FEM_3D.FEM3D(grid, S, R, AP, AC, BC)

@@ -281,3 +281,36 @@ def test_config2_full_size_tet10(gpu_lib):
     G = (H - w * w * Q + 1j * w * BC.mu[7][120] * A).tocsc().astype(np.complex128)
     ref = splu(G).solve(-1j * w * q)
     assert np.linalg.norm(obj.pN[120] - ref) / np.linalg.norm(ref) < 1e-6
+
+
+def test_equivalent_fluid_branch(gpu_lib):
+    """The equivalent-fluid branch (FEM_3D.py:1367-1399, BC.fluid: complex c and rho in a volume domain) against the golden the
+    unmodified reference produced (tests/golden/make_golden_fluid.py; the reference evaluates the mass shape functions in
+    single precision, FEM_3D.py:800) and against the oracle's FP64 restatement."""
+    import os
+    from conftest import GOLDEN_DIR
+    from femder_b200.mesh import Grid
+    d = np.load(os.path.join(GOLDEN_DIR, "fluid", "tet4_fluid.npz"))
+    g = Grid(d["nos"], d["elem_vol"], d["elem_surf"], d["domain_index_surf"], domain_index_vol=d["domain_index_vol"])
+    freq = d["freq"]
+    AP = fd.AirProperties(c0=float(d["c0"]), rho0=float(d["rho0"]))
+    AC = fd.AlgControls(AP, freq_vec=freq)
+    BC = fd.BC(AC, AP)
+    for i, k in enumerate(d["group_ids"]):
+        BC.mu[int(k)] = d["mu"][i]
+    BC.fluid(int(d["fluid_domain"]), complex(d["cc"]), complex(d["rhoc"]))
+    S = fd.Source(coord=d["src"], q=d["src_q"])
+    R = fd.Receiver(coord=d["rcv"])
+    obj = fd.FEM3D(g, S, R, AP, AC, BC, tol=1e-10)
+    obj.compute(timeit=False)
+    assert obj.n_unconverged == 0 and set(obj.rho) == {1, 2}
+    nf = len(freq)
+    c = {1: np.ones(nf) * float(d["c0"]), 2: np.ones(nf, dtype=complex) * complex(d["cc"])}
+    rho = {1: np.ones(nf) * float(d["rho0"]), 2: np.ones(nf, dtype=complex) * complex(d["rhoc"])}
+    r64 = O.compute_fluid(g, freq, BC.mu, c, rho, d["src"], d["src_q"], float32_shape=False)
+    rel = np.linalg.norm(obj.pN - r64["pN"], axis=1) / np.linalg.norm(r64["pN"], axis=1)
+    assert rel.max() < 1e-6, rel
+    relg = np.linalg.norm(obj.pN - d["pN"], axis=1) / np.linalg.norm(d["pN"], axis=1)
+    assert relg.max() < 2e-5, relg
+    pR = obj.evaluate(R)
+    assert np.abs(O.p2SPL(pR) - O.p2SPL(d["pR"].reshape(pR.shape))).max() < 0.01

@@ -98,3 +98,17 @@ def test_gather_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_deal_by_cost_spreads_the_expensive_items():
+    from femder_b200 import sharding
+    cost = np.ones(37)
+    cost[[3, 11, 12, 30, 31, 36]] = 10.0
+    seen = []
+    for r in range(4):
+        idx = sharding.deal_by_cost(cost, r, 4)
+        assert np.all(np.diff(idx) > 0)
+        assert 1 <= (cost[idx] > 1).sum() <= 2          # 6 expensive items over 4 ranks
+        seen.extend(idx.tolist())
+    assert sorted(seen) == list(range(37))
+    assert np.array_equal(sharding.deal_by_cost(cost, 0, 1), np.arange(37))
