@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfemder_b200.so")
-SOURCES = ["pattern.cu", "assemble.cu", "reorder.cu", "sweep.cu", "modal.cu", "capi.cu"]
+SOURCES = ["pattern.cu", "assemble.cu", "reorder.cu", "sweep.cu", "modal.cu", "comm.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "solver.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "femder_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
     if verbose:
         for s, log in zip(todo, logs):
             print(f"==== {s}\n{log}")
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-lcublas", "-lcusolver"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-lcublas", "-lcusolver", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

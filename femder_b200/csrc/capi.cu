@@ -112,6 +112,8 @@ int fdb_system_destroy(fdb_system* sys) {
         fdb::free_sweep_work(sys->work);
         sys->work = nullptr;
         fdb::modal_free_handles(sys);
+        fdb::comm_destroy((fdb::RankComm*)sys->comm);
+        sys->comm = nullptr;
         if (sys->own_stream) cudaStreamDestroy(sys->stream);
         delete sys;
     }
@@ -375,6 +377,31 @@ int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_m
     FDB_API_BEGIN
     FDB_SYS_MUT(sys);
     fdb::modal_compute(sys, f_cut_hz, f_acc_hz, n_modes_hint, tol, max_outer, n_modes_found);
+    FDB_API_END
+}
+
+int fdb_comm_unique_id(char* out128) {
+    FDB_API_BEGIN
+    FDB_REQUIRE(out128 != nullptr, "null argument");
+    fdb::comm_unique_id(out128);
+    FDB_API_END
+}
+
+int fdb_comm_init(fdb_system* sys, const char* id128, int rank, int world) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    FDB_REQUIRE(id128 != nullptr, "null argument");
+    fdb::comm_destroy((fdb::RankComm*)sys->comm);
+    sys->comm = nullptr;
+    sys->comm = fdb::comm_create(id128, rank, world);
+    FDB_API_END
+}
+
+int fdb_comm_free(fdb_system* sys) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    fdb::comm_destroy((fdb::RankComm*)sys->comm);
+    sys->comm = nullptr;
     FDB_API_END
 }
 

@@ -172,6 +172,7 @@ struct fdb_system {
     double rho0 = 0.0, c0 = 0.0;       // of the last fdb_assemble_volume (0: matrices given from outside)
     void* cublas = nullptr;            // cublasHandle_t / cusolverDnHandle_t of the modal set-up (dense Gram products, Rayleigh-Ritz)
     void* cusolver = nullptr;
+    void* comm = nullptr;              // RankComm* (comm.cu): the ranks sharing the modal set-up; nullptr = this process alone
     int modal_outer = 0, modal_block = 0, modal_order = 0;   // diagnostics of the last fdb_modal_compute: outer iterations, block width, mass order
     double modal_resid = 0.0;               // ... worst relative residual of the kept pairs
 

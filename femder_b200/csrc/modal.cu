@@ -923,6 +923,24 @@ __global__ void __launch_bounds__(256) k_modal_scale(double* __restrict__ x, dou
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
 }
 // batch [row][16] <-> columns [16 b, 16 b + 16) of the big row-major matrix [row][nb]
+// two 16-column double panels <-> one 32-column single panel (rows stay 128 bytes: the filter's SpMV stages them unchanged)
+__global__ void __launch_bounds__(256) k_pair_to_f32(const double* __restrict__ xa, const double* __restrict__ xb, int64_t n_rows,
+                                                     float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i >> 5;
+        const int c = (int)(i & 31);
+        out[i] = (float)(c < 16 ? xa[row * 16 + c] : xb[row * 16 + c - 16]);
+    }
+}
+__global__ void __launch_bounds__(256) k_pair_from_f32(const float* __restrict__ in, int64_t n_rows, double* __restrict__ xa,
+                                                       double* __restrict__ xb) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i >> 5;
+        const int c = (int)(i & 31);
+        if (c < 16) xa[row * 16 + c] = (double)in[i]; else xb[row * 16 + c - 16] = (double)in[i];
+    }
+}
+
 __global__ void __launch_bounds__(256) k_modal_to_big(const double* __restrict__ Xb, int64_t n_rows, int nb, int b, double* __restrict__ big) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 16; i += (int64_t)gridDim.x * blockDim.x)
         big[(i >> 4) * nb + 16 * b + (i & 15)] = Xb[i];
@@ -968,8 +986,9 @@ __global__ void k_modal_symmetrize(double* __restrict__ A, int n) {
 static double modal_qscale(double b_up) { return b_up * 1e22; }
 
 // res[i] = ||H x_i - theta_i Q x_i||_2 / ||Q x_i||_2 (eigenvalue units) of the first n columns of the batches X
+// [bt0, bt1): the panels this rank measures (the others' entries of res stay 0 for the caller to sum over the ranks)
 static void modal_residuals(fdb_system* sys, SweepWork* w, const double* X, const std::vector<double>& theta, int n, double s_q,
-                            DevBuf<double>& HX, DevBuf<double>& QX, std::vector<double>& res) {
+                            DevBuf<double>& HX, DevBuf<double>& QX, std::vector<double>& res, int bt0 = 0, int bt1 = 1 << 30) {
     const int64_t N = sys->n_nodes;
     cudaStream_t s = sys->stream;
     const size_t bsz = (size_t)N * 16;
@@ -981,7 +1000,7 @@ static void modal_residuals(fdb_system* sys, SweepWork* w, const double* X, cons
     HX.alloc(bsz); QX.alloc(bsz);
     std::vector<double> hp((size_t)rgrid * 32), th16(16);
     res.assign(n, 0.0);
-    for (int bt = 0; 16 * bt < n; ++bt) {
+    for (int bt = bt0; bt < bt1 && 16 * bt < n; ++bt) {
         const double* xb = X + (size_t)bt * bsz;
         modal_spmv_w2(sys, w, 0.0);
         modal_spmv(sys, w, xb, HX.p);
@@ -1158,8 +1177,22 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     int nb = n_hint > 0 ? ((int)(1.12 * n_hint) + 24 + 15) / 16 * 16 : 64;
     nb = std::max(16, std::min(nb, cap_cols));
 
+    // several ranks sharing the set-up (fdb_comm_init): the block's panels are dealt to them in pairs (the single-precision filter
+    // takes two panels at once); a rank filters, multiplies, rotates and measures its own panels, the block itself is exchanged
+    RankComm* comm = (RankComm*)sys->comm;
+    const int c_rank = comm_rank(comm), c_world = comm_world(comm);
+    int own0 = 0, own1 = 0;                 // this rank's panels [own0, own1) of the current block
+    std::vector<size_t> own_offs;           // panel offsets of all ranks, in doubles of X
+    DevBuf<double> dres;
+    auto deal_panels = [&](int nbat_) {
+        const int pairs = (nbat_ + 1) / 2;
+        own_offs.assign(c_world + 1, 0);
+        for (int r = 0; r <= c_world; ++r) own_offs[r] = (size_t)std::min(nbat_, 2 * (int)((int64_t)pairs * r / c_world)) * (size_t)N * 16;
+        own0 = (int)(own_offs[c_rank] / ((size_t)N * 16));
+        own1 = (int)(own_offs[c_rank + 1] / ((size_t)N * 16));
+    };
     SweepWork* w = modal_spmv_begin(sys);
-    const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr;   // progress lines on stderr; changes nothing that is computed
+    const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr && c_rank == 0;   // progress lines on stderr; changes nothing that is computed
     std::vector<double> theta, res;
     int wanted = 0, wanted_prev = -1, outer = 0, order_t = 0;
     const int max_order = 4;
@@ -1169,6 +1202,17 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     dinfo.alloc(1);
     const int fgrid = (int)std::min<int64_t>(grid_for(N * 16, 256), (int64_t)sys->num_sms * 8);
     bool have_ritz = false, fused_cheb = true;
+    // The filter only has to ENRICH the block in the wanted directions - what comes out is measured by the Rayleigh-Ritz step and the
+    // residuals, both in double precision - so it starts on single-precision copies of the columns, 32 to the SpMV's 128-byte row
+    // instead of 16: half the passes.  Once the worst residual is below f32_until the filter runs in double precision: measured on the
+    // 1M-DOF room, modes finished by a single-precision filter meet the same residual test but cost the sweep a third more
+    // iterations (95 -> 129 mean); single precision for the first outer iterations only costs none.
+    const char* tune = getenv("FDB_TUNING");
+    const bool tuning = tune && tune[0] == '1';
+    bool use_f32 = !(tuning && getenv("FDB_MODAL_F64") && atoi(getenv("FDB_MODAL_F64")) != 0);
+    const double f32_until = (tuning && getenv("FDB_MODAL_F32_UNTIL")) ? atof(getenv("FDB_MODAL_F32_UNTIL")) : 1.0;
+    double worst_last = 1e300;   // the previous outer iteration's worst residual
+    const double growth = (tuning && getenv("FDB_MODAL_GROWTH")) ? atof(getenv("FDB_MODAL_GROWTH")) : 0.05;
     DevBuf<double> dinv_mass;   // 1 / (mass_scale * Q_rr)
     dinv_mass.alloc(N);
     k_modal_dinv<<<grid_for(N, 256), 256, 0, s>>>(sys->diag_hq.p, mass_scale, N, dinv_mass.p);
@@ -1187,6 +1231,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     };
     for (;;) {
         const int nbat = nb / 16;
+        deal_panels(nbat);
         if (!have_ritz) {
             X.alloc((size_t)nbat * bsz);
             k_modal_random<<<fgrid, 256, 0, s>>>(X.p, (int64_t)nbat * bsz, 12345u);
@@ -1216,7 +1261,30 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             const double a = a_low, b = b_up * (1.0 + order_t);
             const int deg = (int)std::max(12.0, std::min(160.0, std::ceil(3.0 * std::sqrt(b / a))));
             const double e = 0.5 * (b - a), c = 0.5 * (b + a);
-            for (int bt = 0; bt < nbat; ++bt) {
+            // two panels at once in single precision (see use_f32): T and Y hold the 32-column single-precision iterates
+            auto filter_pair_f32 = [&](int bt) -> bool {
+                double* xa = X.p + (size_t)bt * bsz;
+                double* xb2 = xa + bsz;
+                k_pair_to_f32<<<fgrid, 256, 0, s>>>(xa, xb2, N, (float*)T.p);
+                double sigma = e / (0.0 - c);
+                const double sigma1 = sigma;
+                modal_spmv_w2(sys, w, 0.0);
+                if (!modal_spmv_cheb(sys, w, T.p, nullptr, Y.p, dinv_mass.p, sigma1 / e, -c * sigma1 / e, 0.0, true)) return false;
+                double *px = T.p, *py = Y.p;
+                for (int i = 2; i <= deg; ++i) {
+                    const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+                    modal_spmv_cheb(sys, w, py, px, px, dinv_mass.p, 2.0 * sigma2 / e, -2.0 * sigma2 * c / e, -sigma * sigma2, true);
+                    std::swap(px, py);
+                    sigma = sigma2;
+                }
+                k_pair_from_f32<<<fgrid, 256, 0, s>>>((const float*)py, N, xa, xb2);
+                return true;
+            };
+            for (int bt = own0; bt < own1; ++bt) {
+                if (use_f32 && worst_last > f32_until && order_t == 0 && fused_cheb && bt + 1 < own1) {
+                    if (filter_pair_f32(bt)) { ++bt; continue; }
+                    use_f32 = false;
+                }
                 double* xb = X.p + (size_t)bt * bsz;
                 double sigma = e / (0.0 - c);
                 const double sigma1 = sigma;
@@ -1248,22 +1316,33 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             FDB_CUDA(cudaGetLastError());
             { const double t_b = tick(); t_ph[0] = t_b - t_a; t_a = t_b; }
             // ---- Rayleigh-Ritz on (H, Q) ----
+            comm_allgatherv(comm, X.p, own_offs, s);         // every rank needs the whole filtered block on the left of the Gram products
             for (int bt = 0; bt < nbat; ++bt) {
                 double* xb = X.p + (size_t)bt * bsz;
+                k_modal_to_big<<<fgrid, 256, 0, s>>>(xb, N, nb, bt, big_x.p);
+                if (bt < own0 || bt >= own1) continue;
                 modal_spmv_w2(sys, w, 0.0);
                 modal_spmv(sys, w, xb, Y.p);                 // H X
                 modal_spmv_w2(sys, w, -s_q);
                 modal_spmv(sys, w, xb, T.p);                 // s Q X
                 k_modal_scale<<<fgrid, 256, 0, s>>>(T.p, 1.0 / s_q, (int64_t)bsz);
-                k_modal_to_big<<<fgrid, 256, 0, s>>>(xb, N, nb, bt, big_x.p);
                 k_modal_to_big<<<fgrid, 256, 0, s>>>(Y.p, N, nb, bt, big_hx.p);
                 k_modal_to_big<<<fgrid, 256, 0, s>>>(T.p, N, nb, bt, big_qx.p);
             }
             FDB_CUDA(cudaGetLastError());
             const double one = 1.0, zero = 0.0;
-            // row-major [N][nb] = column-major (nb x N): Hs = X^T (H X), Qs = X^T (Q X)
-            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, (int)N, &one, big_x.p, nb, big_hx.p, nb, &zero, Hs.p, nb));
-            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, (int)N, &one, big_x.p, nb, big_qx.p, nb, &zero, Qs.p, nb));
+            // row-major [N][nb] = column-major (nb x N): Hs = X^T (H X), Qs = X^T (Q X) - this rank's columns of them
+            const int j0 = 16 * own0, jn = 16 * (own1 - own0);
+            if (jn > 0) {
+                FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, jn, (int)N, &one, big_x.p, nb, big_hx.p + j0, nb, &zero, Hs.p + (size_t)j0 * nb, nb));
+                FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nb, jn, (int)N, &one, big_x.p, nb, big_qx.p + j0, nb, &zero, Qs.p + (size_t)j0 * nb, nb));
+            }
+            if (c_world > 1) {
+                std::vector<size_t> so(c_world + 1);
+                for (int r = 0; r <= c_world; ++r) so[r] = own_offs[r] / ((size_t)N) * (size_t)nb;   // 16 columns per panel x nb rows
+                comm_allgatherv(comm, Hs.p, so, s);
+                comm_allgatherv(comm, Qs.p, so, s);
+            }
             { const double t_b = tick(); t_ph[1] = t_b - t_a; t_a = t_b; }
             k_modal_symmetrize<<<dim3((nb + 127) / 128, nb), 128, 0, s>>>(Hs.p, nb);
             k_modal_symmetrize<<<dim3((nb + 127) / 128, nb), 128, 0, s>>>(Qs.p, nb);
@@ -1271,21 +1350,32 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
                                           work.p, lwork, dinfo.p));
             int info = 0;
             theta.resize(nb);
+            // every rank solved the same small eigenproblem; rank 0's answer is the one all of them use (identical decisions below)
+            comm_bcast(comm, Hs.p, (size_t)nb * nb, 0, s);
+            comm_bcast(comm, W.p, (size_t)nb, 0, s);
             FDB_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
             FDB_CUDA(cudaMemcpyAsync(theta.data(), W.p, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
             FDB_CUDA(cudaStreamSynchronize(s));
             FDB_REQUIRE(info == 0, "the Rayleigh-Ritz eigenproblem of the modal set-up failed (the filtered block lost rank)");
             { const double t_b = tick(); t_ph[2] = t_b - t_a; t_a = t_b; }
             // X <- X Y (Ritz vectors, Q-orthonormal, ascending): (X Y)^T = Y^T X^T in the column-major view
-            FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, nb, (int)N, nb, &one, Hs.p, nb, big_x.p, nb, &zero, big_new.p, nb));
-            for (int bt = 0; bt < nbat; ++bt) k_modal_from_big<<<fgrid, 256, 0, s>>>(big_new.p, N, nb, bt, X.p + (size_t)bt * bsz);
+            if (jn > 0)
+                FDB_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, jn, (int)N, nb, &one, Hs.p + (size_t)j0 * nb, nb, big_x.p, nb, &zero, big_new.p + j0, nb));
+            for (int bt = own0; bt < own1; ++bt) k_modal_from_big<<<fgrid, 256, 0, s>>>(big_new.p, N, nb, bt, X.p + (size_t)bt * bsz);
             have_ritz = true;
             { const double t_b = tick(); t_ph[3] = t_b - t_a; t_a = t_b; }
             ++outer;
             wanted = (int)(std::upper_bound(theta.begin(), theta.end(), lam_cut) - theta.begin());
             if (wanted >= nb - 8 && nb < cap_cols) { grown = true; break; }   // the block holds no guard band: widen it
             // ---- residuals of the wanted pairs on the consistent pencil ----
-            modal_residuals(sys, w, X.p, theta, wanted, s_q, Y, T, res);
+            modal_residuals(sys, w, X.p, theta, wanted, s_q, Y, T, res, own0, own1);
+            if (c_world > 1 && wanted > 0) {
+                dres.alloc(wanted);
+                FDB_CUDA(cudaMemcpyAsync(dres.p, res.data(), wanted * sizeof(double), cudaMemcpyHostToDevice, s));
+                comm_allreduce_sum(comm, dres.p, wanted, s);
+                FDB_CUDA(cudaMemcpyAsync(res.data(), dres.p, wanted * sizeof(double), cudaMemcpyDeviceToHost, s));
+                FDB_CUDA(cudaStreamSynchronize(s));
+            }
             const double th_ref = (two_pi * 10.0) * (two_pi * 10.0);
             worst = 0.0;
             double worst_hi = 0.0;
@@ -1298,11 +1388,12 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             a_low = lam_cut * 1.1;
             if (verbose) {
                 t_ph[4] = tick() - t_a;
-                fprintf(stderr, "[fdb modal] outer %d: block %d, wanted %d, mass order %d, degree %d, worst rel residual %.3e (below f_acc) %.3e (above), top Ritz f %.1f Hz"
+                fprintf(stderr, "[fdb modal] outer %d: block %d, wanted %d, mass order %d, %s filter of degree %d, worst rel residual %.3e (below f_acc) %.3e (above), top Ritz f %.1f Hz"
                                 " | seconds: filter %.3f, H X / Q X + Gram %.3f, eigenproblem %.3f, rotation %.3f, residuals %.3f\n",
-                        outer, nb, wanted, order_t, deg, worst, worst_hi, std::sqrt(std::max(theta[nb - 1], 0.0)) / two_pi, t_ph[0], t_ph[1], t_ph[2],
+                        outer, nb, wanted, order_t, use_f32 ? "single-precision" : "double-precision", deg, worst, worst_hi, std::sqrt(std::max(theta[nb - 1], 0.0)) / two_pi, t_ph[0], t_ph[1], t_ph[2],
                         t_ph[3], t_ph[4]);
             }
+            worst_last = worst;
             const bool stable = wanted == wanted_prev;   // the set of modes below the cut has stopped changing
             const int prev_wanted = wanted_prev;
             wanted_prev = wanted;
@@ -1310,15 +1401,18 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             // keeps a negative direction the correction knows nothing about).  The ones between f_acc and f_cut only ever see
             // lambda - w^2 > 0: whatever the block holds of them helps, none of them is needed.
             // ... but the block should have stopped collecting them: fewer modes between f_acc and f_cut cost the sweep iterations).
-            if (outer >= 2 && worst <= tol && wanted - prev_wanted <= std::max(1, wanted / 20)) { converged = true; break; }
+            if (outer >= 2 && worst <= tol && wanted - prev_wanted <= std::max(1, (int)(wanted * growth))) { converged = true; break; }
             // Once the subspace is in its asymptotic regime the mass approximation of the filter limits what it can reach: raise its
             // order when progress stalls, stop when the highest order stalls too (the residuals are reported; the sweep does not need
             // them small, see k_modal_coef).
             if (stable && worst < 0.2 && worst > 0.5 * worst_prev) {
-                if (order_t < max_order) ++order_t; else { converged = true; break; }
+                if (use_f32) use_f32 = false;
+                else if (order_t < max_order) ++order_t;
+                else { converged = true; break; }
             }
             worst_prev = worst;
         }
+        comm_allgatherv(comm, X.p, own_offs, s);   // the rotated block: every rank keeps all of it (the modes, or the start of a wider block)
         if (!grown) break;
         // widen: keep the Ritz vectors, append random columns
         const int nb2 = std::min(cap_cols, std::max(nb + 64, (int)(nb * 1.6) / 16 * 16));

@@ -37,6 +37,7 @@ struct ChebEpilogue {
     const double* d = nullptr;      // [n_rows] 1 / (lumped mass); nullptr = plain SpMV
     const double* xold = nullptr;   // [n_rows][16] previous iterate (read by the owner of the row only; y may alias it)
     double c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    bool f32 = false;               // the vectors hold 32 single-precision columns per row (same 128 bytes)
 };
 struct SweepWork {
     int F = 0;
@@ -256,7 +257,18 @@ SweepWork* modal_spmv_begin(fdb_system* sys);
 void modal_spmv_w2(fdb_system* sys, SweepWork* w, double w2);
 void modal_spmv(fdb_system* sys, SweepWork* w, const double* x, double* y);
 bool modal_spmv_cheb(fdb_system* sys, SweepWork* w, const double* x, const double* xold, double* out, const double* dinv, double c1, double c2,
-                     double c3);
+                     double c3, bool f32 = false);
 void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const double* r, double* z);
+
+// ---- comm.cu: the ranks that share one modal set-up (NCCL, opened lazily) ----
+struct RankComm;
+void comm_unique_id(char* out128);
+RankComm* comm_create(const char* id128, int rank, int world);
+void comm_destroy(RankComm* c);
+int comm_rank(const RankComm* c);
+int comm_world(const RankComm* c);
+void comm_allgatherv(RankComm* c, double* buf, const std::vector<size_t>& offs, cudaStream_t s);   // in place; rank r holds [offs[r], offs[r+1])
+void comm_bcast(RankComm* c, double* buf, size_t n, int root, cudaStream_t s);
+void comm_allreduce_sum(RankComm* c, double* buf, size_t n, cudaStream_t s);
 
 }  // namespace fdb

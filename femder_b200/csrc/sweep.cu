@@ -489,7 +489,9 @@ constexpr int blob_threads(int tile, int lpr) { return tile * lpr + blob_produce
 //     y[row] = c1 * (G x)[row] * cheb_d[row] + c2 * x[row] + c3 * cheb_xold[row]      (y may alias cheb_xold)
 // with the row's own x taken from the staged tile: the filter step costs one vector read more than the SpMV instead of a
 // second kernel with four vector passes.
-template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE, bool CHEB = false>
+// F32 (with CHEB): the vectors are single precision, 32 columns to the same 128-byte row - one pass filters twice the columns
+// for the same bytes.  All columns share one shift (Scalars::w2[0]); the matrix entry is rounded to single once per entry.
+template <bool CPX, bool DOT, bool OVERLAY, int LPR, int TILE, bool CHEB = false, bool F32 = false>
 __global__ void __launch_bounds__(blob_threads(TILE, LPR), TILE == 64 ? 2 : 1)
 k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ sell_hq,
             const int4* __restrict__ tile_meta, const int32_t* __restrict__ tile_cols, const int32_t* __restrict__ tile_hdr,
@@ -497,6 +499,7 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             const double2* __restrict__ coef, const double* __restrict__ x, double* y, int64_t n_rows,
             int64_t n_tiles, int x_cap, int stage_entries, Scalars* __restrict__ sc, double* __restrict__ partial, int dbg, ChebEpilogue cheb) {
     static_assert(!(CHEB && (CPX || DOT || OVERLAY)), "the Chebyshev epilogue belongs to the real, dot-free SpMV of the modal set-up");
+    static_assert(!F32 || CHEB, "single-precision vectors: the modal filter only");
     constexpr int F = CPX ? 8 : 16;
     constexpr int kBlobTile = TILE;
     constexpr int NCONS = kBlobTile * LPR;            // consumer threads
@@ -604,13 +607,29 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
             const uint16_t* tlx = s_lx + (size_t)buf * stage_entries + o * 8 + (rin & 7);
             const double* xb = xs + (size_t)buf * x_cap * 16;
             double acc[NCH][2];
+            float accf[NCH][4];
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) acc[j][0] = acc[j][1] = 0.0;
+            for (int j = 0; j < NCH; ++j) {
+                acc[j][0] = acc[j][1] = 0.0;
+                accf[j][0] = accf[j][1] = accf[j][2] = accf[j][3] = 0.f;
+            }
 #pragma unroll 4
             for (int k = 0; k < width; ++k) {
                 const double2 m = thq[k * 8];
                 const int li = tlx[k * 8];
                 const double* xr = xb + li * 16;
+                if constexpr (F32) {
+                    const float g = (float)(m.x - w2v[0][0] * m.y);
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(xr + choff[j]);
+                        accf[j][0] = fmaf(g, v.x, accf[j][0]);
+                        accf[j][1] = fmaf(g, v.y, accf[j][1]);
+                        accf[j][2] = fmaf(g, v.z, accf[j][2]);
+                        accf[j][3] = fmaf(g, v.w, accf[j][3]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
@@ -639,7 +658,22 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                 }
             }
             if (valid) {
-                if constexpr (CHEB) {
+                if constexpr (F32) {
+                    // the same byte offsets as the double-precision rows: 128 bytes per row, 16 per chunk
+                    const double* xo = xb + (self0 + rin) * 16;
+                    const float sd = (float)(cheb.c1 * cheb.d[row]), c2 = (float)cheb.c2, c3 = (float)cheb.c3;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(xo + choff[j]);
+                        float4 o = make_float4(fmaf(sd, accf[j][0], c2 * v.x), fmaf(sd, accf[j][1], c2 * v.y), fmaf(sd, accf[j][2], c2 * v.z),
+                                               fmaf(sd, accf[j][3], c2 * v.w));
+                        if (cheb.c3 != 0.0) {
+                            const float4 p = *reinterpret_cast<const float4*>(cheb.xold + row * 16 + choff[j]);
+                            o.x = fmaf(c3, p.x, o.x); o.y = fmaf(c3, p.y, o.y); o.z = fmaf(c3, p.z, o.z); o.w = fmaf(c3, p.w, o.w);
+                        }
+                        *reinterpret_cast<float4*>(y + row * 16 + choff[j]) = o;
+                    }
+                } else if constexpr (CHEB) {
                     const double* xo = xb + (self0 + rin) * 16;
                     const double sd = cheb.c1 * cheb.d[row];
 #pragma unroll
@@ -1349,7 +1383,8 @@ struct Launch {
             if constexpr (!CPX) {
                 if (w->cheb.d != nullptr) {   // modal set-up: one filter step instead of y = G x (128-row tiles, 2 lanes per row)
                     if (tile != 128 || dot) return false;
-                    launch(k_spmv_blob<false, false, false, 2, 128, true>, blob_threads(128, 2));
+                    if (w->cheb.f32) launch(k_spmv_blob<false, false, false, 2, 128, true, true>, blob_threads(128, 2));
+                    else launch(k_spmv_blob<false, false, false, 2, 128, true>, blob_threads(128, 2));
                     return true;
                 }
             }
@@ -2221,9 +2256,10 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
 }
 
 // one Chebyshev filter step fused into the SpMV (false: this mesh's tiles do not run k_spmv_blob - use the separate kernels)
+// f32: x, xold and out hold 32 single-precision columns per row instead of 16 doubles (the same 128 bytes)
 bool modal_spmv_cheb(fdb_system* sys, SweepWork* w, const double* x, const double* xold, double* out, const double* dinv, double c1, double c2,
-                     double c3) {
-    w->cheb.d = dinv; w->cheb.xold = xold; w->cheb.c1 = c1; w->cheb.c2 = c2; w->cheb.c3 = c3;
+                     double c3, bool f32) {
+    w->cheb.d = dinv; w->cheb.xold = xold; w->cheb.c1 = c1; w->cheb.c2 = c2; w->cheb.c3 = c3; w->cheb.f32 = f32;
     const bool ok = Launch<kModalCols>::spmv_blob<false>(sys, w, x, out, false, false);
     w->cheb = ChebEpilogue();
     return ok;

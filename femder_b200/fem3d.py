@@ -490,6 +490,8 @@ class FEM3D:
             f_cut *= 0.97
         key = (f_cut,)
         if self._modes_key is None or self._modes_key[0] < f_cut:
+            if self.shard and sharding.dist_info()[1] > 1:
+                sharding.share_modal_setup(sys)      # the ranks split the set-up's columns (every rank computes the same key)
             sys.modal_compute(f_cut, f_acc=min(f_hi, f_cut))
             self._modes_key = key
         return precond

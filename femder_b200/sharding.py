@@ -43,6 +43,23 @@ def dist_info():
     return 0, 1, 0
 
 
+def share_modal_setup(system, group=None):
+    """Make the ranks of the process group one communicator of ``system``'s library (NCCL, created by the library itself from an id
+    rank 0 makes and torch.distributed hands round): ``System.modal_compute`` then deals the set-up's columns to the ranks.
+    The one exchange on the path - every rank needs the same room modes; the sweep that follows has no collective."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world <= 1 or system.comm_world == world:
+        return
+    box = [system.comm_unique_id() if rank == 0 else None]
+    kw = {}
+    if dist.get_backend(group) == "nccl":
+        kw["device"] = torch.device("cuda", system.device)
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group, **kw)
+    system.comm_init(box[0], rank, world)
+
+
 def gather_rows(local_rows, owned, n_freq, group=None):
     """All ranks contribute ``local_rows`` (len(owned), ...) and get back the full (n_freq, ...) array.
     Host-side gather of python objects: the payload is receiver pressures (small) or, on request, pN rows."""

@@ -61,6 +61,7 @@ class System:
         """``stream``: a ``cudaStream_t`` as int (e.g. ``torch.cuda.Stream().cuda_stream``); it must not be the
         legacy default stream because the sweep captures CUDA graphs on it.  ``None`` -> library-owned stream."""
         self._lib = _lib.load()
+        self.comm_world = 1
         self._h = C.c_void_p()
         check(self._lib.fdb_system_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = int(device)
@@ -258,6 +259,24 @@ class System:
         n = C.c_int(0)
         check(self._lib.fdb_modal_estimate(self._h, float(f), C.byref(n)))
         return n.value
+
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes identifying a new group of ranks (one rank creates it, all ranks pass it to :meth:`comm_init`)."""
+        buf = C.create_string_buffer(128)
+        check(_lib.load().fdb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        """Join the group of ranks that share this room's modal set-up (collective; NCCL).  ``modal_compute`` is then a collective call."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        check(self._lib.fdb_comm_init(self._h, C.create_string_buffer(bytes(unique_id), 128), int(rank), int(world)))
+        self.comm_world = int(world)
+
+    def comm_free(self):
+        check(self._lib.fdb_comm_free(self._h))
+        self.comm_world = 1
 
     def modal_info(self):
         """dict(outer, block, mass_order, worst_residual, residuals) of the stored modes."""

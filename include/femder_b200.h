@@ -159,6 +159,15 @@ int fdb_sizeof_sweep_result(void);
  *              reached on coarse meshes; fdb_modal_info reports what was.
  *   n_modes_hint  expected number of modes below f_cut_hz (sizes the block; 0 = find out by widening) */
 int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found);
+/* Several GPUs, one process each, sweeping shares of the same frequency list over the same room (the reference's frequency loop,
+ * femder/FEM_3D.py:1304-1319, has independent iterations): they all need the same modes, so they can share the work of finding them.
+ * One rank creates an id (fdb_comm_unique_id, 128 bytes) and hands it to the others by whatever means the host program has; every
+ * rank then calls fdb_comm_init on its own system (same mesh and matrices on all of them) and, collectively, fdb_modal_compute with
+ * the same arguments: the block's columns are dealt to the ranks and exchanged over NCCL (NVLink), every rank ends with all the
+ * modes.  NCCL (libnccl.so.2) is loaded on first use.  fdb_sweep itself never communicates. */
+int fdb_comm_unique_id(char* out128);
+int fdb_comm_init(fdb_system* sys, const char* id128, int rank, int world);
+int fdb_comm_free(fdb_system* sys);
 /* Weyl's estimate of the number of room modes below f_hz from the assembled room's volume (total mass) and boundary area; 0 when the
  * matrices were given from outside.  fdb_modal_compute uses it when n_modes_hint is 0. */
 int fdb_modal_estimate(fdb_system* sys, double f_hz, int* n_modes);
