@@ -153,6 +153,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     import femder_b200 as fd
+
+    import room_setup as rs  # noqa: E402
     from femder_b200 import _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -270,16 +272,16 @@ def run_ours(args):
     value = tot[0] / (ms * 1e-3)
 
     # ---- e2e: the user's call, FEM3D.compute(), from pinned HOST mesh buffers to host receiver pressures ----
-    AP = fd.AirProperties(c0=C0, rho0=RHO0)
-    S = fd.Source(coord=grid.nos[src_node], q=[1e-4])
-    R = fd.Receiver(coord=grid.nos[rcv_node])
+    AP = rs.AirProperties(c0=C0, rho0=RHO0)
+    S = rs.Source(coord=grid.nos[src_node], q=[1e-4])
+    R = rs.Receiver(coord=grid.nos[rcv_node])
     n_step = len(step_frequencies(0))
     h2d = nos.nbytes + ev.nbytes + es.nbytes + 4 * len(es) + 16 * n_step * (1 + len(group_ids))
     d2h_holder = [0]
 
     def make_obj(f, **kw):
-        AC = fd.AlgControls(AP, freq_vec=f)
-        BC = fd.BC(AC, AP)
+        AC = rs.AlgControls(AP, freq_vec=f)
+        BC = rs.BC(AC, AP)
         for g in group_ids:
             BC.rigid(int(g))
         return fd.FEM3D(grid, S, R, AP, AC, BC, device=local_rank, stream=stream.cuda_stream, tol=args.tol, max_iter=args.max_iter,
@@ -396,12 +398,12 @@ def run_ours(args):
     if rank == 0 and not args.no_e2e:
         g1 = fd.shoebox_tet4(26, 34, 22)
         f1 = np.arange(F_LO, F_HI + 1.0, 1.0)
-        AC1 = fd.AlgControls(AP, freq_vec=f1)
-        BC1 = fd.BC(AC1, AP)
+        AC1 = rs.AlgControls(AP, freq_vec=f1)
+        BC1 = rs.BC(AC1, AP)
         for g in group_ids:
             BC1.rigid(int(g))
-        S1 = fd.Source(coord=g1.nos[g1.closest_node(SRC)], q=[1e-4])
-        R1 = fd.Receiver(coord=g1.nos[g1.closest_node(RCV)])
+        S1 = rs.Source(coord=g1.nos[g1.closest_node(SRC)], q=[1e-4])
+        R1 = rs.Receiver(coord=g1.nos[g1.closest_node(RCV)])
         o1 = fd.FEM3D(g1, S1, R1, AP, AC1, BC1, device=local_rank, tol=args.tol, max_iter=args.max_iter, shard=False)
         o1.compute(timeit=False, keep_pN=False)      # warm-up (graphs, allocations)
         o1.H = None

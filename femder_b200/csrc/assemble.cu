@@ -432,7 +432,9 @@ void assemble_surface(fdb_system* sys) {
     }
     FDB_CUDA(cudaGetLastError());
     sys->have_A = true;
-    build_overlay(sys);
+    // the overlay is the sweep's copy of the boundary matrices in the volume pattern's internal order: nodes-only systems
+    // (fdb_set_nodes: areas and boundary matrices on their own) have neither
+    if (sys->have_order) build_overlay(sys);
 }
 
 // ------------------------------------------------------------------------------------------------

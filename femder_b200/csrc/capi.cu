@@ -147,6 +147,21 @@ int fdb_set_volume_mesh(fdb_system* sys, int64_t n_nodes, const double* nos, int
     FDB_API_END
 }
 
+int fdb_set_nodes(fdb_system* sys, int64_t n_nodes, const double* nos) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    FDB_REQUIRE(n_nodes > 0 && nos, "no nodes");
+    sys->n_nodes = n_nodes;
+    sys->nos.alloc((size_t)n_nodes * 3);
+    FDB_CUDA(cudaMemcpyAsync(sys->nos.p, nos, (size_t)n_nodes * 3 * sizeof(double), cudaMemcpyDefault, sys->stream));
+    FDB_CUDA(cudaStreamSynchronize(sys->stream));
+    // whatever volume pattern, matrices, order and modes the system held belonged to another mesh
+    sys->have_pattern = sys->have_hq = sys->have_order = sys->have_overlay = false;
+    sys->have_A = sys->have_surf_pattern = false;
+    sys->have_modes = sys->have_adiag = false;
+    FDB_API_END
+}
+
 int fdb_pattern_nnz(fdb_system* sys, int64_t* nnz) {
     FDB_API_BEGIN
     FDB_SYS(sys);

@@ -162,6 +162,15 @@ class System:
         self.set_pattern(Hr.indptr, Hr.indices)
         self.set_HQ_values(Hr.data, Qr.data)
 
+    def set_nodes(self, nos):
+        """Node coordinates only: enough for the surface routines (areas, boundary matrices) without a volume mesh."""
+        nos = _f64(nos)
+        if nos.ndim != 2 or nos.shape[1] != 3:
+            raise ValueError("nos must be (N, 3)")
+        check(self._lib.fdb_set_nodes(self._h, nos.shape[0], ptr(nos)))
+        self.n_nodes = int(nos.shape[0])
+        self.n_elem = 0
+
     def element_matrices(self):
         n2 = self.nper * self.nper
         He = np.empty((n2, self.n_elem), dtype=np.float64)

@@ -42,6 +42,10 @@ int fdb_synchronize(fdb_system* sys);
  * free) pattern scipy produces, symmetric, so CSR == CSC.  nper = 4 (Tet4) or 10 (Tet10, gmsh node order). */
 int fdb_set_volume_mesh(fdb_system* sys, int64_t n_nodes, const double* nos /* [n_nodes][3] */,
                         int64_t n_elem, int nper, const int32_t* conn /* [n_elem][nper] */);
+/* Node coordinates only, for the surface routines on their own (fdb_set_surface_mesh, fdb_heron_areas, fdb_assemble_surface:
+ * the reference's compute_areas / assemble_surface_matrices take vertices and faces, no volume mesh - femder/FEM_3D.py:722-744,
+ * 475-523).  Drops any volume pattern, matrices and modes the system held. */
+int fdb_set_nodes(fdb_system* sys, int64_t n_nodes, const double* nos /* [n_nodes][3] */);
 int fdb_pattern_nnz(fdb_system* sys, int64_t* nnz);
 int fdb_pattern_get(fdb_system* sys, int32_t* indptr /* [n_nodes+1] */, int32_t* indices /* [nnz] */);
 /* elem2nnz[e][a][b] = position in `indices` of entry (row conn[e][a], col conn[e][b]). */

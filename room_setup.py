@@ -1,9 +1,9 @@
-"""Problem-setup holders with the attribute names ``FEM3D`` reads (input contract only).
+"""Problem-setup holders for the benches, tests and scripts of this repository - NOT part of the product package.
 
-The reference's own ``AirProperties`` / ``AlgControls`` / ``BC`` / ``Source`` / ``Receiver`` objects
-(``femder/controlsair.py:6-24, 90-113``, ``BoundaryConditions.py:3-90``, ``sources.py``, ``receivers.py``) can be
-passed to :class:`femder_b200.FEM3D` unchanged - it only reads ``c0, rho0``, ``freq, w``, ``mu, v, rhoc, cc``,
-``coord, q``.  These minimal equivalents exist so the package is usable without the reference installed.
+``femder_b200.FEM3D`` takes the reference's own ``AirProperties`` / ``AlgControls`` / ``BC`` / ``Source`` / ``Receiver`` objects
+(``femder/controlsair.py:6-24, 90-113``, ``BoundaryConditions.py:3-160``, ``sources.py``, ``receivers.py``) unchanged: it only reads
+``c0, rho0``, ``freq, w``, ``mu, v, rhoc, cc``, ``coord, q``.  On a machine without the reference installed (the GPU box) these
+minimal stand-ins carry the same attributes.
 """
 from __future__ import annotations
 
@@ -11,27 +11,26 @@ import numpy as np
 
 
 class AirProperties:
+    """``c0, rho0`` as 0-d arrays like the reference's (``controlsair.py:7-24``); the rest is carried for completeness."""
+
     def __init__(self, c0=343.0, rho0=1.21, temperature=20.0, humid=50.0, p_atm=101325.0):
-        self.c0 = np.array(c0)
-        self.rho0 = np.array(rho0)
-        self.temperature = np.array(temperature, dtype=np.float32)
-        self.hr = np.array(humid, dtype=np.float32)
-        self.p_atm = np.array(p_atm, dtype=np.float32)
+        self.c0, self.rho0 = np.array(c0), np.array(rho0)
+        self.temperature, self.hr, self.p_atm = (np.array(v, dtype=np.float32) for v in (temperature, humid, p_atm))
 
 
 class AlgControls:
+    """The frequency list: ``freq`` (Hz), ``w = 2 pi freq``, ``k0 = w / c0`` (``controlsair.py:90-113``) - either an explicit
+    ``freq_vec`` or ``freq_init .. freq_end`` (inclusive) every ``freq_step``."""
+
     def __init__(self, AP, freq_init=100.0, freq_end=10000.0, freq_step=10, freq_vec=()):
-        freq_vec = np.array(freq_vec, dtype=np.float64)
         self.c0 = AP.c0
-        if freq_vec.size == 0:
-            self.freq_init = np.array(freq_init)
-            self.freq_end = np.array(freq_end)
-            self.freq_step = np.array(freq_step)
-            self.freq = np.arange(self.freq_init, self.freq_end + self.freq_step, self.freq_step)
+        explicit = np.array(freq_vec, dtype=np.float64)
+        if explicit.size:
+            self.freq = explicit
         else:
-            self.freq_init = np.array(freq_vec[0])
-            self.freq_end = np.array(freq_vec[-1])
-            self.freq = freq_vec
+            self.freq_step = np.array(freq_step)
+            self.freq = np.arange(freq_init, freq_end + freq_step, freq_step)
+        self.freq_init, self.freq_end = np.array(self.freq[0] if explicit.size else freq_init), np.array(self.freq[-1] if explicit.size else freq_end)
         self.w = 2.0 * np.pi * self.freq
         self.k0 = self.w / self.c0
         self.fcenter = self.freq

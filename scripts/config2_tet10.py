@@ -3,15 +3,16 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd
+import room_setup as rs  # noqa: E402
 grid = fd.to_tet10(fd.shoebox_tet4(13, 17, 11, jitter=0.1))
-AP = fd.AirProperties()
-AC = fd.AlgControls(AP, 20, 200, 1)
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties()
+AC = rs.AlgControls(AP, 20, 200, 1)
+BC = rs.BC(AC, AP)
 for t in range(2, 7):
     BC.rigid(t)
 BC.normalized_admittance(7, 0.02)
-S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
 obj = fd.FEM3D(grid, S, R, AP, AC, BC)
 obj.compute(timeit=False)
 obj.H = None

@@ -13,6 +13,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
+import room_setup as rs  # noqa: E402
 from femder_b200.mesh import scale_grid  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -24,9 +25,9 @@ a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 dev = int(os.environ.get("LOCAL_RANK", "0"))
 base = fd.shoebox_tet4(*[int(t) for t in a.shape.split(",")])
-AP = fd.AirProperties()
-AC = fd.AlgControls(AP, 20, 200, 1)
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties()
+AC = rs.AlgControls(AP, 20, 200, 1)
+BC = rs.BC(AC, AP)
 for t in range(2, 8):
     BC.rigid(t)
 rng = np.random.default_rng(0)
@@ -36,8 +37,8 @@ nfreq = 0
 obj = None
 for gi in range(rank, a.geometries, world):
     grid = scale_grid(base, factors[gi])
-    S = fd.Source(coord=grid.nos[grid.closest_node(np.array([1.0, 1.0, 1.2]) * factors[gi])], q=[1e-4])
-    R = fd.Receiver(coord=grid.nos[grid.closest_node(np.array([2.0, 3.0, 1.25]) * factors[gi])])
+    S = rs.Source(coord=grid.nos[grid.closest_node(np.array([1.0, 1.0, 1.2]) * factors[gi])], q=[1e-4])
+    R = rs.Receiver(coord=grid.nos[grid.closest_node(np.array([2.0, 3.0, 1.25]) * factors[gi])])
     new = fd.FEM3D(grid, S, R, AP, AC, BC, device=dev, shard=False)
     if obj is not None:
         new._sys = obj._sys          # keep the device allocation; the new coordinates force re-assembly
@@ -45,8 +46,8 @@ for gi in range(rank, a.geometries, world):
     if a.candidates > 0:
         crng = np.random.default_rng(gi)
         lo, hi = grid.nos.min(axis=0) + 0.3, grid.nos.max(axis=0) - 0.3
-        sC = [fd.Source(coord=grid.nos[grid.closest_node(crng.uniform(lo, hi))], q=[1e-4]) for _ in range(a.candidates)]
-        rC = [fd.Receiver(coord=crng.uniform(lo, hi)) for _ in range(a.candidates)]
+        sC = [rs.Source(coord=grid.nos[grid.closest_node(crng.uniform(lo, hi))], q=[1e-4]) for _ in range(a.candidates)]
+        rC = [rs.Receiver(coord=crng.uniform(lo, hi)) for _ in range(a.candidates)]
         obj.compute_candidates(sC, rC)
         nfreq += len(AC.freq) * a.candidates
     else:

@@ -8,19 +8,20 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
+import room_setup as rs  # noqa: E402
 
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 grid = fd.shoebox_tet4(12, 16, 10, jitter=0.2)
-AP = fd.AirProperties()
-AC = fd.AlgControls(AP, 20, 120, 3)
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties()
+AC = rs.AlgControls(AP, 20, 120, 3)
+BC = rs.BC(AC, AP)
 for t in range(2, 8):
     BC.rigid(t)
 BC.normalized_admittance(7, 0.05)
-S = fd.Source(coord=[1.0, 1.0, 1.2], q=[1e-4])
-R = fd.Receiver(coord=[[2.0, 3.0, 1.25], [0.41, 3.6, 0.77]])
+S = rs.Source(coord=[1.0, 1.0, 1.2], q=[1e-4])
+R = rs.Receiver(coord=[[2.0, 3.0, 1.25], [0.41, 3.6, 0.77]])
 obj = fd.FEM3D(grid, S, R, AP, AC, BC, tol=1e-10)
 obj.compute(timeit=False)
 pR = obj.evaluate(R)

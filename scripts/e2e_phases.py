@@ -9,15 +9,16 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
+import room_setup as rs  # noqa: E402
 
 grid = fd.shoebox_tet4(99, 133, 74)
-AP = fd.AirProperties(c0=343.0, rho0=1.21)
-AC = fd.AlgControls(AP, freq_vec=np.arange(20.0, 501.0, 1.0))
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties(c0=343.0, rho0=1.21)
+AC = rs.AlgControls(AP, freq_vec=np.arange(20.0, 501.0, 1.0))
+BC = rs.BC(AC, AP)
 for t in range(2, 8):
     BC.rigid(t)
-S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
 obj = fd.FEM3D(grid, S, R, AP, AC, BC)
 obj.compute(timeit=False, keep_pN=False)          # warm-up: library load, handles, graphs
 obj2 = fd.FEM3D(grid, S, R, AP, AC, BC)

@@ -13,6 +13,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
+import room_setup as rs  # noqa: E402
 from femder_b200 import sharding  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -57,13 +58,13 @@ if rank == 0:
 assert same and abs(m1 - m2) <= max(2, m1 // 50) and rel < 0.05
 
 # sharded FEM3D.compute() against the single-process one
-AP = fd.AirProperties(c0=343.0, rho0=1.21)
-AC = fd.AlgControls(AP, freq_vec=np.arange(20.0, 301.0, 4.0))
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties(c0=343.0, rho0=1.21)
+AC = rs.AlgControls(AP, freq_vec=np.arange(20.0, 301.0, 4.0))
+BC = rs.BC(AC, AP)
 for g in range(2, 8):
     BC.rigid(g)
-S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
 o1 = fd.FEM3D(grid, S, R, AP, AC, BC, device=local, shard=False)
 o1.compute(timeit=False, keep_pN=False)
 o2 = fd.FEM3D(grid, S, R, AP, AC, BC, device=local, shard=True)

@@ -4,18 +4,19 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd
+import room_setup as rs  # noqa: E402
 
 def run(name, grid, freqs, admittance, n_rcv=3, tol=1e-8):
-    AP = fd.AirProperties()
-    AC = fd.AlgControls(AP, freq_vec=np.asarray(freqs, dtype=float))
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties()
+    AC = rs.AlgControls(AP, freq_vec=np.asarray(freqs, dtype=float))
+    BC = rs.BC(AC, AP)
     for t in range(2, 8):
         BC.rigid(t)
     if admittance:
         BC.normalized_admittance(7, admittance)
     rng = np.random.default_rng(1)
-    S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-    R = fd.Receiver(coord=rng.uniform([0.1, 0.1, 0.1], [2.9, 3.9, 2.4], size=(n_rcv, 3)))
+    S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+    R = rs.Receiver(coord=rng.uniform([0.1, 0.1, 0.1], [2.9, 3.9, 2.4], size=(n_rcv, 3)))
     obj = fd.FEM3D(grid, S, R, AP, AC, BC, tol=tol)
     t = time.perf_counter(); obj.compute(timeit=False, keep_pN=False); t = time.perf_counter() - t
     st = obj.stats

@@ -3,17 +3,18 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd
+import room_setup as rs  # noqa: E402
 rigid = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 g1 = fd.shoebox_tet4(26, 34, 22)
-AP = fd.AirProperties()
-AC = fd.AlgControls(AP, 20, 500, 1)
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties()
+AC = rs.AlgControls(AP, 20, 500, 1)
+BC = rs.BC(AC, AP)
 for t in range(2, 8):
     BC.rigid(t)
 if not rigid:
     BC.normalized_admittance(7, 0.02)
-S = fd.Source(coord=g1.nos[g1.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-R = fd.Receiver(coord=g1.nos[g1.closest_node([2.0, 3.0, 1.25])])
+S = rs.Source(coord=g1.nos[g1.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+R = rs.Receiver(coord=g1.nos[g1.closest_node([2.0, 3.0, 1.25])])
 ref = None
 for batch in ([16, 32, 64, "auto"] if rigid else [8, 16, 32, 64, "auto"]):
     o = fd.FEM3D(g1, S, R, AP, AC, BC, tol=1e-8, batch=batch, check_every=64)

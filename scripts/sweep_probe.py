@@ -9,6 +9,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import femder_b200 as fd  # noqa: E402
+import room_setup as rs  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="26,34,22")
@@ -22,15 +23,15 @@ a = ap.parse_args()
 g = fd.shoebox_tet4(*[int(t) for t in a.shape.split(",")])
 if a.tet10:
     g = fd.to_tet10(g)
-AP = fd.AirProperties()
-AC = fd.AlgControls(AP, freq_vec=a.f0 + np.arange(a.nf))
-BC = fd.BC(AC, AP)
+AP = rs.AirProperties()
+AC = rs.AlgControls(AP, freq_vec=a.f0 + np.arange(a.nf))
+BC = rs.BC(AC, AP)
 for t in range(2, 8):
     BC.rigid(t)
 if not a.rigid:
     BC.normalized_admittance(7, 0.02)
-S = fd.Source(coord=g.nos[g.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-R = fd.Receiver(coord=g.nos[g.closest_node([2.0, 3.0, 1.25])])
+S = rs.Source(coord=g.nos[g.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+R = rs.Receiver(coord=g.nos[g.closest_node([2.0, 3.0, 1.25])])
 batch = a.batch if a.batch == "auto" else int(a.batch)
 o = fd.FEM3D(g, S, R, AP, AC, BC, tol=1e-8, batch=batch, check_every=a.check_every)
 t = time.perf_counter()

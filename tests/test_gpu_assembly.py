@@ -170,9 +170,20 @@ def test_function_level_drop_ins(gpu_lib, golden):
         fluid_c = {1: np.ones(len(grid.elem_vol)) * g.c0}
         fluid_rho = {1: np.ones(len(grid.elem_vol)) * g.rho0}
         det_ja, arg_stiff = fn.pre_compute_volume_assemble_vars(grid.elem_vol, grid.nos, 1)
+        # the reference's return values (fem_numerical.py:129-146): det J and (J^-1 grad N)^T (J^-1 grad N) det J per element
+        xc = np.asarray(grid.nos)[np.asarray(grid.elem_vol)]
+        J = np.stack([xc[:, 1] - xc[:, 0], xc[:, 2] - xc[:, 0], xc[:, 3] - xc[:, 0]], axis=1)
+        gradN = np.array([[-1.0, 1, 0, 0], [-1, 0, 1, 0], [-1, 0, 0, 1]])
+        B = np.linalg.inv(J) @ gradN
+        det = np.abs(np.linalg.det(J))
+        ref_stiff = np.einsum("eil,eij->lje", B, B) * det
+        assert det_ja.shape == (len(grid.elem_vol),) and _rel(np.asarray(det_ja), det) < 1e-12
+        assert arg_stiff.shape == (4, 4, len(grid.elem_vol)) and _rel(arg_stiff, ref_stiff) < 1e-12
+        sys_before = fn.device_system(0)
         H, Q = fn.assemble_volume_matrices(grid.elem_vol, grid.nos, fluid_c, fluid_rho, 1, grid.domain_index_vol, 0,
                                            det_ja, arg_stiff)
         A = fn.assemble_surface_matrices(grid.elem_surf, grid.nos, areas, grid.domain_index_surf, g.group_ids, 1)
+        assert fn.device_system(0) is sys_before       # one device system serves every call
         with pytest.raises(ValueError):
             fn.assemble_volume_matrices(grid.elem_vol, grid.nos, fluid_c, fluid_rho, 2, grid.domain_index_vol, 0)
         tol = 4e-7

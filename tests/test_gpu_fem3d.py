@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+import room_setup as rs
 from oracle import femder_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -9,15 +10,15 @@ pytestmark = pytest.mark.gpu
 
 def _run(g, **kw):
     import femder_b200 as fd
-    AP = fd.AirProperties(c0=g.c0, rho0=g.rho0)
-    AC = fd.AlgControls(AP, freq_vec=g.freq)
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties(c0=g.c0, rho0=g.rho0)
+    AC = rs.AlgControls(AP, freq_vec=g.freq)
+    BC = rs.BC(AC, AP)
     for k, v in g.mu.items():
         BC.mu[k] = v
     for k, v in (g.v or {}).items():
         BC.v[k] = v
-    S = fd.Source(coord=g.src, q=g.src_q)
-    R = fd.Receiver(coord=g.rcv)
+    S = rs.Source(coord=g.src, q=g.src_q)
+    R = rs.Receiver(coord=g.rcv)
     obj = fd.FEM3D(g.grid, S, R, AP, AC, BC, tol=1e-10, batch=4, **kw)
     obj.compute(timeit=False)
     return obj, R
@@ -64,7 +65,7 @@ def test_receivers_only_and_offnode(gpu_lib):
     from conftest import Golden
     g = Golden("tet4_shoebox_jitter")
     obj, R = _run(g)
-    Roff = fd.Receiver(coord=g.rcv_off)
+    Roff = rs.Receiver(coord=g.rcv_off)
     pRoff = obj.evaluate(Roff)
     assert np.abs(fd.p2SPL(pRoff) - fd.p2SPL(g.pR_off)).max() < 0.01
     obj.R = Roff
@@ -76,15 +77,15 @@ def test_missing_bc_raises_keyerror(gpu_lib):
     import femder_b200 as fd
     from conftest import Golden
     g = Golden("tet4_cplx_room")
-    AP = fd.AirProperties()
-    AC = fd.AlgControls(AP, freq_vec=g.freq)
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties()
+    AC = rs.AlgControls(AP, freq_vec=g.freq)
+    BC = rs.BC(AC, AP)
     BC.rigid(2)  # group 3 has no boundary condition
-    obj = fd.FEM3D(g.grid, fd.Source(coord=g.src, q=g.src_q), None, AP, AC, BC)
+    obj = fd.FEM3D(g.grid, rs.Source(coord=g.src, q=g.src_q), None, AP, AC, BC)
     with pytest.raises(KeyError):
         obj.compute(timeit=False)
-    BC.rhoc[1] = np.ones(len(g.freq))   # equivalent-fluid domains are outside the hot path
-    with pytest.raises(NotImplementedError):
+    BC.rhoc[1] = np.ones(len(g.freq))   # a fluid domain needs both its density and its sound speed (BC.fluid sets both)
+    with pytest.raises(ValueError):
         fd.FEM3D(g.grid, None, None, AP, AC, BC)
 
 
@@ -94,7 +95,7 @@ def test_h_is_cached_between_computes(gpu_lib):
     g = Golden("tet4_cplx_room")
     obj, _ = _run(g)
     H0 = obj.H
-    obj.S = fd.Source(coord=g.grid.nos[10], q=[2e-4])
+    obj.S = rs.Source(coord=g.grid.nos[10], q=[2e-4])
     obj.compute(timeit=False)
     assert obj.H is H0  # "H is None" is the cache test (FEM_3D.py:1269)
     r = O.compute(g.grid, g.freq, g.mu, g.grid.nos[10:11], [2e-4], g.c0, g.rho0)
@@ -106,9 +107,9 @@ def test_no_boundary_conditions_branch(gpu_lib):
     import femder_b200 as fd
     from conftest import Golden
     g = Golden("tet4_shoebox_rigid")
-    AP = fd.AirProperties(c0=g.c0, rho0=g.rho0)
-    AC = fd.AlgControls(AP, freq_vec=g.freq)
-    S = fd.Source(coord=g.src, q=g.src_q)
+    AP = rs.AirProperties(c0=g.c0, rho0=g.rho0)
+    AC = rs.AlgControls(AP, freq_vec=g.freq)
+    S = rs.Source(coord=g.src, q=g.src_q)
     obj = fd.FEM3D(g.grid, S, None, AP, AC, None, tol=1e-10)
     obj.compute(timeit=False)
     assert obj.A is None and obj.stats.real_arithmetic

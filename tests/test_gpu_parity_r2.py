@@ -10,6 +10,8 @@ import pytest
 from scipy.sparse.linalg import eigsh, splu
 
 import femder_b200 as fd
+
+import room_setup as rs  # noqa: E402
 from femder_b200._lib import FemderB200Error
 from oracle import femder_oracle as O
 
@@ -18,15 +20,15 @@ C0, RHO0 = 343.0, 1.21
 
 
 def _problem(grid, freq, rigid=range(2, 8), adm=None, src=(1.0, 1.0, 1.2), rcv=(2.0, 3.0, 1.25), **kw):
-    AP = fd.AirProperties(c0=C0, rho0=RHO0)
-    AC = fd.AlgControls(AP, freq_vec=np.asarray(freq, dtype=np.float64))
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties(c0=C0, rho0=RHO0)
+    AC = rs.AlgControls(AP, freq_vec=np.asarray(freq, dtype=np.float64))
+    BC = rs.BC(AC, AP)
     for t in rigid:
         BC.rigid(t)
     for t, y in (adm or {}).items():
         BC.normalized_admittance(t, y)
-    S = fd.Source(coord=grid.nos[grid.closest_node(src)], q=[1e-4])
-    R = fd.Receiver(coord=grid.nos[grid.closest_node(rcv)])
+    S = rs.Source(coord=grid.nos[grid.closest_node(src)], q=[1e-4])
+    R = rs.Receiver(coord=grid.nos[grid.closest_node(rcv)])
     return fd.FEM3D(grid, S, R, AP, AC, BC, **kw), S, R, AC, BC
 
 
@@ -123,13 +125,13 @@ def test_config3_fem3d_evaluate_off_node(gpu_lib):
     (FP64 assembly) end to end."""
     from conftest import Golden
     g = Golden("tet4_caixa")
-    AP = fd.AirProperties(c0=g.c0, rho0=g.rho0)
-    AC = fd.AlgControls(AP, freq_vec=g.freq)
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties(c0=g.c0, rho0=g.rho0)
+    AC = rs.AlgControls(AP, freq_vec=g.freq)
+    BC = rs.BC(AC, AP)
     for k, v in g.mu.items():
         BC.mu[k] = v
-    S = fd.Source(coord=g.src, q=g.src_q)
-    R = fd.Receiver(coord=np.vstack([g.rcv, g.rcv_off]))
+    S = rs.Source(coord=g.src, q=g.src_q)
+    R = rs.Receiver(coord=np.vstack([g.rcv, g.rcv_off]))
     obj = fd.FEM3D(g.grid, S, R, AP, AC, BC)
     obj.compute(timeit=False)
     pR = obj.evaluate(R)
@@ -145,14 +147,14 @@ def test_velocity_branch_without_admittance_on_driven_faces(gpu_lib):
     faces carry nothing (FEM_3D.py:1320-1347 walks np.sort([*self.mu]) only).  It must run, and match the oracle."""
     grid = fd.shoebox_tet4(6, 7, 5, jitter=0.2)
     freq = np.array([30.0, 75.0, 140.0])
-    AP = fd.AirProperties(c0=C0, rho0=RHO0)
-    AC = fd.AlgControls(AP, freq_vec=freq)
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties(c0=C0, rho0=RHO0)
+    AC = rs.AlgControls(AP, freq_vec=freq)
+    BC = rs.BC(AC, AP)
     BC.velocity(2, 1e-3)
     BC.velocity(4, 5e-4)
     BC.normalized_admittance(7, 0.1)
-    S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-    R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+    S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+    R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
     obj = fd.FEM3D(grid, S, R, AP, AC, BC, tol=1e-10)
     obj.compute(timeit=False)
     assert set(BC.mu) == {7} and set(BC.v) == {2, 4}
@@ -221,11 +223,11 @@ def test_compute_candidates_against_the_oracle(gpu_lib):
     grid = fd.shoebox_tet4(10, 12, 8, jitter=0.2)
     freq = np.array([35.0, 80.0, 125.0, 160.0, 200.0])
     obj, S0, R0, AC, BC = _problem(grid, freq, rigid=range(2, 7), adm={7: 0.15})
-    srcs = [fd.Source(coord=grid.nos[grid.closest_node(c)], q=[qv]) for c, qv in
+    srcs = [rs.Source(coord=grid.nos[grid.closest_node(c)], q=[qv]) for c, qv in
             (([1.0, 1.0, 1.2], 1e-4), ([2.2, 0.7, 0.6], 2e-4), ([0.5, 3.2, 1.9], 1e-4))]
-    rcvs = [fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])]),
-            fd.Receiver(coord=[[1.93, 2.71, 1.33], list(grid.nos[grid.closest_node([0.4, 0.4, 0.4])])]),     # off-node + on-node
-            fd.Receiver(coord=[1.11, 1.77, 0.83])]
+    rcvs = [rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])]),
+            rs.Receiver(coord=[[1.93, 2.71, 1.33], list(grid.nos[grid.closest_node([0.4, 0.4, 0.4])])]),     # off-node + on-node
+            rs.Receiver(coord=[1.11, 1.77, 0.83])]
     out = obj.compute_candidates(srcs, rcvs)
     assert len(out) == 3 and [o.shape for o in out] == [(5, 1), (5, 2), (5, 1)] and obj.n_unconverged == 0
     for S, R, pR in zip(srcs, rcvs, out):
@@ -293,14 +295,14 @@ def test_equivalent_fluid_branch(gpu_lib):
     d = np.load(os.path.join(GOLDEN_DIR, "fluid", "tet4_fluid.npz"))
     g = Grid(d["nos"], d["elem_vol"], d["elem_surf"], d["domain_index_surf"], domain_index_vol=d["domain_index_vol"])
     freq = d["freq"]
-    AP = fd.AirProperties(c0=float(d["c0"]), rho0=float(d["rho0"]))
-    AC = fd.AlgControls(AP, freq_vec=freq)
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties(c0=float(d["c0"]), rho0=float(d["rho0"]))
+    AC = rs.AlgControls(AP, freq_vec=freq)
+    BC = rs.BC(AC, AP)
     for i, k in enumerate(d["group_ids"]):
         BC.mu[int(k)] = d["mu"][i]
     BC.fluid(int(d["fluid_domain"]), complex(d["cc"]), complex(d["rhoc"]))
-    S = fd.Source(coord=d["src"], q=d["src_q"])
-    R = fd.Receiver(coord=d["rcv"])
+    S = rs.Source(coord=d["src"], q=d["src_q"])
+    R = rs.Receiver(coord=d["rcv"])
     obj = fd.FEM3D(g, S, R, AP, AC, BC, tol=1e-10)
     obj.compute(timeit=False)
     assert obj.n_unconverged == 0 and set(obj.rho) == {1, 2}

@@ -373,15 +373,16 @@ def test_results_land_at_their_frequency_index(gpu_lib):
 def test_config2_tet10_admittance_wall(gpu_lib):
     """Config 2 in the small: Tet10 shoebox (5 733 DOF) with a normalized-admittance wall, GPU assembly + sweep vs oracle."""
     import femder_b200 as fd
+    import room_setup as rs  # noqa: E402
     grid = fd.to_tet10(fd.shoebox_tet4(8, 10, 6, jitter=0.15))
-    AP = fd.AirProperties()
-    AC = fd.AlgControls(AP, freq_vec=[20.0, 57.0, 101.0, 160.0, 200.0])
-    BC = fd.BC(AC, AP)
+    AP = rs.AirProperties()
+    AC = rs.AlgControls(AP, freq_vec=[20.0, 57.0, 101.0, 160.0, 200.0])
+    BC = rs.BC(AC, AP)
     for t in range(2, 7):
         BC.rigid(t)
     BC.normalized_admittance(7, 0.02)
-    S = fd.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
-    R = fd.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
+    S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
+    R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
     obj = fd.FEM3D(grid, S, R, AP, AC, BC, tol=1e-10)
     obj.compute(timeit=False)
     obj.evaluate(R)
