@@ -67,6 +67,7 @@ SIGNATURES = {
     "fdb_modal_estimate": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_int)]),
     "fdb_modal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p, C.c_void_p]),
     "fdb_set_nodes": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "fdb_modal_compression": (C.c_int, [C.c_void_p, C.c_int]),
     "fdb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdb_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "fdb_comm_free": (C.c_int, [C.c_void_p]),

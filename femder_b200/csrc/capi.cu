@@ -395,6 +395,14 @@ int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_m
     FDB_API_END
 }
 
+int fdb_modal_compression(fdb_system* sys, int on) {
+    FDB_API_BEGIN
+    FDB_SYS_MUT(sys);
+    FDB_REQUIRE(sys->have_modes, "no modes");
+    fdb::modal_set_compression(sys, on != 0);
+    FDB_API_END
+}
+
 int fdb_comm_unique_id(char* out128) {
     FDB_API_BEGIN
     FDB_REQUIRE(out128 != nullptr, "null argument");
@@ -498,7 +506,7 @@ int fdb_iteration_enqueue(fdb_system* sys, int batch, int reps, int flags, int w
     FDB_API_BEGIN
     FDB_SYS(sys);
     FDB_REQUIRE(which < 0 || reps > 0, "reps must be positive");
-    FDB_REQUIRE(which >= -1 && which <= 5, "which must be -1 (prepare), 0 (K5), 1 (K6a), 2 (K6b), 3 / 4 / 5 (modal projection / expansion / coefficients)");
+    FDB_REQUIRE(which >= -1 && which <= 6, "which must be -1 (prepare), 0 (K5), 1 (K6a), 2 (K6b), 3 / 4 / 5 / 6 (modal projection / expansion / coefficients / z += Phi u)");
     fdb::run_iteration_enqueue(sys, batch, reps, flags, which, algorithmic_bytes);
     FDB_API_END
 }

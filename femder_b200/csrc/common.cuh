@@ -166,6 +166,13 @@ struct fdb_system {
     fdb::DevBuf<double> modal_res;     // [n_modes] ||H v - lambda Q v|| / ||Q v||: how far each stored vector is from an eigenvector
     std::vector<double> modal_res_host;
     fdb::DevBuf<uint16_t> modal_v;     // bf16 [n_tiles][mode_chunks][16 mode blocks][16 node blocks][8 nodes][8 modes]
+    // tile-compressed modes (modal.cu): V_t ~ Phi_t C_t per 128-node tile
+    bool modal_compress = false;       // the sweep streams Phi and C instead of V
+    bool have_coarse_v = false;        // modal_phi / modal_vc are built
+    bool have_fine_v = false;          // modal_v is packed (always without compression; on demand with it)
+    int64_t nc_rows = 0, n_ctiles = 0; // coarse unknowns (16 per tile) and their 128-row tiles
+    fdb::DevBuf<uint16_t> modal_phi;   // bf16 [n_tiles][2 function blocks][16 node blocks][8 nodes][8 functions]
+    fdb::DevBuf<uint16_t> modal_vc;    // bf16 coefficient tiles C in modal_v's layout over the coarse unknowns
     fdb::DevBuf<double> modal_x;       // FP64 modes [ceil(n_modes / 16)][n_nodes (internal order)][16], kept on request
     fdb::DevBuf<double> modal_adiag;   // [n_groups][n_modes] v_i^T A_g v_i (damping of mode i by group g), built on demand
     bool have_modes = false, have_adiag = false;

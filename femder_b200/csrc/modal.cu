@@ -36,6 +36,8 @@ constexpr int kChunkBytes = 128 * kMC * 2;     // one tile of V for one chunk of
 constexpr int kStages = 4;                     // ring of V chunks in shared memory
 constexpr int kModalThreads = 192;             // warp 0 producer, warp 1 MMA issue + TMEM owner, warps 2..5 operand / epilogue
 constexpr uint32_t kSm = 2048, kSn = 128;      // byte strides of a chunk: mode block (8 modes), node block (8 nodes)
+constexpr int kCF = 16;                        // functions of a tile basis (tile-compressed modes)
+constexpr int kPhiBytes = 128 * kCF * 2;       // one tile basis in the chunk layout: the first two "mode blocks", 4 KB
 // k_modal_coef keeps |lambda - w^2| >= res^2 / lambda (res = the stored vector's residual): below that the inexact vector cannot
 // tell which side of the resonance the drive frequency is on.  Nothing coarser: a bound proportional to res itself was tried
 // and makes V diag(d) V^T stop being the inverse of G on span(V), which the indefinite CG recurrence does not survive
@@ -265,28 +267,36 @@ struct FusedSmem {
                                                   // shared ring could not tell them apart by parity: each consumer has its own barriers.)
     uint64_t b_full[2], b_empty[2];
     uint64_t z_full[2], z_empty[2];
+    uint64_t phi_full[2], phi_empty[2];           // COARSE: the tile bases
     uint64_t done;
     uint32_t tmem_base;
     double2 alpha[16];
     int act[16];
 };
 
-template <bool START, bool CPX>
+// COARSE (tile-compressed modes, see "tile bases" below): instead of the V chunks the tile's basis Phi_t (128 nodes x 16 functions,
+// 4 KB) is the second A operand: t = Phi_t^T r, 16 numbers per column, written to tc[tile][16][16] for the coarse projection.
+// Phi_t sits at the start of a 32 KB operand extent whose remaining rows are whatever shared memory holds: they only feed
+// accumulator rows nobody reads.
+template <bool START, bool CPX, bool COARSE = false>
 __global__ void __launch_bounds__(kModalThreads, 1)
 k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint16_t* __restrict__ binv16, float* __restrict__ z32,
                 const uint16_t* __restrict__ V, int n_chunks, int64_t n_rows, int64_t n_tiles, const Scalars* __restrict__ sc,
-                float* __restrict__ c_part) {
+                float* __restrict__ c_part, const uint16_t* __restrict__ phi16, double* __restrict__ tc) {
     constexpr int F = CPX ? 8 : 16;
     constexpr uint32_t kZCol = 32 * kModalMaxChunks;   // TMEM columns: [0, 256) projection accumulators, [256, 320) two z_bj accumulators
+    constexpr uint32_t kTCol = kZCol + 64;             // COARSE: [320, 384) two t accumulators
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* ring = smem_raw;                                      // [kStages][32 KB]
-    unsigned char* rqbuf = smem_raw + (size_t)kStages * kChunkBytes;     // [2][32 KB]: r (16 KB) | q (16 KB)
+    unsigned char* phis = smem_raw;                                      // COARSE: [2][4 KB] tile bases (reads run on into the ring)
+    unsigned char* ring = smem_raw + (COARSE ? 2 * kPhiBytes : 0);       // [kStages][32 KB]
+    unsigned char* rqbuf = ring + (size_t)kStages * kChunkBytes;         // [2][32 KB]: r (16 KB) | q (16 KB)
     unsigned char* bimg = rqbuf + 2 * (size_t)kChunkBytes;               // [2][8 KB]
     FusedSmem* sm = reinterpret_cast<FusedSmem*>(bimg + 2 * 8192);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n_use, ksteps_last;
     uint32_t bytes_last;
     modal_shape(sc->modes_use, n_use, bytes_last, ksteps_last);
+    if (COARSE) n_use = 0;
     const uint32_t items = 1u + (uint32_t)n_use;   // ring items per tile: B_t, then the V chunks
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sm->s_full[i], 1); mbar_init(&sm->s_empty[i], 1); }
@@ -294,6 +304,7 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
             mbar_init(&sm->rq_full[i], 1); mbar_init(&sm->rq_empty[i], 1);
             mbar_init(&sm->b_full[i], 128); mbar_init(&sm->b_empty[i], 1);
             mbar_init(&sm->z_full[i], 1); mbar_init(&sm->z_empty[i], 128);
+            mbar_init(&sm->phi_full[i], 1); mbar_init(&sm->phi_empty[i], 1);
         }
         mbar_init(&sm->done, 1);
         mbar_fence_init();
@@ -335,6 +346,12 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
                     mbar_expect_tx(&sm->s_full[st], (uint32_t)kChunkBytes);
                     bulk_g2s(ring + (size_t)st * kChunkBytes, binv16 + t * (kChunkBytes / 2), (uint32_t)kChunkBytes, &sm->s_full[st]);
                 }
+                if constexpr (COARSE) {
+                    const int pb = ti & 1;
+                    mbar_wait_bounded(&sm->phi_empty[pb], ((ti >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&sm->phi_full[pb], (uint32_t)kPhiBytes);
+                    bulk_g2s(phis + (size_t)pb * kPhiBytes, phi16 + t * (kPhiBytes / 2), (uint32_t)kPhiBytes, &sm->phi_full[pb]);
+                }
                 for (int j = 0; j < n_use; ++j) {
                     const int st = slot_for(it++);
                     const uint32_t bytes = (j == n_use - 1) ? bytes_last : (uint32_t)kChunkBytes;
@@ -364,7 +381,16 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
                     for (int ks = 0; ks < 8; ++ks)
                         tc_mma_bf16(tmem + kZCol + 32 * bb, tc_desc(a_addr + ks * 2 * kSm, kSm, kSn), tc_desc(b_addr + ks * 256, 128, 2048), idesc_z, ks > 0);
                     tc_commit(&sm->s_empty[st]);
-                    tc_commit(&sm->z_full[bb]);
+                    if constexpr (COARSE) {   // t = Phi_t^T r: rows 0..15 of the accumulator
+                        mbar_wait_bounded(&sm->phi_full[bb], (ti >> 1) & 1u);
+                        tc_fence_after();
+                        const uint32_t p_addr = smem_u32(phis + (size_t)bb * kPhiBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            tc_mma_bf16(tmem + kTCol + 32 * bb, tc_desc(p_addr + ks * 2 * kSn, kSn, kSm), tc_desc(b_addr + ks * 256, 128, 2048), idesc_p, ks > 0);
+                        tc_commit(&sm->phi_empty[bb]);
+                    }
+                    tc_commit(&sm->z_full[bb]);   // both accumulators of the tile
                 }
                 for (int j = 0; j < n_use; ++j) {
                     const uint32_t it = it0 + 1 + j;
@@ -391,6 +417,19 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
             tc_fence_after();
             float acc[32];
             tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + kZCol + 32 * bb, acc);
+            if constexpr (COARSE) {
+                if (qd == 0) {   // lanes 0..15 of the accumulator = the 16 functions
+                    float ta[32];
+                    tmem_ld32(tmem + kTCol + 32 * bb, ta);
+                    if (lane < kCF) {
+                        double4* o = reinterpret_cast<double4*>(tc + (t * kCF + lane) * 16);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            o[k] = make_double4((double)ta[4 * k] + (double)ta[16 + 4 * k], (double)ta[4 * k + 1] + (double)ta[17 + 4 * k],
+                                                (double)ta[4 * k + 2] + (double)ta[18 + 4 * k], (double)ta[4 * k + 3] + (double)ta[19 + 4 * k]);
+                    }
+                }
+            }
             tc_fence_before();
             mbar_arrive(&sm->z_empty[bb]);
             const int64_t row = t * 128 + zrow;
@@ -472,7 +511,7 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
         mbar_wait_bounded(&sm->done, 0);
         tc_fence_after();
         float* out = c_part + (int64_t)blockIdx.x * kModalMaxModes * 16;
-        for (int j = 0; j < n_use; ++j) {
+        for (int j = 0; j < n_use; ++j) {   // (none when COARSE)
             float acc[32];
             tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + 32 * j, acc);
             float4* o = reinterpret_cast<float4*>(out + (int64_t)(j * kMC + qd * 32 + lane) * 16);
@@ -550,7 +589,8 @@ __global__ void __launch_bounds__(256) k_modal_coef(const float* __restrict__ c_
 // expansion  z += V e , then with the complete z:  rho' = r^T z, ||r||^2 and the finalisation of the iteration
 // (fin_update) or of the slot load (START: p = z, fin_start).  T = double (real sweep, 16 slots) or double2 (8 complex).
 // ------------------------------------------------------------------------------------------------
-template <bool CPX, bool START>
+// PLAIN: z32 = V e and nothing else (the coarse stage of the tile-compressed correction: V = the coefficient tiles, z32 = u).
+template <bool CPX, bool START, bool PLAIN = false>
 __global__ void __launch_bounds__(kModalThreads, 1)
 k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __restrict__ p_start, const uint16_t* __restrict__ V, int n_chunks,
                const uint16_t* __restrict__ e_img, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
@@ -625,7 +665,7 @@ k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __
             // the row's residual and block-Jacobi part while the tensor core works
             double rv[16];
             float zv[16];
-            if (valid) {
+            if (valid && !PLAIN) {
                 const double4* src = reinterpret_cast<const double4*>(r + row * 16);
                 const float4* zs = reinterpret_cast<const float4*>(z32 + row * 16);
 #pragma unroll
@@ -651,6 +691,7 @@ k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __
                 float4* zd = reinterpret_cast<float4*>(z32 + row * 16);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) zd[k] = make_float4(zv[4 * k], zv[4 * k + 1], zv[4 * k + 2], zv[4 * k + 3]);
+                if constexpr (PLAIN) continue;
                 if constexpr (START) {
                     // first search direction of the slots being loaded
 #pragma unroll
@@ -679,6 +720,7 @@ k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 64);
+    if constexpr (PLAIN) return;
     double* s_red = reinterpret_cast<double*>(ring);   // [128][3 F]
     if (tid >= 64) {
         const int e = tid - 64;
@@ -700,20 +742,355 @@ k_modal_expand(const double* __restrict__ r, float* __restrict__ z32, double* __
     });
 }
 
+// ================================================================================================
+// Tile-compressed modes.  The mode tiles are what an iteration streams (2 bytes per node and mode, twice), and inside one
+// 128-node tile the modes below the cut are smooth: a tile is a fraction of the shortest wavelength across, so its rows of V
+// are, to the accuracy bf16 stores them with, combinations of kCF = 16 functions (measured: tests/research/
+// compressed_modes_prototype.py - rank 16 reproduces the exact modes' iteration counts, rank 12 and a cubic polynomial fit
+// nearly).  So per tile
+//       V_t ~ Phi_t C_t ,   Phi_t: 128 x 16 (the tile's dominant left singular vectors, bf16), C_t: 16 x modes (bf16)
+// and the correction  V diag(d) V^T  becomes  Phi (C diag(d) C^T) Phi^T:  t = Phi^T r inside K6a (one more MMA group per tile),
+// the two products with C on the coarse vector (16 numbers per tile: 1/8 of the nodes) by the same tensor-core kernels that
+// handled V, and z += Phi u with the scalars of the iteration in k_coarse_finish.  The stream per iteration drops from
+// 4 bytes to ~0.55 bytes per node and mode.
+// ================================================================================================
+
+// One block per tile: Gram matrix of the tile's rows of the modes, orthogonal iteration for its 16 dominant eigenvectors, the
+// bf16 basis in the operand layout, and the tile's rows of the coarse modes  Xc = (Phi_b^T Phi_b)^-1 Phi_b^T X  (the least-squares
+// coefficients for the ROUNDED basis).  FP64 throughout: the spectrum of the Gram matrix falls by ~1e5 over the 16 kept directions.
+constexpr int kTbThreads = 256;
+constexpr int kTbGs = 129, kTbPs = 17;   // padded strides (bank conflicts)
+static size_t tile_basis_smem() { return (size_t)(128 * kTbGs + 3 * 128 * kTbPs + 16 * 16 + 128) * sizeof(double); }
+
+__device__ __forceinline__ double tb_block_sum(double v, double* s_w) {
+    // sum over the block's 256 threads, the same value to every thread (fixed order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTbThreads / 32; ++k) t += s_w[k];
+    return t;
+}
+
+// modified Gram-Schmidt on the 16 columns of A [128][kTbPs]; a column without norm (fewer than 16 independent rows) becomes zero
+__device__ void tb_orthonormalise(double* A, double* s_w, double* s_d) {
+    const int tid = threadIdx.x, i = tid & 127;
+    const bool own = tid < 128;
+    for (int k = 0; k < kCF; ++k) {
+        const double a = own ? A[i * kTbPs + k] : 0.0;
+        const double n2 = tb_block_sum(a * a, s_w);
+        const double inv = n2 > 1e-280 ? rsqrt(n2) : 0.0;
+        if (own) A[i * kTbPs + k] = a * inv;
+        // dots of the normalised column with the later ones: 16 threads per later column would idle most of the block, so every
+        // row thread forms its 15 products and the warps reduce them
+        double d[kCF];
+#pragma unroll
+        for (int j = 0; j < kCF; ++j) d[j] = (own && j > k) ? a * inv * A[i * kTbPs + j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < kCF; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+        __syncthreads();
+        if ((tid & 31) == 0 && own)
+#pragma unroll
+            for (int j = 0; j < kCF; ++j) s_d[(tid >> 5) * kCF + j] = d[j];
+        __syncthreads();
+        if (own) {
+#pragma unroll
+            for (int j = 0; j < kCF; ++j)
+                if (j > k) {
+                    const double dj = s_d[j] + s_d[kCF + j] + s_d[2 * kCF + j] + s_d[3 * kCF + j];
+                    A[i * kTbPs + j] -= dj * a * inv;
+                }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kTbThreads, 1)
+k_tile_basis(const double* __restrict__ X, int64_t n_rows, int n_modes, int n_iter, uint16_t* __restrict__ phi16, double* __restrict__ Xc,
+             int64_t nc_rows) {
+    extern __shared__ __align__(16) unsigned char tb_raw[];
+    double* G = reinterpret_cast<double*>(tb_raw);   // [128][kTbGs]
+    double* blk = G + 128 * kTbGs;                   // [128][kTbPs]  one panel's rows of the tile
+    double* P = blk + 128 * kTbPs;                   // [128][kTbPs]
+    double* Y = P + 128 * kTbPs;                     // [128][kTbPs]
+    double* M = Y + 128 * kTbPs;                     // [16][16]
+    double* s_w = M + 256;                           // [8] + [4][16]
+    double* s_d = s_w + 8;
+    const int tid = threadIdx.x, i = tid & 127, half = tid >> 7;
+    const int64_t t = blockIdx.x;
+    const int nbat = (n_modes + 15) / 16;
+    auto load_panel = [&](int bt) {
+        for (int e = tid; e < 128 * 16; e += kTbThreads) {
+            const int node = e >> 4, k = e & 15;
+            const int64_t row = t * 128 + node;
+            blk[node * kTbPs + k] = (row < n_rows && 16 * bt + k < n_modes) ? X[((int64_t)bt * n_rows + row) * 16 + k] : 0.0;
+        }
+    };
+    // ---- Gram matrix: thread (i, half) owns G[i][64 half .. 64 half + 63] ----
+    double acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+    for (int bt = 0; bt < nbat; ++bt) {
+        __syncthreads();
+        load_panel(bt);
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const double a = blk[i * kTbPs + k];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = fma(a, blk[(64 * half + j) * kTbPs + k], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) G[i * kTbGs + 64 * half + j] = acc[j];
+    __syncthreads();
+    // ---- orthogonal iteration, started from 16 spread columns of G (vectors in the range of the tile's modes) ----
+    if (tid < 128)
+        for (int k = 0; k < kCF; ++k) P[i * kTbPs + k] = G[i * kTbGs + 8 * k + 3];
+    __syncthreads();
+    tb_orthonormalise(P, s_w, s_d);
+    for (int itn = 0; itn < n_iter; ++itn) {
+        double y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = 0.0;
+        for (int j = 0; j < 128; ++j) {
+            const double g = G[i * kTbGs + j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = fma(g, P[j * kTbPs + 8 * half + k], y[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Y[i * kTbPs + 8 * half + k] = y[k];
+        __syncthreads();
+        tb_orthonormalise(Y, s_w, s_d);
+        for (int e = tid; e < 128 * kCF; e += kTbThreads) P[(e >> 4) * kTbPs + (e & 15)] = Y[(e >> 4) * kTbPs + (e & 15)];
+        __syncthreads();
+    }
+    // ---- the basis as stored (bf16), M = Phi_b^T Phi_b, W = Phi_b M^-1 ----
+    for (int e = tid; e < 128 * kCF; e += kTbThreads) {
+        const int node = e >> 4, k = e & 15;
+        P[node * kTbPs + k] = (double)bf16_to_float(bf16_rn((float)P[node * kTbPs + k]));
+    }
+    __syncthreads();
+    {
+        const int a = tid >> 4, b = tid & 15;
+        double m = 0.0;
+        for (int node = 0; node < 128; ++node) m = fma(P[node * kTbPs + a], P[node * kTbPs + b], m);
+        M[a * 16 + b] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // Gauss-Jordan on [M | I] in place (M is the identity to bf16 rounding, or has zero rows / columns where the basis has
+        // zero columns: those stay out)
+        double inv[16][16];
+        for (int a = 0; a < 16; ++a)
+            for (int b = 0; b < 16; ++b) inv[a][b] = (a == b) ? 1.0 : 0.0;
+        for (int c = 0; c < 16; ++c) {
+            const double piv = M[c * 16 + c];
+            if (!(fabs(piv) > 1e-6)) {
+                for (int b = 0; b < 16; ++b) { inv[c][b] = 0.0; M[c * 16 + b] = 0.0; }
+                for (int a = 0; a < 16; ++a) M[a * 16 + c] = 0.0;
+                continue;
+            }
+            const double ip = 1.0 / piv;
+            for (int b = 0; b < 16; ++b) { M[c * 16 + b] *= ip; inv[c][b] *= ip; }
+            for (int a = 0; a < 16; ++a) {
+                if (a == c) continue;
+                const double f = M[a * 16 + c];
+                if (f == 0.0) continue;
+                for (int b = 0; b < 16; ++b) { M[a * 16 + b] -= f * M[c * 16 + b]; inv[a][b] -= f * inv[c][b]; }
+            }
+        }
+        for (int a = 0; a < 16; ++a)
+            for (int b = 0; b < 16; ++b) M[a * 16 + b] = inv[a][b];
+    }
+    __syncthreads();
+    for (int e = tid; e < 128 * kCF; e += kTbThreads) {
+        const int node = e >> 4, k = e & 15;
+        double wv = 0.0;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) wv = fma(P[node * kTbPs + a], M[a * 16 + k], wv);
+        Y[node * kTbPs + k] = wv;
+    }
+    // ---- the basis in the operand layout: function block fb, node block nb, node ni -> fb * 2048 + nb * 128 + ni * 16 (8 functions) ----
+    if (tid < 256) {
+        const int node = tid & 127, fb = tid >> 7;
+        uint32_t w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = bf16_rn((float)P[node * kTbPs + 8 * fb + 2 * k]), hi = bf16_rn((float)P[node * kTbPs + 8 * fb + 2 * k + 1]);
+            w4[k] = lo | (hi << 16);
+        }
+        unsigned char* dst = reinterpret_cast<unsigned char*>(phi16) + (size_t)t * kPhiBytes + fb * kSm + (node >> 3) * kSn + (node & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+    // ---- coarse modes: Xc[bt][16 t + k][c] = sum_node W[node][k] X[bt][128 t + node][c] ----
+    const int kk = tid >> 4, cc = tid & 15;
+    for (int bt = 0; bt < nbat; ++bt) {
+        __syncthreads();
+        load_panel(bt);
+        __syncthreads();
+        double sacc = 0.0;
+        for (int node = 0; node < 128; ++node) sacc = fma(Y[node * kTbPs + kk], blk[node * kTbPs + cc], sacc);
+        Xc[((int64_t)bt * nc_rows + t * kCF + kk) * 16 + cc] = sacc;
+    }
+}
+
+// z += Phi u per tile (CUDA cores: 16 functions x 16 columns per node row), then with the complete z what k_modal_expand does:
+// rho' = r^T z, ||r||^2, the iteration's scalars (fin_update) or the slot load's (START: p = z, fin_start).
+constexpr int kCfThreads = 128;
+template <bool CPX, bool START>
+__global__ void __launch_bounds__(kCfThreads)
+k_coarse_finish(const double* __restrict__ r, float* __restrict__ z32, double* __restrict__ p_start, const uint16_t* __restrict__ phi16,
+                const float* __restrict__ uc, int64_t n_rows, int64_t n_tiles, Scalars* __restrict__ sc, double* __restrict__ partial) {
+    constexpr int F = CPX ? 8 : 16;
+    __shared__ __align__(16) float s_u[2][kCF * 16];
+    __shared__ double s_part[kCfThreads / 32][3 * F];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc_rho[16], acc_rr[F];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc_rho[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F; ++k) acc_rr[k] = 0.0;
+    uint32_t ti = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        const int ub = ti & 1;
+        // the tile's 16 x 16 coarse values (1 KB): two floats per thread
+        *reinterpret_cast<float2*>(&s_u[ub][2 * tid]) = __ldg(reinterpret_cast<const float2*>(uc + t * (kCF * 16) + 2 * tid));
+        const int64_t row = t * 128 + tid;
+        const bool valid = row < n_rows;
+        double rv[16];
+        float zv[16], ph[kCF];
+        if (valid) {
+            const double4* src = reinterpret_cast<const double4*>(r + row * 16);
+            const float4* zs = reinterpret_cast<const float4*>(z32 + row * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double4 d = src[k];
+                rv[4 * k] = d.x; rv[4 * k + 1] = d.y; rv[4 * k + 2] = d.z; rv[4 * k + 3] = d.w;
+                const float4 zf = zs[k];
+                zv[4 * k] = zf.x; zv[4 * k + 1] = zf.y; zv[4 * k + 2] = zf.z; zv[4 * k + 3] = zf.w;
+            }
+            const unsigned char* pb = reinterpret_cast<const unsigned char*>(phi16) + (size_t)t * kPhiBytes + (tid >> 3) * kSn + (tid & 7) * 16;
+#pragma unroll
+            for (int fb = 0; fb < 2; ++fb) {
+                const uint4 wv = __ldg(reinterpret_cast<const uint4*>(pb + fb * kSm));
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ph[8 * fb + 2 * k] = bf16_to_float(ww[k] & 0xffffu);
+                    ph[8 * fb + 2 * k + 1] = bf16_to_float(ww[k] >> 16);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { rv[k] = 0.0; zv[k] = 0.f; }
+#pragma unroll
+            for (int k = 0; k < kCF; ++k) ph[k] = 0.f;
+        }
+        __syncthreads();   // s_u[ub] complete (the other buffer is what slower warps may still read from the previous tile)
+#pragma unroll
+        for (int k = 0; k < kCF; ++k) {
+            const float4* ur = reinterpret_cast<const float4*>(&s_u[ub][k * 16]);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 uv = ur[c4];
+                zv[4 * c4] = fmaf(ph[k], uv.x, zv[4 * c4]);
+                zv[4 * c4 + 1] = fmaf(ph[k], uv.y, zv[4 * c4 + 1]);
+                zv[4 * c4 + 2] = fmaf(ph[k], uv.z, zv[4 * c4 + 2]);
+                zv[4 * c4 + 3] = fmaf(ph[k], uv.w, zv[4 * c4 + 3]);
+            }
+        }
+        if (valid) {
+            float4* zd = reinterpret_cast<float4*>(z32 + row * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) zd[k] = make_float4(zv[4 * k], zv[4 * k + 1], zv[4 * k + 2], zv[4 * k + 3]);
+            if constexpr (START) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (sc->reset[CPX ? (k >> 1) : k]) p_start[row * 16 + k] = (double)zv[k];
+            }
+            if constexpr (CPX) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    const double zr = (double)zv[2 * f], zi = (double)zv[2 * f + 1];
+                    acc_rho[2 * f] += rv[2 * f] * zr - rv[2 * f + 1] * zi;
+                    acc_rho[2 * f + 1] += rv[2 * f] * zi + rv[2 * f + 1] * zr;
+                    acc_rr[f] += rv[2 * f] * rv[2 * f] + rv[2 * f + 1] * rv[2 * f + 1];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    acc_rho[k] += rv[k] * (double)zv[k];
+                    acc_rr[k] += rv[k] * rv[k];
+                }
+            }
+        }
+    }
+    // ---- block sums in a fixed order: lanes by shuffle, then the four warps ----
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        double v0 = CPX ? acc_rho[2 * f] : acc_rho[f], v1 = CPX ? acc_rho[2 * f + 1] : 0.0, v2 = acc_rr[f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if (lane == 0) { s_part[warp][3 * f] = v0; s_part[warp][3 * f + 1] = v1; s_part[warp][3 * f + 2] = v2; }
+    }
+    __syncthreads();
+    if (tid < 3 * F) {
+        double s = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < kCfThreads / 32; ++wq) s += s_part[wq][tid];
+        partial[(int64_t)blockIdx.x * 3 * F + tid] = s;
+    }
+    finalize_last_block<F, 3, kCfThreads>(partial, &sc->ticket[START ? 2 : 1], [&](int ff, const double* tot) {
+        if constexpr (START) fin_start(sc, ff, tot); else fin_update(sc, ff, tot);
+    });
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static size_t fused_smem() { return (size_t)(kStages + 2) * kChunkBytes + 2 * 8192 + sizeof(FusedSmem) + 64; }
+static size_t fused_smem(bool coarse = false) { return (size_t)(kStages + 2) * kChunkBytes + 2 * 8192 + sizeof(FusedSmem) + 64 + (coarse ? 2 * kPhiBytes : 0); }
 static size_t project_smem() { return (size_t)kStages * kChunkBytes + 2 * 8192 + sizeof(ModalSmem) + 64; }
 static size_t expand_smem() { return (size_t)kStages * kChunkBytes + (size_t)kModalMaxChunks * 8192 + sizeof(ModalSmem) + 64; }
 
 int modal_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, sys->num_sms)); }
+static int coarse_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_ctiles, sys->num_sms)); }
+// three resident blocks per SM (registers); more blocks would only lengthen the last block's sum over the block partials
+static int finish_grid(fdb_system* sys) { return (int)std::max<int64_t>(1, std::min<int64_t>(sys->n_tiles, (int64_t)sys->num_sms * 3)); }
+
+// the full-resolution bf16 tiles of V (the uncompressed path; with compression only fdb_modal_apply's reference product asks for them)
+static void modal_ensure_fine(fdb_system* sys) {
+    if (sys->have_fine_v) return;
+    FDB_REQUIRE(sys->modal_x.p != nullptr, "the FP64 modes are gone");
+    sys->modal_v.alloc((size_t)sys->n_tiles * sys->mode_chunks * (kChunkBytes / 2));
+    const int64_t work = sys->n_tiles * 128 * sys->mode_chunks * 16;
+    k_modal_pack<<<grid_for(work, 256), 256, 0, sys->stream>>>(sys->modal_x.p, sys->n_nodes, sys->n_tiles, sys->n_modes, sys->mode_chunks, sys->modal_v.p);
+    FDB_CUDA(cudaGetLastError());
+    sys->have_fine_v = true;
+}
 
 void modal_prepare(fdb_system* sys, SweepWork* w) {
     FDB_REQUIRE(sys->have_modes && sys->n_modes > 0, "no modes: call fdb_modal_compute or fdb_modal_set first");
     FDB_REQUIRE(sys->tile_rows == 128 && sys->n_tiles > 0, "the modal correction needs the 128-row tiles of the internal order");
     w->c_part.alloc((size_t)modal_grid(sys) * kModalMaxModes * 16);
     w->e_img.alloc((size_t)kModalMaxChunks * 4096);
+    if (sys->modal_compress) {
+        w->fused_precond = true;   // t = Phi^T r exists only inside the fused kernel
+        w->tcv.alloc((size_t)sys->n_ctiles * 128 * 16);
+        w->uc.alloc((size_t)sys->n_ctiles * 128 * 16);
+        w->tcv.zero(sys->stream);  // the rows that pad the last coarse tile
+    } else {
+        modal_ensure_fine(sys);
+    }
     static thread_local bool done[64] = {};
     FDB_REQUIRE(sys->device >= 0 && sys->device < 64, "device index out of range");
     if (!done[sys->device]) {
@@ -726,6 +1103,11 @@ void modal_prepare(fdb_system* sys, SweepWork* w) {
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
         FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_modal_expand<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
+        FDB_CUDA(cudaFuncSetAttribute(k_precond_fused<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(true)));
         done[sys->device] = true;
     }
 }
@@ -746,23 +1128,35 @@ int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz) {
 void modal_precond_fused(fdb_system* sys, SweepWork* w, bool start) {
     FDB_REQUIRE(sys->blk_inv16.p != nullptr, "bf16 block inverses missing");
     const int G = modal_grid(sys);
+    const bool coarse = sys->modal_compress;
     auto go = [&](auto kern) {
-        kern<<<G, kModalThreads, fused_smem(), sys->stream>>>((double*)w->r.p, (const double*)w->q.p, sys->blk_inv16.p, w->z32.p, sys->modal_v.p,
-                                                             sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
+        kern<<<G, kModalThreads, fused_smem(coarse), sys->stream>>>((double*)w->r.p, (const double*)w->q.p, sys->blk_inv16.p, w->z32.p, sys->modal_v.p,
+                                                                   sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p, sys->modal_phi.p, w->tcv.p);
     };
+    if (coarse) {
+        if (w->real) { if (start) go(k_precond_fused<true, false, true>); else go(k_precond_fused<false, false, true>); }
+        else { if (start) go(k_precond_fused<true, true, true>); else go(k_precond_fused<false, true, true>); }
+        return;
+    }
     if (w->real) { if (start) go(k_precond_fused<true, false>); else go(k_precond_fused<false, false>); }
     else { if (start) go(k_precond_fused<true, true>); else go(k_precond_fused<false, true>); }
 }
 int64_t modal_fused_bytes(fdb_system* sys, SweepWork* w, int modes_use) {
     const int64_t vec = (int64_t)w->N * kModalCols;
-    return modal_bytes(sys, w, modes_use, 1) + 2 * 8 * vec /* q in, r out */ + 4 * vec /* z32 out */ + sys->n_tiles * (int64_t)kChunkBytes /* B_t */;
+    const int64_t rest = 2 * 8 * vec /* q in, r out */ + 4 * vec /* z32 out */ + sys->n_tiles * (int64_t)kChunkBytes /* B_t */;
+    if (sys->modal_compress) return 8 * vec /* r in */ + rest + sys->n_tiles * (int64_t)kPhiBytes + sys->nc_rows * 16 * 8 /* t out */;
+    return modal_bytes(sys, w, modes_use, 1) + rest;
 }
 
 // parts: 1 = projection, 2 = coefficients, 4 = expansion (bench.py times them one at a time)
 void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts) {
-    const int G = modal_grid(sys);
+    const bool coarse = sys->modal_compress;
+    const int G = coarse ? coarse_grid(sys) : modal_grid(sys);
     const double* r = (const double*)w->r.p;
-    if (parts & 1)
+    if ((parts & 1) && coarse)
+        k_modal_project<<<G, kModalThreads, project_smem(), sys->stream>>>(w->tcv.p, sys->modal_vc.p, sys->mode_chunks, sys->nc_rows, sys->n_ctiles, w->sc.p,
+                                                                          w->c_part.p);
+    else if (parts & 1)
         k_modal_project<<<G, kModalThreads, project_smem(), sys->stream>>>(r, sys->modal_v.p, sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p);
     const int cg = grid_for((int64_t)sys->mode_chunks * kMC * 16, 256);
     if (!(parts & 2)) {
@@ -772,8 +1166,21 @@ void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int pa
     else
         k_modal_coef<true><<<cg, 256, 0, sys->stream>>>(w->c_part.p, G, sys->modal_lam.p, sys->modal_res.p, sys->n_modes, sys->modal_adiag.p, w->coef.p,
                                                        overlay ? sys->n_groups : 0, w->F, w->sc.p, w->e_img.p);
-    if (!(parts & 4)) return;
     double* part = (double*)w->partial.p;
+    if (coarse) {
+        if (parts & 4)
+            k_modal_expand<false, false, true><<<G, kModalThreads, expand_smem(), sys->stream>>>(nullptr, w->uc.p, nullptr, sys->modal_vc.p, sys->mode_chunks,
+                                                                                                w->e_img.p, sys->nc_rows, sys->n_ctiles, w->sc.p, part);
+        if (parts & 8) {
+            auto fin = [&](auto kern) {
+                kern<<<finish_grid(sys), kCfThreads, 0, sys->stream>>>(r, w->z32.p, (double*)w->p.p, sys->modal_phi.p, w->uc.p, w->N, sys->n_tiles, w->sc.p, part);
+            };
+            if (w->real) { if (start) fin(k_coarse_finish<false, true>); else fin(k_coarse_finish<false, false>); }
+            else { if (start) fin(k_coarse_finish<true, true>); else fin(k_coarse_finish<true, false>); }
+        }
+        return;
+    }
+    if (!(parts & 4)) return;
     auto go = [&](auto kern) {
         kern<<<G, kModalThreads, expand_smem(), sys->stream>>>(r, w->z32.p, (double*)w->p.p, sys->modal_v.p, sys->mode_chunks, w->e_img.p, w->N,
                                                               sys->n_tiles, w->sc.p, part);
@@ -785,9 +1192,18 @@ void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int pa
 // Algorithmic bytes of one launch at `modes_use` modes: 2 bytes per node and mode (the bf16 tile stream, whole 8-mode blocks) plus the
 // FP64 residual tile (projection) or the residual, the FP32 z tile read and written and the coefficient image (expansion).
 int64_t modal_bytes(fdb_system* sys, SweepWork* w, int modes_use, int part) {
+    const int64_t vec = (int64_t)w->N * kModalCols;
+    if (sys->modal_compress) {
+        // the coefficient tiles C (2 bytes per coarse unknown and mode), the coarse vectors (16 numbers per tile and column), the tile bases
+        const int64_t vc = sys->n_ctiles * 128 * (int64_t)(((modes_use + 7) / 8) * 8) * 2;
+        const int64_t cvec = sys->nc_rows * 16;
+        if (part == 1) return vc + 8 * cvec;
+        if (part == 4) return vc + 4 * cvec + (int64_t)modes_use * 64;
+        if (part == 8) return 8 * vec + 2 * 4 * vec + sys->n_tiles * (int64_t)kPhiBytes + 4 * cvec;
+        return (int64_t)coarse_grid(sys) * modes_use * 64 + (int64_t)modes_use * 64;
+    }
     const int64_t rows_pad = sys->n_tiles * 128;
     const int64_t v = rows_pad * (int64_t)(((modes_use + 7) / 8) * 8) * 2;
-    const int64_t vec = (int64_t)w->N * kModalCols;
     if (part == 1) return v + 8 * vec;
     if (part == 4) return v + 8 * vec + 2 * 4 * vec + (int64_t)modes_use * 64;
     return (int64_t)modal_grid(sys) * modes_use * 64 + (int64_t)modes_use * 64;   // coefficients: the block partials in, the image out
@@ -1071,6 +1487,53 @@ int modal_estimate(fdb_system* sys, double f_hz) {
 }
 
 // modal_x (FP64 batches) + modal_lam_host -> bf16 tiles, device eigenvalues, per-mode residuals of the consistent pencil
+// which form of the modes the sweep streams: the tile-compressed one (default) or the full-resolution tiles
+void modal_set_compression(fdb_system* sys, bool on) {
+    FDB_REQUIRE(sys->n_modes > 0 && sys->modal_x.p != nullptr, "no modes");
+    const int n_modes = sys->n_modes;
+    if (on && !sys->have_coarse_v) {
+        // tile bases and coefficient tiles (see "Tile-compressed modes")
+        sys->nc_rows = sys->n_tiles * kCF;
+        sys->n_ctiles = (sys->nc_rows + 127) / 128;
+        sys->modal_phi.alloc((size_t)sys->n_tiles * (kPhiBytes / 2));
+        const int nbat = (n_modes + 15) / 16;
+        DevBuf<double> Xc;
+        Xc.alloc((size_t)nbat * sys->nc_rows * 16);
+        static thread_local bool attr_done[64] = {};
+        if (!attr_done[sys->device & 63]) {
+            FDB_CUDA(cudaFuncSetAttribute(k_tile_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_basis_smem()));
+            attr_done[sys->device & 63] = true;
+        }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr;
+        if (verbose) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, sys->stream); }
+        int n_iter = 6;
+        {
+            const char* tune = getenv("FDB_TUNING");
+            if (tune && tune[0] == '1' && getenv("FDB_TILE_ITERS")) n_iter = std::max(0, atoi(getenv("FDB_TILE_ITERS")));
+        }
+        k_tile_basis<<<(unsigned)sys->n_tiles, kTbThreads, tile_basis_smem(), sys->stream>>>(sys->modal_x.p, sys->n_nodes, n_modes, n_iter, sys->modal_phi.p,
+                                                                                            Xc.p, sys->nc_rows);
+        if (verbose) {
+            cudaEventRecord(e1, sys->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[fdb modal] tile bases: %lld tiles x %d modes in %.1f ms\n", (long long)sys->n_tiles, n_modes, ms);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        sys->modal_vc.alloc((size_t)sys->n_ctiles * sys->mode_chunks * (kChunkBytes / 2));
+        const int64_t work = sys->n_ctiles * 128 * sys->mode_chunks * 16;
+        k_modal_pack<<<grid_for(work, 256), 256, 0, sys->stream>>>(Xc.p, sys->nc_rows, sys->n_ctiles, n_modes, sys->mode_chunks, sys->modal_vc.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cudaStreamSynchronize(sys->stream));   // Xc goes out of scope
+        sys->have_coarse_v = true;
+    }
+    if (!on) modal_ensure_fine(sys);
+    sys->modal_compress = on;
+    invalidate_graph(sys);
+}
+
 void modal_finish(fdb_system* sys, int n_modes) {
     FDB_REQUIRE(sys->have_order && sys->tile_rows == 128, "the modal correction needs the 128-row tiles of the internal order");
     n_modes = std::min(n_modes, kModalMaxModes);
@@ -1079,10 +1542,13 @@ void modal_finish(fdb_system* sys, int n_modes) {
     sys->mode_chunks = (n_modes + kMC - 1) / kMC;
     sys->modal_lam.alloc(n_modes);
     FDB_CUDA(cudaMemcpyAsync(sys->modal_lam.p, sys->modal_lam_host.data(), n_modes * sizeof(double), cudaMemcpyHostToDevice, sys->stream));
-    sys->modal_v.alloc((size_t)sys->n_tiles * sys->mode_chunks * (kChunkBytes / 2));
-    const int64_t work = sys->n_tiles * 128 * sys->mode_chunks * 16;
-    k_modal_pack<<<grid_for(work, 256), 256, 0, sys->stream>>>(sys->modal_x.p, sys->n_nodes, sys->n_tiles, n_modes, sys->mode_chunks, sys->modal_v.p);
-    FDB_CUDA(cudaGetLastError());
+    sys->have_fine_v = false;
+    sys->have_coarse_v = false;
+    {
+        const char* tune = getenv("FDB_TUNING");
+        const char* e = (tune && tune[0] == '1') ? getenv("FDB_MODAL_COMPRESS") : nullptr;
+        modal_set_compression(sys, !(e && atoi(e) == 0));
+    }
     // How far each stored vector is from an eigenvector: k_modal_coef bounds 1 / (lambda - w^2) by it, so an inaccurate mode that a
     // drive frequency comes close to is deflated only as far as it can be trusted.
     double mass_scale, b_up;

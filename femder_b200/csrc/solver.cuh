@@ -66,6 +66,8 @@ struct SweepWork {
     int precond = 0;              // 0 Jacobi, 1 block-Jacobi (16 real columns per row at most, 128-row tiles), 2 block-Jacobi + modal
     int graph_precond = 0;
     DevBuf<float> c_part;         // modal: per-block partial projections [grid][kModalMaxModes][16]
+    DevBuf<double> tcv;           // modal, tile-compressed: t = Phi^T r [16 n_tiles (padded to 128)][16]
+    DevBuf<float> uc;             // modal, tile-compressed: u = C e  [16 n_tiles (padded to 128)][16]
     DevBuf<uint16_t> e_img;       // modal: coefficients e = D V^T r as the bf16 (hi, lo) operand image of the expansion
     ChebEpilogue cheb;            // modal set-up: the SpMV writes a Chebyshev filter step (see k_spmv_blob)
     bool fused_precond = true;    // modal: K6a + projection as one tensor-core kernel (k_precond_fused); false = k_update_bj + k_modal_project
@@ -241,8 +243,11 @@ __device__ __forceinline__ void fin_start(Scalars* __restrict__ sc, int ff, cons
 // ---- modal.cu: the modal coarse correction inside a solver iteration ----
 constexpr int kModalCols = 16;   // real columns per row the tensor-core kernels are built for (16 real or 8 complex slots)
 void modal_prepare(fdb_system* sys, SweepWork* w);
+void modal_set_compression(fdb_system* sys, bool on);
 int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz);
-void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts = 7);   // c = V^T r ; e = d c ; z += V e, rho', ||r||^2, finalisation
+// parts: 1 c = V^T r ; 2 e = d c ; 4 z += V e, rho', ||r||^2, finalisation.  Tile-compressed modes: 1 c = C^T t (t from
+// modal_precond_fused) ; 2 e = d c ; 4 u = C e ; 8 z += Phi u, rho', ||r||^2, finalisation
+void modal_apply(fdb_system* sys, SweepWork* w, bool overlay, bool start, int parts = 15);
 int64_t modal_bytes(fdb_system* sys, SweepWork* w, int modes_use, int part);
 void modal_precond_fused(fdb_system* sys, SweepWork* w, bool start);   // r -= alpha q ; z = B r ; c = V^T r  (one tcgen05 kernel)
 int64_t modal_fused_bytes(fdb_system* sys, SweepWork* w, int modes_use);

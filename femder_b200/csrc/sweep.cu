@@ -1546,7 +1546,8 @@ struct Launch {
         spmv(sys, w, w->p.p, w->q.p, true, overlay);
         if (w->precond == 2 && w->fused_precond) {
             modal_precond_fused(sys, w, false);          // K6a + projection on the tensor cores
-            modal_apply(sys, w, overlay, false, 2 | 4);  // coefficients, expansion + scalars
+            // coefficients, expansion + scalars (tile-compressed modes: coarse projection, coefficients, coarse expansion, z += Phi u + scalars)
+            modal_apply(sys, w, overlay, false, sys->modal_compress ? 15 : (2 | 4));
         } else {
             vec_kernel_t<T>(sys, w, overlay, 1);
             if (w->precond == 2) modal_apply(sys, w, overlay, false);
@@ -1590,8 +1591,8 @@ struct Launch {
         bool started = false;
         if (w->precond == 2 && w->fused_precond) {
             modal_precond_fused(sys, w, true);
-            modal_apply(sys, w, overlay, true, 2 | 4);
-            nk += 2;
+            modal_apply(sys, w, overlay, true, sys->modal_compress ? 15 : (2 | 4));
+            nk += sys->modal_compress ? 4 : 2;
             started = true;
         } else {
             if (w->precond >= 1) started = bj_update<T>(sys, w, true);
@@ -2079,7 +2080,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         }
         FDB_CUDA(cudaGraphLaunch(w->graph, s));
         n_spmv += check_every;
-        n_kernels += (use_modal ? (w->fused_precond ? 5 : 6) : 3) * (int64_t)check_every;
+        n_kernels += (use_modal ? (sys->modal_compress ? 7 : (w->fused_precond ? 5 : 6)) : 3) * (int64_t)check_every;
         FDB_CUDA(cudaMemcpyAsync(&h, w->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         FDB_CUDA(cudaStreamSynchronize(s));
         FDB_CUDA(cudaGetLastError());
@@ -2291,6 +2292,7 @@ void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const doub
     SweepWork* w = modal_spmv_begin(sys);
     w->precond = 2;
     { bool okb = false; FDB_DISPATCH_F(kModalCols, bj_supported(w, &okb)); (void)okb; }
+    if (sys->modal_compress) { FDB_DISPATCH_F(kModalCols, bj_prepare(sys, w)); }   // the fused kernel that forms t = Phi^T r also multiplies by B_t
     w->z32.alloc((size_t)w->N * kModalCols);
     modal_prepare(sys, w);
     std::vector<double> om(kModalCols);
@@ -2298,7 +2300,10 @@ void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const doub
     Scalars h;
     memset(&h, 0, sizeof(h));
     std::vector<double2> coef((size_t)std::max(1, w->n_groups) * kModalCols, make_double2(0.0, 0.0));
-    for (int f = 0; f < kModalCols; ++f) fill_slot(h, coef, kModalCols, w->n_groups, f, om[f], nullptr, 0.0);
+    for (int f = 0; f < kModalCols; ++f) {
+        fill_slot(h, coef, kModalCols, w->n_groups, f, om[f], nullptr, 0.0);
+        h.reset[f] = 1;   // tile-compressed modes: every column of r takes part in the slot-load flavour of the fused kernel
+    }
     h.tol2 = 1.0;
     h.modes_use = std::min(((std::max(n_use, 1) + 15) / 16) * 16, sys->mode_chunks * 128);
     upload_scalars(sys, w, h, coef);
@@ -2307,6 +2312,7 @@ void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const doub
     double* tmp = (double*)w->tmp.p;
     FDB_CUDA(cudaMemcpyAsync(tmp, r, n * sizeof(double), cudaMemcpyDefault, sys->stream));
     k_permute_rows<double><<<pg, kBlock, 0, sys->stream>>>(tmp, (double*)w->r.p, sys->perm.p, kModalCols, w->N, true);
+    if (sys->modal_compress) modal_precond_fused(sys, w, true);   // t = Phi^T r (its block-Jacobi product is discarded)
     FDB_CUDA(cudaMemsetAsync(w->z32.p, 0, n * sizeof(float), sys->stream));
     modal_apply(sys, w, false, false);
     k_z32_to_f64<<<pg, kBlock, 0, sys->stream>>>(w->z32.p, (int64_t)n, (double*)w->q.p);
@@ -2438,6 +2444,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
         else if (which == 3) modal_apply(sys, w, false, false, 1);
         else if (which == 4) modal_apply(sys, w, false, false, 4);
         else if (which == 5) modal_apply(sys, w, false, false, 2);
+        else if (which == 6) modal_apply(sys, w, false, false, 8);
         else { FDB_DISPATCH_F(F, vec_kernel(sys, w, false, which)); }
     }
     FDB_CUDA(cudaGetLastError());
@@ -2447,6 +2454,7 @@ void run_iteration_enqueue(fdb_system* sys, int F, int reps, int flags, int whic
         else if (which == 3) *bytes = modal_bytes(sys, w, modes_all, 1);
         else if (which == 4) *bytes = modal_bytes(sys, w, modes_all, 4);
         else if (which == 5) *bytes = modal_bytes(sys, w, modes_all, 2);
+        else if (which == 6) *bytes = sys->modal_compress ? modal_bytes(sys, w, modes_all, 8) : 0;
         else if (which == 1) *bytes = bj ? 3 * vb + 4 * ne + sys->n_tiles * (int64_t)kBjPacked * 4 : 3 * vb + 16 * N;
         else *bytes = bj ? 4 * vb + 4 * ne : 5 * vb + 16 * N;
     }

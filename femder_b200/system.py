@@ -269,6 +269,10 @@ class System:
         check(self._lib.fdb_modal_estimate(self._h, float(f), C.byref(n)))
         return n.value
 
+    def modal_compression(self, on=True):
+        """Stream the modes tile-compressed (default: 16 basis functions per 128-node tile) or at full resolution."""
+        check(self._lib.fdb_modal_compression(self._h, 1 if on else 0))
+
     @staticmethod
     def comm_unique_id():
         """128 bytes identifying a new group of ranks (one rank creates it, all ranks pass it to :meth:`comm_init`)."""

@@ -163,6 +163,10 @@ int fdb_sizeof_sweep_result(void);
  *              reached on coarse meshes; fdb_modal_info reports what was.
  *   n_modes_hint  expected number of modes below f_cut_hz (sizes the block; 0 = find out by widening) */
 int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found);
+/* The form in which fdb_sweep streams the modes.  on = 1 (the default after fdb_modal_compute / fdb_modal_set): tile-compressed -
+ * per 128-node tile V_t ~ Phi_t C_t with 16 basis functions, ~0.55 bytes per node and mode and iteration instead of 4, same iteration
+ * counts (csrc/modal.cu "Tile-compressed modes").  on = 0: the full-resolution bf16 tiles. */
+int fdb_modal_compression(fdb_system* sys, int on);
 /* Several GPUs, one process each, sweeping shares of the same frequency list over the same room (the reference's frequency loop,
  * femder/FEM_3D.py:1304-1319, has independent iterations): they all need the same modes, so they can share the work of finding them.
  * One rank creates an id (fdb_comm_unique_id, 128 bytes) and hands it to the others by whatever means the host program has; every
