@@ -628,18 +628,18 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                         accf[j][2] = fmaf(g, v.z, accf[j][2]);
                         accf[j][3] = fmaf(g, v.w, accf[j][3]);
                     }
-                    continue;
-                }
+                } else {
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
-                    if constexpr (CPX) {
-                        const double g = m.x - w2v[j][0] * m.y;
-                        acc[j][0] += g * v.x;
-                        acc[j][1] += g * v.y;
-                    } else {
-                        acc[j][0] += (m.x - w2v[j][0] * m.y) * v.x;
-                        acc[j][1] += (m.x - w2v[j][1] * m.y) * v.y;
+                    for (int j = 0; j < NCH; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(xr + choff[j]);
+                        if constexpr (CPX) {
+                            const double g = m.x - w2v[j][0] * m.y;
+                            acc[j][0] += g * v.x;
+                            acc[j][1] += g * v.y;
+                        } else {
+                            acc[j][0] += (m.x - w2v[j][0] * m.y) * v.x;
+                            acc[j][1] += (m.x - w2v[j][1] * m.y) * v.y;
+                        }
                     }
                 }
             }

@@ -15,10 +15,12 @@ cap() {  # name, kernel regex, script args
   echo "$1 capture rc=$?"; tail -1 gpurun_out/plain_$1.log
   ncu -i gpurun_out/$1_$R.ncu-rep --page raw --csv > gpurun_out/$1_$R.raw.csv 2>/dev/null
 }
-cap modal_expand k_modal_expand "--which 4"
 cap precond_fused k_precond_fused "--which 1"
+cap coarse_finish k_coarse_finish "--which 6"
+cap coarse_project k_modal_project "--which 3"
+cap coarse_expand k_modal_expand "--which 4"
 cap spmv_real16 k_spmv_blob "--which 0 --modal 0"
 cap pupdate_bj_real16 k_pupdate_bj "--which 2 --modal 0"
 # gpurun merges at most 64 MiB back: keep the two reports worth opening with the source page, the others as raw CSV
-rm -f gpurun_out/pupdate_bj_real16_$R.ncu-rep gpurun_out/spmv_real16_$R.ncu-rep
+rm -f gpurun_out/pupdate_bj_real16_$R.ncu-rep gpurun_out/spmv_real16_$R.ncu-rep gpurun_out/coarse_project_$R.ncu-rep gpurun_out/coarse_expand_$R.ncu-rep
 ls -la gpurun_out | grep $R
