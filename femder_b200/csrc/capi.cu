@@ -399,7 +399,7 @@ int fdb_modal_compression(fdb_system* sys, int on) {
     FDB_API_BEGIN
     FDB_SYS_MUT(sys);
     FDB_REQUIRE(sys->have_modes, "no modes");
-    fdb::modal_set_compression(sys, on != 0);
+    fdb::modal_set_compression(sys, on != 0, on == 2);
     FDB_API_END
 }
 

@@ -168,6 +168,7 @@ struct fdb_system {
     fdb::DevBuf<uint16_t> modal_v;     // bf16 [n_tiles][mode_chunks][16 mode blocks][16 node blocks][8 nodes][8 modes]
     // tile-compressed modes (modal.cu): V_t ~ Phi_t C_t per 128-node tile
     bool modal_compress = false;       // the sweep streams Phi and C instead of V
+    double modal_fit_worst = 0.0;      // worst relative fit error of a mode in the compressed form
     bool have_coarse_v = false;        // modal_phi / modal_vc are built
     bool have_fine_v = false;          // modal_v is packed (always without compression; on demand with it)
     int64_t nc_rows = 0, n_ctiles = 0; // coarse unknowns (16 per tile) and their 128-row tiles

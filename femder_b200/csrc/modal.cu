@@ -38,6 +38,7 @@ constexpr int kModalThreads = 192;             // warp 0 producer, warp 1 MMA is
 constexpr uint32_t kSm = 2048, kSn = 128;      // byte strides of a chunk: mode block (8 modes), node block (8 nodes)
 constexpr int kCF = 16;                        // functions of a tile basis (tile-compressed modes)
 constexpr int kPhiBytes = 128 * kCF * 2;       // one tile basis in the chunk layout: the first two "mode blocks", 4 KB
+constexpr double kMaxFitError = 1.5e-2;        // worst relative fit error of a mode above which the tile-compressed form is not used
 // k_modal_coef keeps |lambda - w^2| >= res^2 / lambda (res = the stored vector's residual): below that the inexact vector cannot
 // tell which side of the resonance the drive frequency is on.  Nothing coarser: a bound proportional to res itself was tried
 // and makes V diag(d) V^T stop being the inverse of G on span(V), which the indefinite CG recurrence does not survive
@@ -812,7 +813,7 @@ __device__ void tb_orthonormalise(double* A, double* s_w, double* s_d) {
 
 __global__ void __launch_bounds__(kTbThreads, 1)
 k_tile_basis(const double* __restrict__ X, int64_t n_rows, int n_modes, int n_iter, uint16_t* __restrict__ phi16, double* __restrict__ Xc,
-             int64_t nc_rows) {
+             int64_t nc_rows, double* __restrict__ fit /* [n_modes][2]: squared fit error and squared norm of every mode, summed over the tiles */) {
     extern __shared__ __align__(16) unsigned char tb_raw[];
     double* G = reinterpret_cast<double*>(tb_raw);   // [128][kTbGs]
     double* blk = G + 128 * kTbGs;                   // [128][kTbPs]  one panel's rows of the tile
@@ -937,6 +938,34 @@ k_tile_basis(const double* __restrict__ X, int64_t n_rows, int n_modes, int n_it
         double sacc = 0.0;
         for (int node = 0; node < 128; ++node) sacc = fma(Y[node * kTbPs + kk], blk[node * kTbPs + cc], sacc);
         Xc[((int64_t)bt * nc_rows + t * kCF + kk) * 16 + cc] = sacc;
+        // what the compressed form loses of this panel's modes on this tile: || V_t - Phi_b C_t ||^2 per mode (the host decides from
+        // the sums over all tiles whether the tiles are small enough against the shortest wavelength for 16 functions)
+        M[kk * 16 + cc] = sacc;
+        __syncthreads();
+        double e2[8], n2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double v = blk[i * kTbPs + 8 * half + c];
+            double rec = 0.0;
+#pragma unroll
+            for (int k = 0; k < kCF; ++k) rec = fma(P[i * kTbPs + k], M[k * 16 + 8 * half + c], rec);
+            e2[c] = (v - rec) * (v - rec);
+            n2[c] = v * v;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                e2[c] += __shfl_xor_sync(0xffffffffu, e2[c], o);
+                n2[c] += __shfl_xor_sync(0xffffffffu, n2[c], o);
+            }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int mode = 16 * bt + 8 * half + c;
+                if (mode < n_modes) { atomicAdd(&fit[2 * mode], e2[c]); atomicAdd(&fit[2 * mode + 1], n2[c]); }
+            }
+        }
     }
 }
 
@@ -1530,7 +1559,7 @@ int modal_estimate(fdb_system* sys, double f_hz) {
 
 // modal_x (FP64 batches) + modal_lam_host -> bf16 tiles, device eigenvalues, per-mode residuals of the consistent pencil
 // which form of the modes the sweep streams: the tile-compressed one (default) or the full-resolution tiles
-void modal_set_compression(fdb_system* sys, bool on) {
+void modal_set_compression(fdb_system* sys, bool on, bool force) {
     FDB_REQUIRE(sys->n_modes > 0 && sys->modal_x.p != nullptr, "no modes");
     const int n_modes = sys->n_modes;
     if (on && !sys->have_coarse_v) {
@@ -1554,8 +1583,13 @@ void modal_set_compression(fdb_system* sys, bool on) {
             const char* tune = getenv("FDB_TUNING");
             if (tune && tune[0] == '1' && getenv("FDB_TILE_ITERS")) n_iter = std::max(0, atoi(getenv("FDB_TILE_ITERS")));
         }
+        DevBuf<double> fit;
+        fit.alloc((size_t)2 * n_modes);
+        fit.zero(sys->stream);
         k_tile_basis<<<(unsigned)sys->n_tiles, kTbThreads, tile_basis_smem(), sys->stream>>>(sys->modal_x.p, sys->n_nodes, n_modes, n_iter, sys->modal_phi.p,
-                                                                                            Xc.p, sys->nc_rows);
+                                                                                            Xc.p, sys->nc_rows, fit.p);
+        std::vector<double> hfit((size_t)2 * n_modes);
+        FDB_CUDA(cudaMemcpyAsync(hfit.data(), fit.p, hfit.size() * sizeof(double), cudaMemcpyDeviceToHost, sys->stream));
         if (verbose) {
             cudaEventRecord(e1, sys->stream);
             cudaEventSynchronize(e1);
@@ -1570,7 +1604,16 @@ void modal_set_compression(fdb_system* sys, bool on) {
         FDB_CUDA(cudaGetLastError());
         FDB_CUDA(cudaStreamSynchronize(sys->stream));   // Xc goes out of scope
         sys->have_coarse_v = true;
+        double worst = 0.0;
+        for (int i2 = 0; i2 < n_modes; ++i2)
+            if (hfit[2 * i2 + 1] > 0.0) worst = std::max(worst, std::sqrt(hfit[2 * i2] / hfit[2 * i2 + 1]));
+        sys->modal_fit_worst = worst;
+        if (getenv("FDB_MODAL_VERBOSE")) fprintf(stderr, "[fdb modal] tile-compressed modes: worst relative fit error %.3e\n", worst);
     }
+    // 16 functions per tile describe the modes only while a tile is small against the shortest wavelength (fit error 3e-3 on the 1M-DOF
+    // room's highest mode; at 1e-2 the sweep starts to pay in iterations, tests/research/compressed_modes_prototype.py): a mesh too
+    // coarse for that keeps the full-resolution tiles
+    if (on && !force && sys->modal_fit_worst > kMaxFitError) on = false;
     if (!on) modal_ensure_fine(sys);
     sys->modal_compress = on;
     invalidate_graph(sys);
@@ -1589,7 +1632,7 @@ void modal_finish(fdb_system* sys, int n_modes) {
     {
         const char* tune = getenv("FDB_TUNING");
         const char* e = (tune && tune[0] == '1') ? getenv("FDB_MODAL_COMPRESS") : nullptr;
-        modal_set_compression(sys, !(e && atoi(e) == 0));
+        modal_set_compression(sys, !(e && atoi(e) == 0), e && atoi(e) == 2);
     }
     // How far each stored vector is from an eigenvector: k_modal_coef bounds 1 / (lambda - w^2) by it, so an inaccurate mode that a
     // drive frequency comes close to is deflated only as far as it can be trusted.
@@ -1730,6 +1773,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     const bool locking = tuning && getenv("FDB_MODAL_LOCK") && atoi(getenv("FDB_MODAL_LOCK")) != 0;   // off: measured below
     const double lock_tol = (tuning && getenv("FDB_MODAL_LOCK_TOL")) ? atof(getenv("FDB_MODAL_LOCK_TOL")) : tol / 8.0;
     const bool f32_active = tuning && getenv("FDB_MODAL_F32_ACTIVE") && atoi(getenv("FDB_MODAL_F32_ACTIVE")) != 0;   // single precision for unlocked columns throughout
+    const double first_mult = (tuning && getenv("FDB_MODAL_DEG1")) ? atof(getenv("FDB_MODAL_DEG1")) : 2.0;
     const double growth = (tuning && getenv("FDB_MODAL_GROWTH")) ? atof(getenv("FDB_MODAL_GROWTH")) : 0.05;
     DevBuf<double> dinv_mass;   // 1 / (mass_scale * Q_rr)
     dinv_mass.alloc(N);
@@ -1776,7 +1820,10 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             // sum_{j <= t} (1 - x)^j <= t + 1 on the mass spectrum x in (0, 1]: a safe upper end for the spectrum of Qt^-1 H (components
             // above the filter's interval would be amplified, not damped)
             const double a = a_low, b = b_up * (1.0 + order_t);
-            const int deg = (int)std::max(12.0, std::min(160.0, std::ceil(3.0 * std::sqrt(b / a))));
+            // the first pass starts from noise: twice the degree there replaces the first two passes and the Rayleigh-Ritz step between
+            // them (the amplification ratio between the lowest modes and those next to the cut stays inside single precision)
+            const double deg_mult = (outer == 0 && !have_ritz) ? first_mult : 1.0;
+            const int deg = (int)std::max(12.0, std::min(160.0, std::ceil(3.0 * deg_mult * std::sqrt(b / a))));
             const double e = 0.5 * (b - a), c = 0.5 * (b + a);
             // two panels at once in single precision (see use_f32): T and Y hold the 32-column single-precision iterates
             auto filter_pair_f32 = [&](int bt) -> bool {

@@ -271,7 +271,7 @@ class System:
 
     def modal_compression(self, on=True):
         """Stream the modes tile-compressed (default: 16 basis functions per 128-node tile) or at full resolution."""
-        check(self._lib.fdb_modal_compression(self._h, 1 if on else 0))
+        check(self._lib.fdb_modal_compression(self._h, 2 if on == "force" else (1 if on else 0)))
 
     @staticmethod
     def comm_unique_id():

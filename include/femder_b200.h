@@ -165,7 +165,9 @@ int fdb_sizeof_sweep_result(void);
 int fdb_modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_modes_hint, double tol, int max_outer, int* n_modes_found);
 /* The form in which fdb_sweep streams the modes.  on = 1 (the default after fdb_modal_compute / fdb_modal_set): tile-compressed -
  * per 128-node tile V_t ~ Phi_t C_t with 16 basis functions, ~0.55 bytes per node and mode and iteration instead of 4, same iteration
- * counts (csrc/modal.cu "Tile-compressed modes").  on = 0: the full-resolution bf16 tiles. */
+ * counts (csrc/modal.cu "Tile-compressed modes") - unless the mesh is so coarse that 16 functions per tile miss a mode by more than
+ * 1.5 % (the tiles are then not small against the shortest wavelength), in which case the full-resolution tiles stay in use.
+ * on = 2: compressed regardless of the fit.  on = 0: the full-resolution bf16 tiles. */
 int fdb_modal_compression(fdb_system* sys, int on);
 /* Several GPUs, one process each, sweeping shares of the same frequency list over the same room (the reference's frequency loop,
  * femder/FEM_3D.py:1304-1319, has independent iterations): they all need the same modes, so they can share the work of finding them.

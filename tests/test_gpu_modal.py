@@ -65,7 +65,7 @@ def test_tile_compressed_modes_match_the_exact_operator(room):
     noise, where the tile bases see only their own span of r, it stays a small perturbation of the exact operator."""
     s, lam, V, Q = room["sys"], room["lam"], room["V"], room["Q"]
     s.modal_set(lam, V)
-    s.modal_compression(True)
+    s.modal_compression("force")        # whatever the fit on this small mesh (the default falls back to the full tiles above 1.5 %)
     N = V.shape[1]
     rng = np.random.default_rng(1)
     f = np.linspace(55.0, 190.0, 16)
@@ -82,7 +82,7 @@ def test_tile_compressed_modes_match_the_exact_operator(room):
         assert err.max() < tol, err
     s.modal_compression(False)
     z_fine = s.modal_apply(om, m, r_smooth)
-    s.modal_compression(True)
+    s.modal_compression("force")
     z_comp = s.modal_apply(om, m, r_smooth)
     assert (np.linalg.norm(z_comp - z_fine, axis=0) / np.linalg.norm(z_fine, axis=0)).max() < 2e-2
 
