@@ -35,6 +35,7 @@ constexpr int kModalMaxModes = kMC * kModalMaxChunks;
 constexpr int kChunkBytes = 128 * kMC * 2;     // one tile of V for one chunk of modes: 32 KB
 constexpr int kStages = 4;                     // ring of V chunks in shared memory
 constexpr int kModalThreads = 192;             // warp 0 producer, warp 1 MMA issue + TMEM owner, warps 2..5 operand / epilogue
+constexpr int kFusedThreads = 64 + 2 * 128;    // k_precond_fused: two groups of operand / epilogue warps
 constexpr uint32_t kSm = 2048, kSn = 128;      // byte strides of a chunk: mode block (8 modes), node block (8 nodes)
 constexpr int kCF = 16;                        // functions of a tile basis (tile-compressed modes)
 constexpr int kPhiBytes = 128 * kCF * 2;       // one tile basis in the chunk layout: the first two "mode blocks", 4 KB
@@ -264,7 +265,7 @@ k_modal_project(const double* __restrict__ r, const uint16_t* __restrict__ V, in
 // ------------------------------------------------------------------------------------------------
 struct FusedSmem {
     uint64_t s_full[kStages], s_empty[kStages];   // ring of B_t and V chunks: filled by the producer, consumed IN ORDER by the MMA thread
-    uint64_t rq_full[2], rq_empty[2];             // [r | q] tiles: consumed by the converter warps.  (A consumer that skipped phases of a
+    uint64_t rq_full[4], rq_empty[4];             // [r | q] tiles: consumed by the converter warps.  (A consumer that skipped phases of a
                                                   // shared ring could not tell them apart by parity: each consumer has its own barriers.)
     uint64_t b_full[2], b_empty[2];
     uint64_t z_full[2], z_empty[2];
@@ -280,18 +281,23 @@ struct FusedSmem {
 // Phi_t sits at the start of a 32 KB operand extent whose remaining rows are whatever shared memory holds: they only feed
 // accumulator rows nobody reads.
 template <bool START, bool CPX, bool COARSE = false>
-__global__ void __launch_bounds__(kModalThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint16_t* __restrict__ binv16, float* __restrict__ z32,
                 const uint16_t* __restrict__ V, int n_chunks, int64_t n_rows, int64_t n_tiles, const Scalars* __restrict__ sc,
                 float* __restrict__ c_part, const uint16_t* __restrict__ phi16, double* __restrict__ tc) {
     constexpr int F = CPX ? 8 : 16;
     constexpr uint32_t kZCol = 32 * kModalMaxChunks;   // TMEM columns: [0, 256) projection accumulators, [256, 320) two z_bj accumulators
     constexpr uint32_t kTCol = kZCol + 64;             // COARSE: [320, 384) two t accumulators
+    // shared memory: six 32 KB buffers.  With V chunks in the ring it takes four of them and [r | q] is double-buffered; the COARSE
+    // ring carries one item per tile (B_t), so two slots do and [r | q] gets four: three tiles of vectors in flight ahead of the
+    // converter warps, whose per-tile work is one long dependent chain
+    constexpr int RS = COARSE ? 2 : kStages;           // ring slots
+    constexpr int RQ = COARSE ? 4 : 2;                 // [r | q] buffers
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* phis = smem_raw;                                      // COARSE: [2][4 KB] tile bases (reads run on into the ring)
     unsigned char* ring = smem_raw + (COARSE ? 2 * kPhiBytes : 0);       // [kStages][32 KB]
-    unsigned char* rqbuf = ring + (size_t)kStages * kChunkBytes;         // [2][32 KB]: r (16 KB) | q (16 KB)
-    unsigned char* bimg = rqbuf + 2 * (size_t)kChunkBytes;               // [2][8 KB]
+    unsigned char* rqbuf = ring + (size_t)RS * kChunkBytes;              // [RQ][32 KB]: r (16 KB) | q (16 KB)
+    unsigned char* bimg = rqbuf + RQ * (size_t)kChunkBytes;              // [2][8 KB]
     FusedSmem* sm = reinterpret_cast<FusedSmem*>(bimg + 2 * 8192);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n_use, ksteps_last;
@@ -301,8 +307,8 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
     const uint32_t items = 1u + (uint32_t)n_use;   // ring items per tile: B_t, then the V chunks
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sm->s_full[i], 1); mbar_init(&sm->s_empty[i], 1); }
+        for (int i = 0; i < RQ; ++i) { mbar_init(&sm->rq_full[i], 1); mbar_init(&sm->rq_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm->rq_full[i], 1); mbar_init(&sm->rq_empty[i], 1);
             mbar_init(&sm->b_full[i], 128); mbar_init(&sm->b_empty[i], 1);
             mbar_init(&sm->z_full[i], 1); mbar_init(&sm->z_empty[i], 128);
             mbar_init(&sm->phi_full[i], 1); mbar_init(&sm->phi_empty[i], 1);
@@ -329,19 +335,24 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0, ti = 0;
-            auto slot_for = [&](uint32_t i) { mbar_wait_bounded(&sm->s_empty[i % kStages], ((i / kStages) & 1u) ^ 1u); return (int)(i % kStages); };
-            auto load_rq = [&](int64_t t, uint32_t k) {   // [r | q] of tile t into buffer k & 1
-                const int bb = k & 1;
+            auto slot_for = [&](uint32_t i) { mbar_wait_bounded(&sm->s_empty[i % RS], ((i / RS) & 1u) ^ 1u); return (int)(i % RS); };
+            auto load_rq = [&](int64_t t, uint32_t k) {   // [r | q] of tile t (the block's k-th) into buffer k % RQ
+                const int bb = k % RQ;
                 const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
-                mbar_wait_bounded(&sm->rq_empty[bb], ((k >> 1) & 1u) ^ 1u);
+                mbar_wait_bounded(&sm->rq_empty[bb], ((k / RQ) & 1u) ^ 1u);
                 unsigned char* dst = rqbuf + (size_t)bb * kChunkBytes;
                 mbar_expect_tx(&sm->rq_full[bb], rows * 128u * (START ? 1u : 2u));
                 bulk_g2s(dst, r + t * 128 * 16, rows * 128u, &sm->rq_full[bb]);
                 if (!START) bulk_g2s(dst + 16384, q + t * 128 * 16, rows * 128u, &sm->rq_full[bb]);
             };
-            if ((int64_t)blockIdx.x < n_tiles) load_rq(blockIdx.x, 0);
+            int64_t t_pref = blockIdx.x;
+            uint32_t k_pref = 0;
+            auto prefetch_upto = [&](uint32_t k_limit) {   // the vectors of the block's tiles 0 .. k_limit
+                while (k_pref <= k_limit && t_pref < n_tiles) { load_rq(t_pref, k_pref); t_pref += gridDim.x; ++k_pref; }
+            };
+            prefetch_upto(RQ - 2);
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
-                if (t + gridDim.x < n_tiles) load_rq(t + gridDim.x, ti + 1);   // the next tile's vectors ahead of this tile's mode chunks
+                prefetch_upto(ti + RQ - 1);   // the next tiles' vectors ahead of this tile's block inverse and mode chunks
                 {   // B_t
                     const int st = slot_for(it++);
                     mbar_expect_tx(&sm->s_full[st], (uint32_t)kChunkBytes);
@@ -373,8 +384,8 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
                 const uint32_t b_addr = smem_u32(bimg + bb * 8192);
                 {   // z_bj = B_t r
                     const uint32_t it = it0;
-                    const int st = it % kStages;
-                    mbar_wait_bounded(&sm->s_full[st], (it / kStages) & 1u);
+                    const int st = it % RS;
+                    mbar_wait_bounded(&sm->s_full[st], (it / RS) & 1u);
                     mbar_wait_bounded(&sm->z_empty[bb], ((ti >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
@@ -395,8 +406,8 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
                 }
                 for (int j = 0; j < n_use; ++j) {
                     const uint32_t it = it0 + 1 + j;
-                    const int st = it % kStages;
-                    mbar_wait_bounded(&sm->s_full[st], (it / kStages) & 1u);
+                    const int st = it % RS;
+                    mbar_wait_bounded(&sm->s_full[st], (it / RS) & 1u);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + (size_t)st * kChunkBytes);
 #pragma unroll
@@ -409,7 +420,11 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
             tc_commit(&sm->done);
         }
     } else {
-        const int i = tid - 64;            // node row of the tile this thread converts
+        // Two groups of four converter / epilogue warps take alternate tiles (group = parity of the block's tile counter = the
+        // operand image and accumulator pair the tile uses): a tile's conversion is one long dependent chain, and with a single
+        // warp per scheduler every instruction's latency was exposed (the kernel ran at 0.78 of the HBM rate whatever was in flight).
+        const int grp = (tid - 64) >> 7;
+        const int i = (tid - 64) & 127;    // node row of the tile this thread converts
         const int qd = warp & 3;           // TMEM lanes this warp may read
         const int zrow = qd * 32 + lane;   // ... = the row whose z_bj it stores
         auto epilogue = [&](int64_t t, uint32_t ti) {
@@ -442,14 +457,16 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
                                         acc[4 * k + 3] + acc[19 + 4 * k]);
             }
         };
-        uint32_t ti = 0;
+        uint32_t ti = 0, ti_prev = 0;
         int64_t t_prev = -1;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
             const int bb = ti & 1;
+            if (bb != grp) continue;
             const int64_t row = t * 128 + i;
             const bool valid = row < n_rows;
-            mbar_wait_bounded(&sm->rq_full[bb], (ti >> 1) & 1u);
-            double* rs = reinterpret_cast<double*>(rqbuf + (size_t)bb * kChunkBytes) + i * 16;
+            const int rb = ti % RQ;
+            mbar_wait_bounded(&sm->rq_full[rb], (ti / RQ) & 1u);
+            double* rs = reinterpret_cast<double*>(rqbuf + (size_t)rb * kChunkBytes) + i * 16;
             const double* qs = rs + 2048;
             double v[16];
             // 16-byte chunks of the row, rotated by the row index: the 8 threads of a quarter-warp phase hit 8 different bank groups
@@ -493,26 +510,27 @@ k_precond_fused(double* __restrict__ r, const double* __restrict__ q, const uint
             fence_proxy_async();
             mbar_arrive(&sm->b_full[bb]);
             // the updated residual leaves from the slot it arrived in; the slot goes back to the producer when the store has read it
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             if (i == 0) {
                 if (!START) {
                     const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
-                    bulk_s2g(r + t * 128 * 16, rqbuf + (size_t)bb * kChunkBytes, rows * 128u);
+                    bulk_s2g(r + t * 128 * 16, rqbuf + (size_t)rb * kChunkBytes, rows * 128u);
                     bulk_commit();
                     bulk_wait_read<0>();
                 }
-                mbar_arrive(&sm->rq_empty[bb]);
+                mbar_arrive(&sm->rq_empty[rb]);
             }
-            if (t_prev >= 0) epilogue(t_prev, ti - 1);
+            if (t_prev >= 0) epilogue(t_prev, ti_prev);
             t_prev = t;
+            ti_prev = ti;
         }
-        if (t_prev >= 0) epilogue(t_prev, ti - 1);
+        if (t_prev >= 0) epilogue(t_prev, ti_prev);
         if (i == 0 && !START) bulk_wait<0>();
         // ---- this block's partial projections ----
         mbar_wait_bounded(&sm->done, 0);
         tc_fence_after();
         float* out = c_part + (int64_t)blockIdx.x * kModalMaxModes * 16;
-        for (int j = 0; j < n_use; ++j) {   // (none when COARSE)
+        for (int j = 0; j < (grp == 0 ? n_use : 0); ++j) {   // (none when COARSE)
             float acc[32];
             tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + 32 * j, acc);
             float4* o = reinterpret_cast<float4*>(out + (int64_t)(j * kMC + qd * 32 + lane) * 16);
@@ -1123,6 +1141,129 @@ k_coarse_finish(const double* __restrict__ r, float* z32, double* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6b on 128-byte vector rows (16 real or 8 complex slots): x += alpha p ; p = z + beta p.  Same shape as k_coarse_finish: a
+// producer thread streams tiles (x | p | z, 40 KB) into a ring with bulk copies, eight warps update them in place (two threads
+// per row) and the tiles leave by bulk stores out of the buffers they arrived in.  (The grid-stride version with 8-byte accesses
+// ran at 0.74 of the HBM rate.  A second consumer group on alternate tiles bought nothing here - there is next to no arithmetic
+// to overlap - and with an odd number of stages, where a stage alternates between the groups, it corrupted tiles now and then:
+// in the kernels that do use two groups every buffer always returns to the same group.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kPuThreads = 32 + 256;
+constexpr int kPuStages = 5;
+constexpr int kPuOffP = 16384, kPuOffZ = 32768, kPuStageBytes = 32768 + 8192;
+struct PuSmem {
+    uint64_t full[kPuStages], empty[kPuStages];
+    double2 alpha[16], beta[16];
+    int xpend[16], act[16];
+};
+static size_t pupdate_smem() { return (size_t)kPuStages * kPuStageBytes + sizeof(PuSmem) + 64; }
+
+template <bool CPX>
+__global__ void __launch_bounds__(kPuThreads, 1)
+k_pupdate_tiles(double* x, double* p, const float* __restrict__ z32, int64_t n_rows, int64_t n_tiles, const Scalars* __restrict__ sc) {
+    constexpr int F = CPX ? 8 : 16;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    PuSmem* sm = reinterpret_cast<PuSmem*>(smem_raw + (size_t)kPuStages * kPuStageBytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < kPuStages; ++i) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], 1); }
+        mbar_fence_init();
+    }
+    if (tid < F) {
+        sm->alpha[tid] = sc->alpha[tid];
+        sm->beta[tid] = sc->beta[tid];
+        sm->xpend[tid] = sc->xpend[tid];
+        sm->act[tid] = sc->active[tid];
+    }
+    __syncthreads();
+    bool any = false;
+    for (int f = 0; f < F; ++f) any |= sm->xpend[f] != 0;
+    if (!any) return;   // nothing pending in any slot (uniform)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int st = it % kPuStages;
+                mbar_wait_bounded(&sm->empty[st], ((it / kPuStages) & 1u) ^ 1u);
+                const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
+                unsigned char* dst = smem_raw + (size_t)st * kPuStageBytes;
+                mbar_expect_tx(&sm->full[st], rows * 128u * 2u + rows * 64u);
+                bulk_g2s(dst, x + t * 128 * 16, rows * 128u, &sm->full[st]);
+                bulk_g2s(dst + kPuOffP, p + t * 128 * 16, rows * 128u, &sm->full[st]);
+                bulk_g2s(dst + kPuOffZ, z32 + t * 128 * 16, rows * 64u, &sm->full[st]);
+            }
+        }
+    } else {
+        const int j = tid - 32;
+        const int i = j >> 1, h = j & 1;   // node row of the tile, half of its columns
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int st = it % kPuStages;
+            const uint32_t rows = (uint32_t)min((int64_t)128, n_rows - t * 128);
+            mbar_wait_bounded(&sm->full[st], (it / kPuStages) & 1u);
+            unsigned char* stg = smem_raw + (size_t)st * kPuStageBytes;
+            if (i < (int)rows) {
+                double* xs = reinterpret_cast<double*>(stg) + i * 16 + 8 * h;
+                double* ps = reinterpret_cast<double*>(stg + kPuOffP) + i * 16 + 8 * h;
+                const float* zs = reinterpret_cast<const float*>(stg + kPuOffZ) + i * 16 + 8 * h;
+                // 16-byte chunks rotated by the row (bank groups), each chunk = 2 real slots or one complex slot
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int ch = (jj + i) & 3;
+                    const int col = 8 * h + 2 * ch;             // first real column of the chunk
+                    const int f0 = CPX ? (col >> 1) : col, f1 = CPX ? f0 : col + 1;
+                    if (!sm->xpend[f0] && !sm->xpend[f1]) continue;
+                    double2 xv = *reinterpret_cast<const double2*>(xs + 2 * ch);
+                    double2 pv = *reinterpret_cast<const double2*>(ps + 2 * ch);
+                    const float2 zf = *reinterpret_cast<const float2*>(zs + 2 * ch);
+                    if constexpr (CPX) {
+                        const double2 al = sm->alpha[f0], be = sm->beta[f0];
+                        xv = make_double2(xv.x + al.x * pv.x - al.y * pv.y, xv.y + al.x * pv.y + al.y * pv.x);
+                        if (sm->act[f0]) pv = make_double2((double)zf.x + be.x * pv.x - be.y * pv.y, (double)zf.y + be.x * pv.y + be.y * pv.x);
+                    } else {
+                        if (sm->xpend[f0]) {
+                            xv.x += sm->alpha[f0].x * pv.x;
+                            if (sm->act[f0]) pv.x = (double)zf.x + sm->beta[f0].x * pv.x;
+                        }
+                        if (sm->xpend[f1]) {
+                            xv.y += sm->alpha[f1].x * pv.y;
+                            if (sm->act[f1]) pv.y = (double)zf.y + sm->beta[f1].x * pv.y;
+                        }
+                    }
+                    *reinterpret_cast<double2*>(xs + 2 * ch) = xv;
+                    *reinterpret_cast<double2*>(ps + 2 * ch) = pv;
+                }
+            }
+            fence_proxy_async();   // the generic-proxy writes above before the bulk stores read the tile
+            __syncwarp();
+            asm volatile("barrier.sync 1, 256;" ::: "memory");
+            if (j == 0) {
+                bulk_s2g(x + t * 128 * 16, stg, rows * 128u);
+                bulk_s2g(p + t * 128 * 16, stg + kPuOffP, rows * 128u);
+                bulk_commit();
+                bulk_wait_read<0>();
+                mbar_arrive(&sm->empty[st]);
+            }
+        }
+        if (j == 0) bulk_wait<0>();
+    }
+}
+
+void pupdate_tiles(fdb_system* sys, SweepWork* w) {
+    static thread_local bool done[64] = {};
+    if (!done[sys->device & 63]) {
+        FDB_CUDA(cudaFuncSetAttribute(k_pupdate_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pupdate_smem()));
+        FDB_CUDA(cudaFuncSetAttribute(k_pupdate_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pupdate_smem()));
+        done[sys->device & 63] = true;
+    }
+    const int64_t n_tiles = (w->N + 127) / 128;
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, sys->num_sms));
+    if (w->real) k_pupdate_tiles<false><<<G, kPuThreads, pupdate_smem(), sys->stream>>>((double*)w->x.p, (double*)w->p.p, w->z32.p, w->N, n_tiles, w->sc.p);
+    else k_pupdate_tiles<true><<<G, kPuThreads, pupdate_smem(), sys->stream>>>((double*)w->x.p, (double*)w->p.p, w->z32.p, w->N, n_tiles, w->sc.p);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static size_t fused_smem(bool coarse = false) { return (size_t)(kStages + 2) * kChunkBytes + 2 * 8192 + sizeof(FusedSmem) + 64 + (coarse ? 2 * kPhiBytes : 0); }
@@ -1200,7 +1341,7 @@ void modal_precond_fused(fdb_system* sys, SweepWork* w, bool start) {
     const int G = modal_grid(sys);
     const bool coarse = sys->modal_compress;
     auto go = [&](auto kern) {
-        kern<<<G, kModalThreads, fused_smem(coarse), sys->stream>>>((double*)w->r.p, (const double*)w->q.p, sys->blk_inv16.p, w->z32.p, sys->modal_v.p,
+        kern<<<G, kFusedThreads, fused_smem(coarse), sys->stream>>>((double*)w->r.p, (const double*)w->q.p, sys->blk_inv16.p, w->z32.p, sys->modal_v.p,
                                                                    sys->mode_chunks, w->N, sys->n_tiles, w->sc.p, w->c_part.p, sys->modal_phi.p, w->tcv.p);
     };
     if (coarse) {

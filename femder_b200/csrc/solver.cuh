@@ -243,6 +243,7 @@ __device__ __forceinline__ void fin_start(Scalars* __restrict__ sc, int ff, cons
 // ---- modal.cu: the modal coarse correction inside a solver iteration ----
 constexpr int kModalCols = 16;   // real columns per row the tensor-core kernels are built for (16 real or 8 complex slots)
 void modal_prepare(fdb_system* sys, SweepWork* w);
+void pupdate_tiles(fdb_system* sys, SweepWork* w);   // K6b on 128-byte vector rows (16 real / 8 complex slots), bulk copies both ways
 void modal_set_compression(fdb_system* sys, bool on, bool force = false);   // force: even where the fit is poor (tests)
 int modal_modes_for(fdb_system* sys, double w2_max, double delta_hz);
 // parts: 1 c = V^T r ; 2 e = d c ; 4 z += V e, rho', ||r||^2, finalisation.  Tile-compressed modes: 1 c = C^T t (t from
