@@ -1915,6 +1915,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     const double lock_tol = (tuning && getenv("FDB_MODAL_LOCK_TOL")) ? atof(getenv("FDB_MODAL_LOCK_TOL")) : tol / 8.0;
     const bool f32_active = tuning && getenv("FDB_MODAL_F32_ACTIVE") && atoi(getenv("FDB_MODAL_F32_ACTIVE")) != 0;   // single precision for unlocked columns throughout
     const double first_mult = (tuning && getenv("FDB_MODAL_DEG1")) ? atof(getenv("FDB_MODAL_DEG1")) : 2.0;
+    const double late_mult = (tuning && getenv("FDB_MODAL_DEG_LATE")) ? atof(getenv("FDB_MODAL_DEG_LATE")) : 1.0;   // degree of the double-precision passes
     const double growth = (tuning && getenv("FDB_MODAL_GROWTH")) ? atof(getenv("FDB_MODAL_GROWTH")) : 0.05;
     DevBuf<double> dinv_mass;   // 1 / (mass_scale * Q_rr)
     dinv_mass.alloc(N);
@@ -1963,7 +1964,7 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
             const double a = a_low, b = b_up * (1.0 + order_t);
             // the first pass starts from noise: twice the degree there replaces the first two passes and the Rayleigh-Ritz step between
             // them (the amplification ratio between the lowest modes and those next to the cut stays inside single precision)
-            const double deg_mult = (outer == 0 && !have_ritz) ? first_mult : 1.0;
+            const double deg_mult = (outer == 0 && !have_ritz) ? first_mult : ((use_f32 && worst_last > f32_until) ? 1.0 : late_mult);
             const int deg = (int)std::max(12.0, std::min(160.0, std::ceil(3.0 * deg_mult * std::sqrt(b / a))));
             const double e = 0.5 * (b - a), c = 0.5 * (b + a);
             // two panels at once in single precision (see use_f32): T and Y hold the 32-column single-precision iterates

@@ -94,12 +94,12 @@ for name, kid, title in (("spmv_real16", "K5", "K5 fused multi-frequency SpMV k_
                          ("coarse_project", "K8a", "K8a k_modal_project on the coarse vector, batch 16 real, 747 modes: c = C^T t on tcgen05"),
                          ("coarse_expand", "K8c", "K8c k_modal_expand on the coarse vector, batch 16 real, 747 modes: u = C e on tcgen05"),
                          ("coarse_finish", "K8d", "K8d k_coarse_finish, batch 16 real: z += Phi u, rho' = r^T z, ||r||^2, iteration scalars"),
-                         ("pupdate_bj_real16", "K6b", "K6b k_pupdate_bj, batch 16 real: x += alpha p, p = z + beta p")):
+                         ("pupdate_tiles_real16", "K6b", "K6b k_pupdate_tiles, batch 16 real: x += alpha p, p = z + beta p (bulk copies both ways)")):
     v = capture(name, title)
     if v and kid:
         traffic[kid] = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
 if traffic:
-    traffic["source"] = f"profiles/{R}_spmv_real16.md, {R}_precond_fused.md, {R}_coarse_project.md, {R}_coarse_expand.md, {R}_coarse_finish.md, {R}_pupdate_bj_real16.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    traffic["source"] = f"profiles/{R}_spmv_real16.md, {R}_precond_fused.md, {R}_coarse_project.md, {R}_coarse_expand.md, {R}_coarse_finish.md, {R}_pupdate_tiles_real16.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     json.dump(traffic, open(os.path.join(OUT, "kernel_traffic.json"), "w"))
 for fn in ("bench_%s.json" % R,):
     src = os.path.join(GO, fn)
