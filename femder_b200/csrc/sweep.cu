@@ -613,7 +613,10 @@ k_spmv_blob(const uint16_t* __restrict__ sell_lidx, const double2* __restrict__ 
                 acc[j][0] = acc[j][1] = 0.0;
                 accf[j][0] = accf[j][1] = accf[j][2] = accf[j][3] = 0.f;
             }
-#pragma unroll 4
+            // a row's ~15 entries: the deeper unrolling keeps more of the (value, position, x row) shared-memory loads in flight per warp
+            // - the consumer warps' dependent chains, not bandwidth, were what the kernel waited on (127 -> 118 us at config 4)
+            // (the filter variants, with their heavier epilogue, are faster at the old depth)
+#pragma unroll (CHEB ? 4 : 32)
             for (int k = 0; k < width; ++k) {
                 const double2 m = thq[k * 8];
                 const int li = tlx[k * 8];
