@@ -16,13 +16,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libfemder_b200.so")
+# FDB_BUILD_TUNING=1: the A/B build (-DFDB_TUNING: the solver's and the modal set-up's tuning knobs become environment variables),
+# next to the shipped library, never instead of it: load it with FDB_LIB_PATH
+TUNING = os.environ.get("FDB_BUILD_TUNING") == "1"
+OBJ = os.path.join(HERE, "_ab", "build") if TUNING else os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "_ab", "libfemder_b200_tuning.so") if TUNING else os.path.join(HERE, "libfemder_b200.so")
 SOURCES = ["pattern.cu", "assemble.cu", "reorder.cu", "sweep.cu", "modal.cu", "comm.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "solver.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "femder_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"]
+FLAGS = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"] + (["-DFDB_TUNING"] if TUNING else [])
 
 
 def nvcc_path():

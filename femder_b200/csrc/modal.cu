@@ -1720,10 +1720,7 @@ void modal_set_compression(fdb_system* sys, bool on, bool force) {
         const bool verbose = getenv("FDB_MODAL_VERBOSE") != nullptr;
         if (verbose) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, sys->stream); }
         int n_iter = 6;
-        {
-            const char* tune = getenv("FDB_TUNING");
-            if (tune && tune[0] == '1' && getenv("FDB_TILE_ITERS")) n_iter = std::max(0, atoi(getenv("FDB_TILE_ITERS")));
-        }
+        if (const char* e = tune_env("FDB_TILE_ITERS")) n_iter = std::max(0, atoi(e));
         DevBuf<double> fit;
         fit.alloc((size_t)2 * n_modes);
         fit.zero(sys->stream);
@@ -1771,8 +1768,7 @@ void modal_finish(fdb_system* sys, int n_modes) {
     sys->have_fine_v = false;
     sys->have_coarse_v = false;
     {
-        const char* tune = getenv("FDB_TUNING");
-        const char* e = (tune && tune[0] == '1') ? getenv("FDB_MODAL_COMPRESS") : nullptr;
+        const char* e = tune_env("FDB_MODAL_COMPRESS");
         modal_set_compression(sys, !(e && atoi(e) == 0), e && atoi(e) == 2);
     }
     // How far each stored vector is from an eigenvector: k_modal_coef bounds 1 / (lambda - w^2) by it, so an inaccurate mode that a
@@ -1906,17 +1902,16 @@ void modal_compute(fdb_system* sys, double f_cut_hz, double f_acc_hz, int n_hint
     // instead of 16: half the passes.  Once the worst residual is below f32_until the filter runs in double precision: measured on the
     // 1M-DOF room, modes finished by a single-precision filter meet the same residual test but cost the sweep a third more
     // iterations (95 -> 129 mean); single precision for the first outer iterations only costs none.
-    const char* tune = getenv("FDB_TUNING");
-    const bool tuning = tune && tune[0] == '1';
-    bool use_f32 = !(tuning && getenv("FDB_MODAL_F64") && atoi(getenv("FDB_MODAL_F64")) != 0);
-    const double f32_until = (tuning && getenv("FDB_MODAL_F32_UNTIL")) ? atof(getenv("FDB_MODAL_F32_UNTIL")) : 1.0;
+    auto knob = [](const char* name, double dflt) { const char* e = tune_env(name); return e ? atof(e) : dflt; };
+    bool use_f32 = knob("FDB_MODAL_F64", 0.0) == 0.0;
+    const double f32_until = knob("FDB_MODAL_F32_UNTIL", 1.0);
     double worst_last = 1e300;   // the previous outer iteration's worst residual
-    const bool locking = tuning && getenv("FDB_MODAL_LOCK") && atoi(getenv("FDB_MODAL_LOCK")) != 0;   // off: measured below
-    const double lock_tol = (tuning && getenv("FDB_MODAL_LOCK_TOL")) ? atof(getenv("FDB_MODAL_LOCK_TOL")) : tol / 8.0;
-    const bool f32_active = tuning && getenv("FDB_MODAL_F32_ACTIVE") && atoi(getenv("FDB_MODAL_F32_ACTIVE")) != 0;   // single precision for unlocked columns throughout
-    const double first_mult = (tuning && getenv("FDB_MODAL_DEG1")) ? atof(getenv("FDB_MODAL_DEG1")) : 2.0;
-    const double late_mult = (tuning && getenv("FDB_MODAL_DEG_LATE")) ? atof(getenv("FDB_MODAL_DEG_LATE")) : 1.0;   // degree of the double-precision passes
-    const double growth = (tuning && getenv("FDB_MODAL_GROWTH")) ? atof(getenv("FDB_MODAL_GROWTH")) : 0.05;
+    const bool locking = knob("FDB_MODAL_LOCK", 0.0) != 0.0;   // off: measured below
+    const double lock_tol = knob("FDB_MODAL_LOCK_TOL", tol / 8.0);
+    const bool f32_active = knob("FDB_MODAL_F32_ACTIVE", 0.0) != 0.0;   // single precision for unlocked columns throughout
+    const double first_mult = knob("FDB_MODAL_DEG1", 2.0);
+    const double late_mult = knob("FDB_MODAL_DEG_LATE", 1.0);   // degree of the double-precision passes
+    const double growth = knob("FDB_MODAL_GROWTH", 0.05);
     DevBuf<double> dinv_mass;   // 1 / (mass_scale * Q_rr)
     dinv_mass.alloc(N);
     k_modal_dinv<<<grid_for(N, 256), 256, 0, s>>>(sys->diag_hq.p, mass_scale, N, dinv_mass.p);

@@ -1,5 +1,6 @@
 // Declarations shared by sweep.cu (K5/K6 kernels, sweep driver) and modal.cu (modal coarse correction, modal set-up).
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
 #include "../../include/femder_b200.h"
@@ -265,6 +266,15 @@ void modal_spmv(fdb_system* sys, SweepWork* w, const double* x, double* y);
 bool modal_spmv_cheb(fdb_system* sys, SweepWork* w, const double* x, const double* xold, double* out, const double* dinv, double c1, double c2,
                      double c3, bool f32 = false);
 void run_modal_apply(fdb_system* sys, const double* omega, int n_use, const double* r, double* z);
+
+// A/B knobs of the solver and of the modal set-up are environment variables that exist only in builds made with -DFDB_TUNING
+// (`FDB_BUILD_TUNING=1 python -m femder_b200.build` -> femder_b200/_ab/libfemder_b200_tuning.so, loaded with FDB_LIB_PATH): a
+// stray variable cannot change what the shipped library computes.
+#ifdef FDB_TUNING
+inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 // ---- comm.cu: the ranks that share one modal set-up (NCCL, opened lazily) ----
 struct RankComm;

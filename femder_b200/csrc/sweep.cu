@@ -1527,7 +1527,7 @@ struct Launch {
         if (w->precond >= 1) {
             if (which == 1) { if (bj_update<T>(sys, w, false)) return; }
             else if constexpr (std::is_same<T, double2>::value ? kBjCpx : kBjReal) {
-                static const bool old_k6b = getenv("FDB_TUNING") && getenv("FDB_OLD_K6B");
+                static const bool old_k6b = tune_env("FDB_OLD_K6B") != nullptr;   // A/B: the grid-stride K6b
                 if (!old_k6b && ((w->real && F == 16) || (!w->real && F == 8))) pupdate_tiles(sys, w);   // 128-byte rows
                 else k_pupdate_bj<T, F><<<egrid(w), kBlock, 0, sys->stream>>>(x, p, w->z32.p, ne, w->sc.p);
                 return;
