@@ -254,19 +254,63 @@ __global__ void __launch_bounds__(256) k_reduce_hq(const int32_t* __restrict__ c
     hq[z] = make_double2(h, q);
 }
 
-void assemble_volume(fdb_system* sys, double rho0, double c0) {
-    FDB_REQUIRE(sys->have_pattern && sys->vol.n_elem > 0 && sys->vol.conn.p, "fdb_set_volume_mesh must be called first");
-    FDB_REQUIRE(rho0 != 0.0 && c0 != 0.0, "rho0 and c0 must be non-zero");
-    sys->rho0 = rho0;   // kept for Weyl's mode-count estimate (modal.cu)
-    sys->c0 = c0;
+// Tet4 without the element-matrix round trip: one thread per nnz recomputes each of its contributions (element e, entry (a, b))
+// from the element's four node coordinates - the same expressions as k_tet4_elem, added in the same ascending (element, ab)
+// order, so the values are those of the two-kernel path - instead of reading them back from 2 x 16 E doubles that another
+// kernel wrote (1.5 GB out and in again at config 4).  Connectivity and coordinates of neighbouring nnz are the same few
+// elements: they come out of L1 / L2.
+__global__ void __launch_bounds__(256) k_assemble_tet4_direct(const int32_t* __restrict__ c_ptr, const int32_t* __restrict__ c_src,
+                                                               const int4* __restrict__ conn, const double* __restrict__ nos, int64_t nnz,
+                                                               double inv_rho, double inv_rhoc2, double2* __restrict__ hq) {
+    int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= nnz) return;
+    double h = 0, q = 0;
+    const int32_t kb = c_ptr[z], ke = c_ptr[z + 1];
+    for (int32_t k = kb; k < ke; ++k) {
+        const int32_t key = c_src[k];
+        const int e = key >> 4, a = (key >> 2) & 3, b = key & 3;
+        const int4 c = __ldg(&conn[e]);
+        const int id[4] = {c.x, c.y, c.z, c.w};
+        double X[4][3];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) X[n][d] = __ldg(&nos[(int64_t)id[n] * 3 + d]);
+        double J[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) J[i][d] = X[i + 1][d] - X[0][d];
+        const double det = det3(J);
+        double Ji[3][3];
+        inv3(J, det, Ji);
+        double Ba[3], Bb[3];   // columns a and b of B = J^-1 GNi
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double b0 = -(Ji[i][0] + Ji[i][1] + Ji[i][2]);
+            Ba[i] = a == 0 ? b0 : (a == 1 ? Ji[i][0] : (a == 2 ? Ji[i][1] : Ji[i][2]));
+            Bb[i] = b == 0 ? b0 : (b == 1 ? Ji[i][0] : (b == 2 ? Ji[i][1] : Ji[i][2]));
+        }
+        const double btb = Ba[0] * Bb[0] + Ba[1] * Bb[1] + Ba[2] * Bb[2];
+        const double arg = btb * det;
+        h += inv_rho * arg / 6;
+        q += c_tet4.S[a * 4 + b] * det * inv_rhoc2 / 24;
+    }
+    hq[z] = make_double2(h, q);
+}
+
+// the element matrices themselves (fdb_get_element_matrices; the Tet10 assembly): K1 / K2
+void element_matrices(fdb_system* sys) {
+    FDB_REQUIRE(sys->have_pattern && sys->vol.n_elem > 0 && sys->rho0 != 0.0 && sys->c0 != 0.0, "fdb_assemble_volume must be called first");
+    if (sys->have_elem_matrices) return;
     upload_constants();
     Pattern& P = sys->vol;
     const int nper = P.nper, n2 = nper * nper;
     const int64_t E = P.n_elem;
     sys->He.alloc((size_t)n2 * E);
     sys->Qe.alloc((size_t)n2 * E);
-    const double inv_rho = 1.0 / rho0;
-    const double inv_rhoc2 = 1.0 / (rho0 * (c0 * c0));
+    const double inv_rho = 1.0 / sys->rho0;
+    const double inv_rhoc2 = 1.0 / (sys->rho0 * (sys->c0 * sys->c0));
     if (nper == 4) {
         k_tet4_elem<<<grid_for(E, 128), 128, 0, sys->stream>>>((const int4*)P.conn.p, sys->nos.p, E, inv_rho, inv_rhoc2,
                                                                sys->He.p, sys->Qe.p);
@@ -274,11 +318,32 @@ void assemble_volume(fdb_system* sys, double rho0, double c0) {
         dim3 grid(grid_for(E, kT10Tile), 10);
         k_tet10_elem<<<grid, kT10Tile, 0, sys->stream>>>(P.conn.p, sys->nos.p, E, inv_rho, inv_rhoc2, sys->He.p, sys->Qe.p);
     }
+    FDB_CUDA(cudaGetLastError());
+    sys->have_elem_matrices = true;
+}
+
+void assemble_volume(fdb_system* sys, double rho0, double c0) {
+    FDB_REQUIRE(sys->have_pattern && sys->vol.n_elem > 0 && sys->vol.conn.p, "fdb_set_volume_mesh must be called first");
+    FDB_REQUIRE(rho0 != 0.0 && c0 != 0.0, "rho0 and c0 must be non-zero");
+    sys->rho0 = rho0;   // kept for Weyl's mode-count estimate (modal.cu)
+    sys->c0 = c0;
+    upload_constants();
+    Pattern& P = sys->vol;
+    const int nper = P.nper;
+    const int64_t E = P.n_elem;
+    sys->have_elem_matrices = false;   // of another fluid or geometry
     sys->hq.alloc(P.nnz);
-    if (nper == 4)
-        k_reduce_hq<16><<<grid_for(P.nnz, 256), 256, 0, sys->stream>>>(P.c_ptr.p, P.c_src.p, sys->He.p, sys->Qe.p, E, P.nnz, sys->hq.p);
-    else
+    if (nper == 4) {
+        // Tet4: straight from the coordinates (the element matrices are formed only if somebody asks for them)
+        sys->He.release();
+        sys->Qe.release();
+        k_assemble_tet4_direct<<<grid_for(P.nnz, 256), 256, 0, sys->stream>>>(P.c_ptr.p, P.c_src.p, (const int4*)P.conn.p, sys->nos.p, P.nnz,
+                                                                             1.0 / rho0, 1.0 / (rho0 * (c0 * c0)), sys->hq.p);
+    } else {
+        // Tet10: 4 Gauss points x 10 nodes per entry are too much to recompute per contribution
+        element_matrices(sys);
         k_reduce_hq<100><<<grid_for(P.nnz, 256), 256, 0, sys->stream>>>(P.c_ptr.p, P.c_src.p, sys->He.p, sys->Qe.p, E, P.nnz, sys->hq.p);
+    }
     FDB_CUDA(cudaGetLastError());
     sys->have_hq = true;
     extract_diagonal(sys);

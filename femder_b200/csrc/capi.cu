@@ -139,6 +139,7 @@ int fdb_set_volume_mesh(fdb_system* sys, int64_t n_nodes, const double* nos, int
     FDB_CUDA(cudaMemcpyAsync(sys->vol.conn.p, conn, (size_t)n_elem * nper * sizeof(int32_t), cudaMemcpyDefault, sys->stream));
     sys->have_pattern = false;
     sys->have_hq = false;
+    sys->have_elem_matrices = false;
     sys->have_order = false;
     sys->have_overlay = false;   // stored in the internal order of the previous pattern
     fdb::build_pattern(sys->vol, n_nodes, n_elem, nper, sys->vol.conn.p, sys->stream);
@@ -240,8 +241,9 @@ int fdb_set_HQ(fdb_system* sys, const double* H_vals, const double* Q_vals) {
 
 int fdb_get_element_matrices(fdb_system* sys, double* He, double* Qe) {
     FDB_API_BEGIN
-    FDB_SYS(sys);
-    FDB_REQUIRE(sys->He.p && sys->Qe.p && He && Qe, "no element matrices (call fdb_assemble_volume)");
+    FDB_SYS_MUT(sys);
+    FDB_REQUIRE(sys->have_hq && sys->vol.n_elem > 0 && He && Qe, "no element matrices (call fdb_assemble_volume)");
+    fdb::element_matrices(sys);
     FDB_CUDA(cudaMemcpyAsync(He, sys->He.p, sys->He.bytes(), cudaMemcpyDefault, sys->stream));
     FDB_CUDA(cudaMemcpyAsync(Qe, sys->Qe.p, sys->Qe.bytes(), cudaMemcpyDefault, sys->stream));
     FDB_CUDA(cudaStreamSynchronize(sys->stream));

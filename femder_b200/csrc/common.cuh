@@ -108,7 +108,8 @@ struct fdb_system {
     fdb::DevBuf<double> nos;  // [n_nodes][3]
     fdb::Pattern vol;
     bool have_pattern = false;
-    fdb::DevBuf<double> He, Qe;      // [nper*nper][n_elem]
+    fdb::DevBuf<double> He, Qe;      // [nper*nper][n_elem]: formed on request (fdb_get_element_matrices) and for the Tet10 assembly
+    bool have_elem_matrices = false;
     fdb::DevBuf<double2> hq;         // [nnz] (H, Q) interleaved: the layout the SpMV streams
     bool have_hq = false;
     fdb::DevBuf<double2> diag_hq;    // [n_nodes] diagonal of H and Q
@@ -196,6 +197,7 @@ void check_external_pattern(const int32_t* indptr, const int32_t* indices, int64
 
 // ---- assemble.cu ----
 void assemble_volume(fdb_system* sys, double rho0, double c0);
+void element_matrices(fdb_system* sys);
 void heron_areas(fdb_system* sys);
 void assemble_surface(fdb_system* sys);
 void build_overlay(fdb_system* sys);
