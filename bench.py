@@ -231,12 +231,20 @@ def run_ours(args):
         near = np.minimum(np.abs(lam_modes[k] - w2), np.abs(lam_modes[k - 1] - w2)) / w2
         return f[sharding.deal_by_cost(np.where(near < 1e-3, 10.0, 1.0) + f / f.max(), rank, world)]
 
+    # N > 1 on one node: the ranks share ONE queue of the step's frequencies (a counter in shared memory claimed with atomic
+    # adds inside the sweep, one counter per step) - what FEM3D.compute() does; otherwise static dealing (my_share)
+    queue = sharding.counters() if (world > 1 and sharding.same_node() and not args.static_dealing) else None
+
     def step_resident(i):
-        f = my_share(step_frequencies(i))
+        f = step_frequencies(i) if queue is not None else my_share(step_frequencies(i))
         _, pR, st = sysm.sweep(2 * np.pi * f, np.zeros((len(group_ids), len(f)), dtype=np.complex128), [src_node], [1e-4],
                                rcv_nodes, rcv_w, want_pN=False, tol=args.tol, max_iter=args.max_iter,
                                batch="auto" if args.precond == "modal" else args.batch, check_every=args.check_every,
-                               precond=args.precond, modal_delta=delta)
+                               precond=args.precond, modal_delta=delta,
+                               shared_next=None if queue is None else queue.address(queue.fresh()))
+        if queue is not None:
+            st.iters, st.relres = st.iters[st.solved], st.relres[st.solved]
+            return int(st.solved.sum()), st, pR
         return len(f), st, pR
 
     def barrier():
@@ -310,7 +318,7 @@ def run_ours(args):
         # read back: Heron areas, receiver pressures, iteration counts, residuals (H, Q, A stay on the GPU until asked for)
         d2h_holder[0] = obj.areas.nbytes // 2 + obj.pR.nbytes + obj.iters.nbytes + obj.relres.nbytes + (obj.pN.nbytes if keep_pN else 0)
         st = obj.stats
-        return (len(obj.freq) if world == 1 else len(my_share(obj.freq))), st, obj.pR
+        return (len(obj.freq) if world == 1 else int(np.asarray(st.iters).size)), st, obj.pR   # st covers what THIS rank solved
 
     e2e = None
     e2e_pN = None
@@ -447,7 +455,9 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD,
                            "step": f"one sweep call over the {n_step} frequencies 20..500 Hz every {STEP_STRIDE} Hz (COCG to a TRUE relative residual of "
                                    f"{args.tol:g}, 16 real solver slots with continuous refill, preconditioner {args.precond})",
-                           "parallelism": f"frequency-sharded x{world}: the same sweep split over the ranks, no collective on the solve path",
+                           "parallelism": f"frequency-sharded x{world}: the same sweep split over the ranks"
+                                          + (" (one common queue in shared memory, claimed with atomic adds)" if queue is not None else "")
+                                          + ", no collective on the solve path",
                            "l2": "working set per step (matrix 0.3 GB + block inverses 0.26 GB + 5 vectors x 128 MB + mode coefficient tiles 0.2 GB) > 126 MB L2 (no flush needed)",
                            "N": int(grid.NumNosC), "nnz": int(sysm.nnz), "assembly_seconds_once": t_setup,
                            "assembly_kernel": {"what": "fdb_assemble_volume (Tet4: one kernel, every nnz recomputes its contributions from the "
@@ -492,6 +502,7 @@ def main():
     ap.add_argument("--shape", default=",".join(str(s) for s in SHAPE))
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--cpu-sizes", type=int, default=3, help="rungs of the CPU ladder the reference arm measures (21 735 / 47 250 / 94 424 DOF)")
+    ap.add_argument("--static-dealing", action="store_true", help="N > 1: deal the frequencies to the ranks up front instead of sharing one queue")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pn", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -26,13 +26,14 @@ class SweepParams(C.Structure):
                 ("batch", C.c_int32), ("check_every", C.c_int32), ("warm_start", C.c_int32), ("precond", C.c_int32),
                 ("arithmetic", C.c_int32), ("n_rhs_vec", C.c_int64), ("rhs_ptr", C.c_void_p), ("rhs_nodes", C.c_void_p),
                 ("rhs_vals", C.c_void_p), ("rhs_coef", C.c_void_p), ("n_rcv", C.c_int64), ("rcv_nodes", C.c_void_p), ("rcv_w", C.c_void_p),
-                ("modal_delta_hz", C.c_double)]
+                ("modal_delta_hz", C.c_double), ("shared_next", C.c_void_p)]
 
 
 class SweepResult(C.Structure):
     _fields_ = [("pR", C.c_void_p), ("pN", C.c_void_p), ("iters", C.c_void_p), ("relres", C.c_void_p),
                 ("seconds", C.c_double), ("n_spmv", C.c_int64), ("n_kernels", C.c_int64),
-                ("n_unconverged", C.c_int32), ("real_arithmetic", C.c_int32), ("n_resumed", C.c_int32), ("precond_used", C.c_int32)]
+                ("n_unconverged", C.c_int32), ("real_arithmetic", C.c_int32), ("n_resumed", C.c_int32), ("precond_used", C.c_int32),
+                ("solved", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/femder_b200.h declares

@@ -2017,14 +2017,23 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         return omega[fa] > omega[fb];
     });
 
+    // the next system of the queue: this call's own, or the one the processes of a node share (fdb_sweep_params.shared_next)
+    bool queue_dry = false;
+    auto claim = [&]() -> int64_t {
+        if (queue_dry) return -1;
+        const int64_t k = prm->shared_next ? __atomic_fetch_add(prm->shared_next, (int64_t)1, __ATOMIC_RELAXED) : next++;
+        if (k >= n_sys) { queue_dry = true; return -1; }
+        return order[k];
+    };
+    if (res->solved) memset(res->solved, 0, (size_t)n_sys);
     auto assign = [&](int slot) {
-        if (next >= n_sys) {
+        const int64_t si = claim();
+        if (si < 0) {
             slot_freq[slot] = -1;
             h.active[slot] = 0;
             h.reset[slot] = 0;
             return false;
         }
-        const int64_t si = order[next++];
         const int64_t fi = si % nf, st = si / nf;
         for (int g = 0; g < ng; ++g) {
             mu_f[2 * g] = mu[((size_t)g * nf + fi) * 2];
@@ -2158,6 +2167,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
                 any_reset = true;
                 continue;
             }
+            if (res->solved) res->solved[fi] = 1;
             if (res->iters) res->iters[fi] = h.iters[f];
             if (res->relres) res->relres[fi] = rel;
             if (!(rel <= prm->tol)) ++n_unconv;
@@ -2176,7 +2186,7 @@ void run_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* r
         constexpr bool no_narrow = false;
 #endif
         // (the modal correction's tensor-core kernels are built for 16 real columns: its batches stay as they are)
-        if (next >= n_sys && n_busy > 0 && !any_reset && !no_narrow && !use_modal) {
+        if (queue_dry && n_busy > 0 && !any_reset && !no_narrow && !use_modal) {
             int F2 = F;
             while (F2 / 2 >= 1 && F2 / 2 >= n_busy) F2 /= 2;
             if (F2 < F) {

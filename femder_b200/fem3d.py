@@ -414,7 +414,14 @@ class FEM3D:
         nf = len(w)
         precond = self._prepare_preconditioner(sys, nf)
         rank, world, _ = sharding.dist_info() if self.shard else (0, 1, 0)
-        if world > 1 and precond == "modal":
+        shared = None
+        if world > 1 and not keep_pN and sharding.same_node():
+            # one common queue for the ranks of the node (a counter in shared memory, claimed with atomic adds inside the sweep):
+            # a rank that runs out of work takes the next frequency instead of idling.  (With keep_pN every rank would need the
+            # whole (n_freq, N) array: static dealing then.)
+            shared = sharding.counters()
+            owned = np.arange(nf, dtype=np.int64)
+        elif world > 1 and precond == "modal":
             # iterations are flat in frequency with the modal correction, except next to a resonance (up to several times the usual
             # count): deal those first so every rank gets its share of them, then the rest by frequency
             lam, _ = sys.modal_get(vectors=False)
@@ -428,7 +435,12 @@ class FEM3D:
         pN, pR, stats = sys.sweep(w[owned], mu[:, owned], src_nodes, src_q, rcv_nodes, rcv_w, want_pN=keep_pN, pN_out=pN_out,
                                   tol=self.tol, max_iter=self.max_iter, batch=self.batch if precond != "modal" else "auto",
                                   check_every=self.check_every, warm_start=self.warm_start, precond=precond, rhs_vecs=rhs_vecs,
-                                  rhs_coef=None if rhs_coef is None else rhs_coef[:, owned], modal_delta=self.modal_delta)
+                                  rhs_coef=None if rhs_coef is None else rhs_coef[:, owned], modal_delta=self.modal_delta,
+                                  shared_next=None if shared is None else shared.address(shared.fresh()))
+        if shared is not None:
+            owned = np.flatnonzero(stats.solved)
+            pR = None if pR is None else pR[owned]
+            stats.iters, stats.relres = stats.iters[owned], stats.relres[owned]
         self.stats = stats
         if precond == "modal" and stats.n_unconverged:
             # Safety net: what the modal path handed back above tol (a mesh too coarse for its modes near the top of the sweep, an

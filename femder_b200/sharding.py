@@ -43,6 +43,79 @@ def dist_info():
     return 0, 1, 0
 
 
+def same_node(group=None):
+    """True when every rank of the group runs on this node (what a shared-memory work queue needs)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    return world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", "0")) == dist.get_world_size()
+
+
+class SharedCounters:
+    """``n`` int64 counters in POSIX shared memory (a file under /dev/shm mapped by every rank of the node): the common work queue
+    of a sharded sweep.  ``System.sweep(..., shared_next=counters.address(k))`` claims systems with atomic fetch-and-adds on
+    counter k, so a rank that runs out of work takes the next system instead of idling - still no collective on the solve path.
+    Collective to create; the file is unlinked as soon as every rank has mapped it."""
+
+    def __init__(self, n=256, group=None):
+        import mmap
+        import uuid
+
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        box = [None]
+        if rank == 0:
+            box[0] = f"/dev/shm/femder_b200_{os.getpid()}_{uuid.uuid4().hex}"
+            with open(box[0], "wb") as f:
+                f.write(b"\0" * (8 * n))
+        _broadcast(box, group)
+        self._f = open(box[0], "r+b")
+        self._map = mmap.mmap(self._f.fileno(), 8 * n)
+        self.values = np.frombuffer(self._map, dtype=np.int64)
+        import ctypes
+        self._base = ctypes.addressof(ctypes.c_char.from_buffer(self._map))
+        self.n = n
+        self._next = 0
+        self._group = group
+        dist.barrier(group)
+        if rank == 0:
+            os.unlink(box[0])
+
+    def address(self, k):
+        return self._base + 8 * int(k)
+
+    def fresh(self):
+        """Index of a zeroed counter, the same on every rank (collective: all ranks call it the same number of times)."""
+        import torch.distributed as dist
+        k = self._next % self.n
+        self._next += 1
+        if self._next > self.n:      # wrapped round: somebody may still be reading the old value
+            dist.barrier(self._group)
+            if dist.get_rank(self._group) == 0:
+                self.values[k] = 0
+            dist.barrier(self._group)
+        return k
+
+
+_COUNTERS = None
+
+
+def counters():
+    """The process group's counters (created collectively on first use)."""
+    global _COUNTERS
+    if _COUNTERS is None:
+        _COUNTERS = SharedCounters()
+    return _COUNTERS
+
+
+def _broadcast(box, group=None):
+    import torch
+    import torch.distributed as dist
+    kw = {}
+    if dist.get_backend(group) == "nccl":
+        kw["device"] = torch.device("cuda", torch.cuda.current_device())
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group, **kw)
+
+
 def share_modal_setup(system, group=None):
     """Make the ranks of the process group one communicator of ``system``'s library (NCCL, created by the library itself from an id
     rank 0 makes and torch.distributed hands round): ``System.modal_compute`` then deals the set-up's columns to the ranks.

@@ -338,7 +338,7 @@ class System:
     # ---- sweep --------------------------------------------------------------------------------
     def sweep(self, omega, mu, src_nodes, src_q, rcv_nodes=None, rcv_w=None, want_pN=True, tol=1e-8,
               max_iter=200000, batch=8, check_every=32, warm_start=False, pN_out=None, force_complex=False, rhs_vecs=None,
-              rhs_coef=None, src_sets=None, precond="block", modal_delta=0.0):
+              rhs_coef=None, src_sets=None, precond="block", modal_delta=0.0, shared_next=None):
         """Solve ``(H - w^2 Q + 1j w sum_g mu_g A_g) p = -1j w q`` for every w in ``omega``.
 
         mu: (n_groups, n_freq) complex.  ``rhs_vecs`` (list of real length-N vectors, dense or scipy sparse) with
@@ -437,6 +437,11 @@ class System:
         res.pR = ptr(pR)
         res.iters = ptr(iters)
         res.relres = ptr(relres)
+        # shared_next: address of an int64 counter shared by the processes of this node that were given the same list
+        # (sharding.SharedCounters): systems are claimed from one common queue; stats.solved marks the ones solved here
+        solved = np.zeros(n_sets * nf, dtype=np.uint8)
+        res.solved = ptr(solved)
+        prm.shared_next = C.c_void_p(int(shared_next)) if shared_next else None
         check(self._lib.fdb_sweep(self._h, C.byref(prm), C.byref(res)))
         if src_sets is not None:
             if pN is not None and pN_out is None:
@@ -446,6 +451,7 @@ class System:
             iters, relres = iters.reshape(n_sets, nf), relres.reshape(n_sets, nf)
         st = SweepStats(iters, relres, res.seconds, res.n_spmv, res.n_kernels, res.n_unconverged, res.n_resumed, res.precond_used)
         st.real_arithmetic = bool(res.real_arithmetic)
+        st.solved = solved.astype(bool).reshape(iters.shape)
         return pN, pR, st
 
     def spmv(self, omega, mu, x):

@@ -127,9 +127,14 @@ typedef struct fdb_sweep_params {
     const int32_t* rcv_nodes; /* [n_rcv][4] (unused slots: weight 0, any valid node) */
     const double* rcv_w;      /* [n_rcv][4] */
     double modal_delta_hz;    /* precond 2: a batch applies the modes below sqrt(f_max^2 + modal_delta_hz^2); 0 = default (300 Hz) */
+    int64_t* shared_next;     /* NULL: this call solves every system it is given.  Otherwise a HOST counter shared by the processes
+                               * that were all given the SAME list (one per GPU of a node; e.g. in POSIX shared memory, zero before
+                               * the first of them starts): systems are claimed one at a time, in the sweep's own dispatch order,
+                               * with an atomic fetch-and-add, so a process that runs out of work takes the next system of the
+                               * common queue instead of idling; fdb_sweep_result.solved says which ones this call solved */
 } fdb_sweep_params;
-/* Multi-GPU: frequencies are independent, so each rank creates its own system on its own
- * GPU and passes only the frequencies it owns; there is no collective on this path. */
+/* Multi-GPU: frequencies are independent, so each rank creates its own system on its own GPU and either passes
+ * only the frequencies it owns or shares one queue with the other ranks (shared_next); there is no collective on this path. */
 
 typedef struct fdb_sweep_result {
     double* pR;       /* [n_sets][n_freq][n_rcv] complex; may be NULL */
@@ -143,6 +148,7 @@ typedef struct fdb_sweep_result {
     int32_t real_arithmetic;  /* 1 if the sweep ran in real arithmetic (G real, b imaginary: p = 1j*u) */
     int32_t n_resumed;        /* restarts from the true residual (see tol) */
     int32_t precond_used;     /* the preconditioner the sweep actually ran: 0, 1 or 2 as in fdb_sweep_params.precond */
+    uint8_t* solved;  /* [n_sets][n_freq] 1 where this call solved the system (all of them without shared_next); may be NULL */
 } fdb_sweep_result;
 
 int fdb_sweep(fdb_system* sys, const fdb_sweep_params* prm, fdb_sweep_result* res);

@@ -112,3 +112,60 @@ def test_deal_by_cost_spreads_the_expensive_items():
         seen.extend(idx.tolist())
     assert sorted(seen) == list(range(37))
     assert np.array_equal(sharding.deal_by_cost(cost, 0, 1), np.arange(37))
+
+
+_QUEUE_WORKER = r'''
+import ctypes, os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from femder_b200 import sharding
+dist.init_process_group("gloo")
+rank, world, _ = sharding.dist_info()
+assert sharding.same_node()
+q = sharding.counters()
+assert q is sharding.counters()
+k = q.fresh()
+assert k == 0 and q.values[k] == 0
+# every rank claims items from the common queue the way fdb_sweep does (atomic fetch-and-add on the shared counter)
+import fcntl
+n_items, mine = 1000, []
+add = ctypes.c_int64.from_address(q.address(k))
+while True:
+    # the library claims with __atomic_fetch_add; two Python processes emulate the atomicity with an advisory file lock
+    with open(sys.argv[2], "a") as lf:
+        fcntl.flock(lf, fcntl.LOCK_EX)
+        i = add.value
+        add.value = i + 1
+        fcntl.flock(lf, fcntl.LOCK_UN)
+    if i >= n_items:
+        break
+    mine.append(i)
+parts = [None] * world
+dist.all_gather_object(parts, mine)
+allc = sorted(sum(parts, []))
+assert allc == list(range(n_items)), (len(allc), rank)          # every item exactly once
+assert q.values[k] >= n_items
+k2 = q.fresh()
+assert k2 == 1 and q.values[k2] == 0
+# the rows of a dynamically claimed sweep are gathered like statically dealt ones
+rows = np.asarray(mine, dtype=np.float64)[:, None] * (1 + 1j)
+full = sharding.gather_rows(rows, np.asarray(mine, dtype=np.int64), n_items)
+assert np.array_equal(full[:, 0], np.arange(n_items) * (1 + 1j))
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write(f"rank {rank} ok {len(mine)}\n"); sys.stdout.flush()
+'''
+
+
+def test_shared_queue_world_size_2_gloo(tmp_path):
+    """The common work queue of a sharded sweep (sharding.SharedCounters: a counter in POSIX shared memory that fdb_sweep claims
+    systems from): both ranks see the same memory, every item is claimed exactly once, counters are handed out in step."""
+    script = tmp_path / "queue_worker.py"
+    script.write_text(_QUEUE_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29618", str(script), ROOT, str(tmp_path / "lock")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
