@@ -19,9 +19,10 @@ for t in range(2, 8):
     BC.rigid(t)
 S = rs.Source(coord=grid.nos[grid.closest_node([1.0, 1.0, 1.2])], q=[1e-4])
 R = rs.Receiver(coord=grid.nos[grid.closest_node([2.0, 3.0, 1.25])])
-obj = fd.FEM3D(grid, S, R, AP, AC, BC)
+KW = dict(modal_delta=float(os.environ["FDB_SETUP_DELTA"])) if "FDB_SETUP_DELTA" in os.environ else {}
+obj = fd.FEM3D(grid, S, R, AP, AC, BC, **KW)
 obj.compute(timeit=False, keep_pN=False)          # warm-up: library load, handles, graphs
-obj2 = fd.FEM3D(grid, S, R, AP, AC, BC)
+obj2 = fd.FEM3D(grid, S, R, AP, AC, BC, **KW)
 obj2._sys = obj._sys
 pr = cProfile.Profile()
 t = time.perf_counter()
