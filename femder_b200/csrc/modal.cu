@@ -12,13 +12,17 @@
 // with its spectrum bounded away from zero (tests/research/modal_deflation_prototype.py: 1879 -> 37 iterations at 300 Hz on
 // the config-1 mesh; bfloat16 V and modes of the lumped-mass problem do as well as exact FP64 modes).
 //
-// The two products per iteration are the ONE dense contraction of the hot path, and they run on tcgen05:
+// The products with V are the dense contractions of the hot path, and they run on tcgen05:
 //   projection  c = V^T r     (k_modal_project)   D[128 modes x 32] += A[128 modes x 16 nodes] B[16 nodes x 32]
 //   expansion   z += V e      (k_modal_expand)    D[128 nodes x 32] += A[128 nodes x 16 modes] B[16 modes x 32]
 // Both read the SAME bytes of V: a tile of 128 nodes x 128 modes is stored as 8 x 8 bf16 core matrices, the expansion reads
 // it K-major, the projection MN-major (tc.cuh).  The 32 operand columns are the batch's 16 real columns (16 real slots or
 // 8 complex ones) split into bf16 (hi, lo) pairs: 16 mantissa bits of the FP32 value, accumulated in FP32 in TMEM.
-// Both kernels are bound by the HBM stream of V (2 bytes per node and mode): the tensor pipe is ~10 % busy.
+// By default V is not streamed at all: per 128-node tile V_t ~ Phi_t C_t with 16 basis functions ("Tile-compressed modes"
+// below), t = Phi^T r is one more MMA group inside the fused K6a, the two kernels above work on the coefficient tiles C and a
+// vector of 16 numbers per tile, and z += Phi u is k_coarse_finish.  Everything here is bound by its HBM stream: the tensor pipe
+// is ~5 % busy.  This file also holds K6b (k_pupdate_tiles), the modal set-up (Chebyshev-filtered subspace iteration) and the
+// tile-basis kernel.
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 #include "solver.cuh"

@@ -444,3 +444,31 @@ def test_config4_spmv_full_size(gpu_lib):
     lhs = np.einsum("nf,nf->f", z, y)      # z^T G x (unconjugated)
     rhs = np.einsum("nf,nf->f", x, yz)     # x^T G z
     assert np.abs(lhs - rhs).max() / np.abs(lhs).max() < 1e-11
+
+
+def test_shared_queue_single_process(gpu_lib):
+    """fdb_sweep_params.shared_next: systems are claimed from a caller-owned counter (the common queue of the ranks of a node).
+    One process alone claims them all: same solutions as without the queue, every system marked solved, the counter past the end;
+    a counter that starts beyond the list leaves nothing to solve."""
+    import ctypes
+    import femder_b200 as fd
+    grid = fd.shoebox_tet4(6, 7, 5, jitter=0.2)
+    s = fd.System(0)
+    s.set_volume_mesh(grid.nos, grid.elem_vol)
+    s.assemble_volume(1.21, 343.0)
+    freq = np.linspace(40.0, 160.0, 11)
+    w = 2 * np.pi * freq
+    mu = np.zeros((0, len(w)))
+    pN0, _, st0 = s.sweep(w, mu, [5], [1e-4], tol=1e-10, batch=4)
+    counter = np.zeros(2, dtype=np.int64)
+    addr = counter.ctypes.data
+    pN1, _, st1 = s.sweep(w, mu, [5], [1e-4], tol=1e-10, batch=4, shared_next=addr)
+    assert st0.solved.all() and st1.solved.all() and counter[0] >= len(w) and counter[1] == 0
+    assert np.abs(pN1 - pN0).max() <= 1e-9 * np.abs(pN0).max()
+    counter[0] = 7                                   # somebody else took the first seven systems of the dispatch order
+    pN2, _, st2 = s.sweep(w, mu, [5], [1e-4], tol=1e-10, batch=4, shared_next=addr)
+    assert st2.solved.sum() == len(w) - 7 and st2.n_unconverged == 0
+    assert np.abs(pN2[st2.solved] - pN0[st2.solved]).max() <= 1e-9 * np.abs(pN0).max()
+    counter[0] = 100
+    _, _, st3 = s.sweep(w, mu, [5], [1e-4], tol=1e-10, batch=4, shared_next=addr)
+    assert not st3.solved.any()
