@@ -1787,6 +1787,10 @@ void modal_finish(fdb_system* sys, int n_modes) {
     DevBuf<double> HX, QX;
     std::vector<double> res;
     modal_residuals(sys, w, sys->modal_x.p, sys->modal_lam_host, n_modes, modal_qscale(b_up), HX, QX, res);
+    if (const char* e = tune_env("FDB_MODAL_FLOOR")) {   // A/B: scale of the bound k_modal_coef keeps |lambda - w^2| above (res^2 / lambda)
+        const double f = std::sqrt(std::max(0.0, atof(e)));
+        for (auto& r : res) r *= f;
+    }
     sys->modal_res_host = res;
     sys->modal_res.alloc(n_modes);
     FDB_CUDA(cudaMemcpyAsync(sys->modal_res.p, res.data(), n_modes * sizeof(double), cudaMemcpyHostToDevice, sys->stream));
